@@ -1,0 +1,1117 @@
+// obca_solver.cuh -- one OBCA parking NLP solved by one CTA (thread k <-> stage k).
+//
+// Replaces, for the batched path, what the reference does with JuMP + Ipopt + MUMPS inside
+// ParkingSignedDist.jl:41-43,213-240 / ParkingDist.jl:41-43,215-241:
+//   K1  stage_eval     fused evaluation of objective, constraints, Jacobian/Hessian blocks and KKT-error pieces,
+//                      with in-register condensation of every OBCA block onto the stage pose
+//   K3  kkt_solve      stage-banded KKT solve (Riccati sweep = block LDL' in time order) + inertia test
+//   K4  recover / merit / update   step recovery, fraction-to-the-boundary, filter line search, iterate update
+// The algorithm is the published Ipopt algorithm (Waechter & Biegler 2006): monotone barrier update, inertia
+// correction by delta_w escalation, filter line search (oracle/ipm_ref.py is the independent restatement).
+//
+// Execution model: OBCA_FOR_STAGES bodies run once per stage (device: thread k of the CTA; host emulation: a loop),
+// OBCA_SERIAL bodies run once per problem (device: thread 0).  Everything that lives across phases is in the
+// per-CTA workspace W (global memory, L2 resident) or in the ProbState struct (shared memory).
+#pragma once
+#include "obca_common.cuh"
+#include "obca_local.cuh"
+#include "obca_stage.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define OBCA_FOR_STAGES(k, ns) for (int k = threadIdx.x; k < (ns); k += blockDim.x)
+#define OBCA_SYNC() __syncthreads()
+#define OBCA_SERIAL if (threadIdx.x == 0)
+#else
+#define OBCA_FOR_STAGES(k, ns) for (int k = 0; k < (ns); ++k)
+#define OBCA_SYNC()
+#define OBCA_SERIAL
+#endif
+
+namespace obca {
+
+// ---- workspace layout: every entry is an array of NSP doubles indexed by stage ----
+struct PkLay {
+  int NSP;
+  // iterate
+  int X, Y, PS, VL, DE, AC, LAM, MU, SL;
+  int ZXL, ZXU, ZYL, ZYU, ZVL, ZVU, ZDL, ZDU, ZAL, ZAU, ZLAM, ZMU;
+  int PI, YN, YR;
+  int SD, VD, SN, VN, RS, RVL, RVU;
+  // step
+  int dX, dY, dPS, dVL, dDE, dAC, dLAM, dMU, dSL;
+  int PIn, YNn, YRn, dSD, dSN, dRS;
+  // KKT workspace
+  int QS, qs, DYN, R4, RK, RP, LF;
+  int nfac;
+  // reductions
+  int RED;
+  int total;
+};
+enum { R_DUAL = 0, R_PR, R_CMAX, R_CMIN, R_SY, R_SZ, R_TH, R_PHI, R_RT, R_OK, R_APR, R_ADU, R_DPHI, R_F, R_NUM };
+
+inline PkLay make_layout(const ParkProblem& P, int nfac) {
+  PkLay L;
+  const int NS = P.N + 1;
+  L.NSP = ((NS + 31) / 32) * 32;
+  int c = 0;
+  auto take = [&](int n) { int o = c; c += n; return o; };
+  L.X = take(1); L.Y = take(1); L.PS = take(1); L.VL = take(1); L.DE = take(1); L.AC = take(1);
+  L.LAM = take(P.V); L.MU = take(4 * P.nOb); L.SL = take(P.nOb);
+  L.ZXL = take(1); L.ZXU = take(1); L.ZYL = take(1); L.ZYU = take(1); L.ZVL = take(1); L.ZVU = take(1);
+  L.ZDL = take(1); L.ZDU = take(1); L.ZAL = take(1); L.ZAU = take(1);
+  L.ZLAM = take(P.V); L.ZMU = take(4 * P.nOb);
+  L.PI = take(4); L.YN = take(P.nOb); L.YR = take(2 * P.nOb);
+  L.SD = take(P.nOb); L.VD = take(P.nOb); L.SN = take(P.nOb); L.VN = take(P.nOb);
+  L.RS = take(1); L.RVL = take(1); L.RVU = take(1);
+  L.dX = take(1); L.dY = take(1); L.dPS = take(1); L.dVL = take(1); L.dDE = take(1); L.dAC = take(1);
+  L.dLAM = take(P.V); L.dMU = take(4 * P.nOb); L.dSL = take(P.nOb);
+  L.PIn = take(4); L.YNn = take(P.nOb); L.YRn = take(2 * P.nOb);
+  L.dSD = take(P.nOb); L.dSN = take(P.nOb); L.dRS = take(1);
+  L.QS = take(NQ); L.qs = take(NYV); L.DYN = take(20); L.R4 = take(4);
+  L.RK = take(16); L.RP = take(NSV * (NSV + 1) / 2 + NSV);
+  L.nfac = nfac;
+  L.LF = take(P.nOb * nfac);
+  L.RED = take(R_NUM);
+  L.total = c;
+  return L;
+}
+
+// per-problem scalar state (shared memory on the device)
+struct ProbState {
+  double t, zTL, zTU, dt;           // time scale, its bound multipliers, its step
+  double mu, tau;
+  double dw, dw_last;
+  double theta_max, theta_min;
+  double th_k, ph_k, dphi, f_k;
+  double e0, e_dual, e_pr, e_cmax, e_cmin, sum_y, sum_z, rz_t;
+  double a_pr, a_du, alpha, a_min;
+  double th_t, ph_t;
+  int nfilt;
+  double filt_th[64], filt_ph[64];
+  int status;     // 1 converged, 0 running / max_iter, -1 line-search failure, -2 inertia failure
+  int iters;
+  int flag;       // generic broadcast flag
+  int ok;
+  int n_fact;     // factorisations
+};
+
+struct PkInputs {
+  const double* x0;    // 4
+  const double* xF;    // 4
+  const double* rx;    // NS
+  const double* ry;
+  const double* ryaw;
+  const double* xWS;   // (N+1) x 4 column-major  (ParkingSignedDist.jl:216: setvalue(x, xWS'))
+  int ldx;             // leading dimension (rows) of xWS
+  const double* uWS;   // rows x 2 column-major, rows >= N (:217)
+  int ldu;
+  const double* lWS;   // (N+1) x V column-major (:221)
+  const double* nWS;   // (N+1) x 4nOb column-major (:222)
+};
+
+// outputs of one problem, in the reference's return shapes (ParkingSignedDist.jl:302-313), column-major
+struct PkOutputs {
+  double* xp;      // 4 x (N+1)
+  double* up;      // 2 x N
+  double* ts;      // N+1   (timeScalep; ones if fixTime, :304-308)
+  double* lp;      // V x (N+1)
+  double* np;      // 4nOb x (N+1)
+  double* sl;      // nOb x (N+1)  (SD only; may be null)
+  double* duals;   // optional (may be null): pi 4 x N, then y_rot 2nOb x (N+1), y_norm nOb x (N+1), vd nOb x (N+1)
+};
+
+struct PkCtx {
+  const ParkProblem* P;
+  const IpmOpts* O;
+  PkLay L;
+  double* W;
+  ProbState* S;
+  PkInputs in;
+};
+
+#define WA(name, k) (C.W[(size_t)(C.L.name) * C.L.NSP + (k)])
+#define WV(name, i, k) (C.W[(size_t)(C.L.name + (i)) * C.L.NSP + (k)])
+
+OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
+  const double pl = dmin_(k1 * dmax(1.0, dabs(lo)), k2 * (hi - lo));
+  const double pu = dmin_(k1 * dmax(1.0, dabs(hi)), k2 * (hi - lo));
+  x = dmax(x, lo + pl);
+  x = dmin_(x, hi - pu);
+  return x;
+}
+
+template <int VM, bool SDV>
+struct ParkSolver {
+  typedef LocalDims<VM, SDV> LD;
+
+  // ---------------------------------------------------------------------------------------------------
+  // load rows / variables of block (k, j), optionally at the trial point  z + alpha dz
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void load_rows(const PkCtx& C, int j, ObsRows<VM>& R) {
+    const ParkProblem& P = *C.P;
+    R.v = P.vOb[j];
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      const bool on = i < R.v;
+      const int r = P.voff[j] + (on ? i : 0);
+      R.a1[i] = on ? P.A[r][0] : 0.0;
+      R.a2[i] = on ? P.A[r][1] : 0.0;
+      R.bb[i] = on ? P.b[r] : 0.0;
+    }
+  }
+  OBCA_HD static void load_vars(const PkCtx& C, int k, int j, const ObsRows<VM>& R, ObsVars<VM>& Q) {
+    const ParkProblem& P = *C.P;
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      const bool on = i < R.v;
+      Q.lam[i] = on ? WV(LAM, P.voff[j] + i, k) : 1.0;
+      Q.zlam[i] = on ? WV(ZLAM, P.voff[j] + i, k) : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { Q.mu[m] = WV(MU, 4 * j + m, k); Q.zmu[m] = WV(ZMU, 4 * j + m, k); }
+    Q.sl = SDV ? WV(SL, j, k) : 0.0;
+    Q.yn = SDV ? WV(YN, j, k) : 0.0;
+    Q.yr1 = WV(YR, 2 * j, k); Q.yr2 = WV(YR, 2 * j + 1, k);
+    Q.sd = WV(SD, j, k); Q.vd = WV(VD, j, k);
+    Q.sn = SDV ? 0.0 : WV(SN, j, k);
+    Q.vn = SDV ? 0.0 : WV(VN, j, k);
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // P0: initial point (ParkingSignedDist.jl:213-222) + Ipopt's projection into the bounds, slacks, multipliers
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void init_stage(const PkCtx& C, int k) {
+    const ParkProblem& P = *C.P;
+    const IpmOpts& O = *C.O;
+    const int N = P.N;
+    const bool pose_free = (k >= 1 && k <= N - 1);
+    double X = C.in.xWS[0 * C.in.ldx + k], Y = C.in.xWS[1 * C.in.ldx + k];
+    double ps = C.in.xWS[2 * C.in.ldx + k], v = C.in.xWS[3 * C.in.ldx + k];
+    if (k == 0) { X = C.in.x0[0]; Y = C.in.x0[1]; ps = C.in.x0[2]; v = C.in.x0[3]; }
+    if (k == N) { X = C.in.xF[0]; Y = C.in.xF[1]; ps = C.in.xF[2]; v = C.in.xF[3]; }
+    if (pose_free) {
+      X = push_lo(X, P.xyb[0], P.xyb[1], O.kappa1, O.kappa2);
+      Y = push_lo(Y, P.xyb[2], P.xyb[3], O.kappa1, O.kappa2);
+      v = push_lo(v, -1.0, 2.0, O.kappa1, O.kappa2);
+    }
+    WA(X, k) = X; WA(Y, k) = Y; WA(PS, k) = ps; WA(VL, k) = v;
+    WA(ZXL, k) = 1.0; WA(ZXU, k) = 1.0; WA(ZYL, k) = 1.0; WA(ZYU, k) = 1.0; WA(ZVL, k) = 1.0; WA(ZVU, k) = 1.0;
+    double de = 0.0, ac = 0.0;
+    if (k < N) {
+      de = push_lo(C.in.uWS[0 * C.in.ldu + k], -0.6, 0.6, O.kappa1, O.kappa2);
+      ac = push_lo(C.in.uWS[1 * C.in.ldu + k], -0.4, 0.4, O.kappa1, O.kappa2);
+    }
+    WA(DE, k) = de; WA(AC, k) = ac;
+    WA(ZDL, k) = 1.0; WA(ZDU, k) = 1.0; WA(ZAL, k) = 1.0; WA(ZAU, k) = 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) WV(PI, i, k) = 0.0;
+    const double lpush = O.kappa1;   // lower bound 0: kappa1 * max(1, |0|)
+    for (int r = 0; r < P.V; ++r) {
+      WV(LAM, r, k) = dmax(C.in.lWS[(size_t)r * (N + 1) + k], lpush);
+      WV(ZLAM, r, k) = 1.0;
+    }
+    for (int r = 0; r < 4 * P.nOb; ++r) {
+      WV(MU, r, k) = dmax(C.in.nWS[(size_t)r * (N + 1) + k], lpush);
+      WV(ZMU, r, k) = 1.0;
+    }
+    for (int j = 0; j < P.nOb; ++j) {
+      if (SDV) { WV(SL, j, k) = 0.0; WV(YN, j, k) = 0.0; }
+      WV(YR, 2 * j, k) = 0.0; WV(YR, 2 * j + 1, k) = 0.0;
+    }
+  }
+  // slacks need the pushed primal point of the neighbours -> separate phase
+  OBCA_HD static void init_slacks(const PkCtx& C, int k) {
+    const ParkProblem& P = *C.P;
+    const IpmOpts& O = *C.O;
+    const int N = P.N;
+    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
+    double s, c;
+    sincos(ps, &s, &c);
+    for (int j = 0; j < P.nOb; ++j) {
+      ObsRows<VM> R; ObsVars<VM> Q; ObsGeom<VM> G;
+      load_rows(C, j, R);
+      load_vars(C, k, j, R, Q);
+      Q.sd = 0.0; Q.sn = 0.0;
+      obs_geom<VM, SDV>(P, X, Y, c, s, R, Q, G);
+      WV(SD, j, k) = dmax(G.gd, P.dmin + O.kappa1 * dmax(1.0, dabs(P.dmin)));
+      WV(VD, j, k) = 1.0;
+      if (!SDV) { WV(SN, j, k) = dmin_(G.pp, 1.0 - O.kappa1); WV(VN, j, k) = 1.0; }
+    }
+    if (k < N) {
+      const double h = (P.fix_time ? 1.0 : C.S->t) * P.Ts;
+      const double wd = k > 0 ? WA(DE, k - 1) : 0.0;
+      const double gr = (wd - WA(DE, k)) / h;
+      WA(RS, k) = push_lo(gr, -0.6, 0.6, O.kappa1, O.kappa2);
+      WA(RVL, k) = 1.0; WA(RVU, k) = 1.0;
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // P1 (K1): fused evaluation at the current iterate.
+  //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm) {
+    const ParkProblem& P = *C.P;
+    const ProbState& S = *C.S;
+    const int N = P.N;
+    const bool fix = P.fix_time != 0;
+    const double mu_b = S.mu, dw = S.dw;
+    const bool pose_free = (k >= 1 && k <= N - 1);
+    const bool has_u = k < N;
+    const double t = fix ? 1.0 : S.t;
+    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k), v = WA(VL, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+
+    double Q[NQ], q[NYV];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) Q[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NYV; ++i) q[i] = 0.0;
+    double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0;
+    double rz_t = 0.0;
+    int ok = 1;
+    // Lagrangian gradient rows of the pose
+    double rzX = 0.0, rzY = 0.0, rzP = 0.0, rzV = 0.0;
+
+    // ---- (A) state objective + bounds ----
+    {
+      const double ex = X - C.in.rx[k], ey = Y - C.in.ry[k], ep = ps - C.in.ryaw[k];
+      fobj += 1e-4 * v * v + 1e-3 * ex * ex + 1e-3 * ey * ey + P.w_yaw * ep * ep;
+      if (pose_free) {
+        const double gX = 2e-3 * ex, gY = 2e-3 * ey, gP = 2.0 * P.w_yaw * ep, gV = 2e-4 * v;
+        const double aXl = X - P.xyb[0], aXu = P.xyb[1] - X, aYl = Y - P.xyb[2], aYu = P.xyb[3] - Y;
+        const double aVl = v + 1.0, aVu = 2.0 - v;
+        const double zXl = WA(ZXL, k), zXu = WA(ZXU, k), zYl = WA(ZYL, k), zYu = WA(ZYU, k), zVl = WA(ZVL, k), zVu = WA(ZVU, k);
+        Q[sym_idx<NYV>(IX, IX)] += 2e-3 + zXl / aXl + zXu / aXu + dw;
+        Q[sym_idx<NYV>(IY, IY)] += 2e-3 + zYl / aYl + zYu / aYu + dw;
+        Q[sym_idx<NYV>(IP, IP)] += 2.0 * P.w_yaw + dw;
+        Q[sym_idx<NYV>(IV, IV)] += 2e-4 + zVl / aVl + zVu / aVu + dw;
+        q[IX] += gX - mu_b / aXl + mu_b / aXu;
+        q[IY] += gY - mu_b / aYl + mu_b / aYu;
+        q[IP] += gP;
+        q[IV] += gV - mu_b / aVl + mu_b / aVu;
+        rzX += gX - zXl + zXu; rzY += gY - zYl + zYu; rzP += gP; rzV += gV - zVl + zVu;
+        // multiplier of the dynamics row that produced x_k
+        rzX += WV(PI, 0, k - 1); rzY += WV(PI, 1, k - 1); rzP += WV(PI, 2, k - 1); rzV += WV(PI, 3, k - 1);
+        if (do_err) {
+          const double c6[6] = {aXl * zXl, aXu * zXu, aYl * zYl, aYu * zYu, aVl * zVl, aVu * zVu};
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { cmax = dmax(cmax, c6[i]); cmin = dmin_(cmin, c6[i]); }
+          sum_z += zXl + zXu + zYl + zYu + zVl + zVu;
+          phi -= mu_b * (log(aXl) + log(aXu) + log(aYl) + log(aYu) + log(aVl) + log(aVu));
+        }
+      }
+    }
+    // ---- (B) controls, input-rate terms, steering-rate row, dynamics ----
+    DynOut dyn;
+    double r4[4] = {0, 0, 0, 0};
+    if (has_u) {
+      const double de = WA(DE, k), ac = WA(AC, k);
+      const double wd = k > 0 ? WA(DE, k - 1) : 0.0, wa = k > 0 ? WA(AC, k - 1) : 0.0;
+      const double h = t * P.Ts, ih = 1.0 / h, ih2 = ih * ih, it = 1.0 / t;
+      const double ed = de - wd, ea = ac - wa;
+      const double T = 0.1 * (ed * ed + ea * ea) * ih2;
+      fobj += 0.01 * de * de + P.w_a * ac * ac + T;
+      const double gD = 0.02 * de + 0.2 * ed * ih2, gA = 2.0 * P.w_a * ac + 0.2 * ea * ih2;
+      const double gWd = -0.2 * ed * ih2, gWa = -0.2 * ea * ih2;
+      const double gT = fix ? 0.0 : -2.0 * T * it;
+      const double aDl = de + 0.6, aDu = 0.6 - de, aAl = ac + 0.4, aAu = 0.4 - ac;
+      const double zDl = WA(ZDL, k), zDu = WA(ZDU, k), zAl = WA(ZAL, k), zAu = WA(ZAU, k);
+      Q[sym_idx<NYV>(IDE, IDE)] += 0.02 + 0.2 * ih2 + zDl / aDl + zDu / aDu + dw;
+      Q[sym_idx<NYV>(IAC, IAC)] += 2.0 * P.w_a + 0.2 * ih2 + zAl / aAl + zAu / aAu + dw;
+      Q[sym_idx<NYV>(IWD, IWD)] += 0.2 * ih2;
+      Q[sym_idx<NYV>(IWA, IWA)] += 0.2 * ih2;
+      Q[sym_idx<NYV>(IWD, IDE)] += -0.2 * ih2;
+      Q[sym_idx<NYV>(IWA, IAC)] += -0.2 * ih2;
+      if (!fix) {
+        Q[sym_idx<NYV>(IT, IDE)] += -0.4 * ed * ih2 * it;
+        Q[sym_idx<NYV>(IT, IAC)] += -0.4 * ea * ih2 * it;
+        Q[sym_idx<NYV>(IWD, IT)] += 0.4 * ed * ih2 * it;
+        Q[sym_idx<NYV>(IWA, IT)] += 0.4 * ea * ih2 * it;
+        Q[sym_idx<NYV>(IT, IT)] += 6.0 * T * it * it;
+      }
+      // steering-rate row (ParkingSignedDist.jl:167-173):  -0.6 <= (wd - de)/(t Ts) <= 0.6
+      const double gr = (wd - de) * ih;
+      const double rs = WA(RS, k), rvl = WA(RVL, k), rvu = WA(RVU, k);
+      const double yIr = rvu - rvl;
+      const double gl = rs + 0.6, gu = 0.6 - rs;
+      const double Sr = rvl / gl + rvu / gu;
+      const double cIr = gr - rs;
+      const double yr0 = -mu_b / gl + mu_b / gu + Sr * cIr;
+      const double jw = ih, jd = -ih, jt = fix ? 0.0 : -gr * it;
+      Q[sym_idx<NYV>(IWD, IWD)] += Sr * jw * jw;
+      Q[sym_idx<NYV>(IWD, IDE)] += Sr * jw * jd;
+      Q[sym_idx<NYV>(IDE, IDE)] += Sr * jd * jd;
+      if (!fix) {
+        Q[sym_idx<NYV>(IWD, IT)] += Sr * jw * jt - yIr * ih * it;
+        Q[sym_idx<NYV>(IT, IDE)] += Sr * jt * jd + yIr * ih * it;
+        Q[sym_idx<NYV>(IT, IT)] += Sr * jt * jt + yIr * 2.0 * gr * it * it;
+      }
+      q[IWD] += gWd + jw * yr0;
+      q[IWA] += gWa;
+      q[IDE] += gD + jd * yr0 - mu_b / aDl + mu_b / aDu;
+      q[IAC] += gA - mu_b / aAl + mu_b / aAu;
+      q[IT] += gT + jt * yr0;
+      // dynamics
+      double pi[4], H5[15];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pi[i] = WV(PI, i, k);
+      dyn_eval(P, X, Y, ps, v, de, ac, t, dyn, pi, H5);
+      {
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int j = i; j < 5; ++j) Q[sym_idx_any<NYV>(q5_to_y(i), q5_to_y(j))] += H5[e++];
+      }
+      double xn[4];
+      if (k + 1 == N) { xn[0] = C.in.xF[0]; xn[1] = C.in.xF[1]; xn[2] = C.in.xF[2]; xn[3] = C.in.xF[3]; }
+      else { xn[0] = WA(X, k + 1); xn[1] = WA(Y, k + 1); xn[2] = WA(PS, k + 1); xn[3] = WA(VL, k + 1); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r4[i] = dyn.f[i] - xn[i];
+      // Lagrangian gradient: -A' pi on the pose rows
+      if (pose_free) {
+        rzX -= pi[0]; rzY -= pi[1];
+        rzP -= pi[0] * dyn.fx[0][0] + pi[1] * dyn.fx[1][0] + pi[2] * dyn.fx[2][0] + pi[3] * dyn.fx[3][0];
+        rzV -= pi[0] * dyn.fx[0][1] + pi[1] * dyn.fx[1][1] + pi[2] * dyn.fx[2][1] + pi[3] * dyn.fx[3][1];
+      }
+      if (do_err) {
+        // rows of (de_k, a_k): own terms + the "previous control" role in stage k+1
+        double rzD = gD + jd * yIr - zDl + zDu, rzA = gA - zAl + zAu;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { rzD -= pi[i] * dyn.fu[i][0]; rzA -= pi[i] * dyn.fu[i][1]; }
+        if (k + 1 < N) {
+          const double ed2 = WA(DE, k + 1) - de, ea2 = WA(AC, k + 1) - ac;
+          rzD += -0.2 * ed2 * ih2 + (WA(RVU, k + 1) - WA(RVL, k + 1)) * ih;
+          rzA += -0.2 * ea2 * ih2;
+        }
+        e_dual = dmax(e_dual, dmax(dabs(rzD), dabs(rzA)));
+        if (!fix) {
+          rz_t += gT + jt * yIr;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rz_t -= pi[i] * dyn.ft[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { e_pr = dmax(e_pr, dabs(r4[i])); th += dabs(r4[i]); sum_y += dabs(pi[i]); }
+        e_pr = dmax(e_pr, dabs(cIr)); th += dabs(cIr);
+        sum_y += dabs(yIr); sum_z += rvl + rvu + zDl + zDu + zAl + zAu;
+        const double c6[6] = {aDl * zDl, aDu * zDu, aAl * zAl, aAu * zAu, gl * rvl, gu * rvu};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { cmax = dmax(cmax, c6[i]); cmin = dmin_(cmin, c6[i]); }
+        phi -= mu_b * (log(aDl) + log(aDu) + log(aAl) + log(aAu) + log(gl) + log(gu));
+      }
+    }
+    // ---- (C) obstacle blocks ----
+    for (int j = 0; j < P.nOb; ++j) {
+      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
+      load_rows(C, j, R);
+      load_vars(C, k, j, R, Qv);
+      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      if (do_err) {
+        double rl[VM], rm[4], rs_, gx[3];
+        obs_lagr_grad<VM, SDV>(P, R, Qv, G, rl, rm, rs_, gx);
+        rzX += gx[0]; rzY += gx[1]; rzP += gx[2];
+#pragma unroll
+        for (int i = 0; i < VM; ++i) {
+          if (i < R.v) {
+            e_dual = dmax(e_dual, dabs(rl[i]));
+            const double cp = Qv.lam[i] * Qv.zlam[i];
+            cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+            sum_z += Qv.zlam[i];
+            phi -= mu_b * log(Qv.lam[i]);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          e_dual = dmax(e_dual, dabs(rm[m]));
+          const double cp = Qv.mu[m] * Qv.zmu[m];
+          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+          sum_z += Qv.zmu[m];
+          phi -= mu_b * log(Qv.mu[m]);
+        }
+        if (SDV) { e_dual = dmax(e_dual, dabs(rs_)); fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl; }
+        e_pr = dmax(e_pr, dmax(dmax(dabs(G.cn), dabs(G.cd)), dmax(dabs(G.cr1), dabs(G.cr2))));
+        th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
+        sum_y += dabs(Qv.yr1) + dabs(Qv.yr2) + Qv.vd + (SDV ? dabs(Qv.yn) : Qv.vn);
+        sum_z += Qv.vd + (SDV ? 0.0 : Qv.vn);
+        {
+          const double cp = (Qv.sd - P.dmin) * Qv.vd;
+          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+          phi -= mu_b * log(Qv.sd - P.dmin);
+        }
+        if (!SDV) {
+          const double cp = (1.0 - Qv.sn) * Qv.vn;
+          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+          phi -= mu_b * log(1.0 - Qv.sn);
+        }
+      } else if (SDV) {
+        fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
+      }
+      if (do_asm) {
+        const int piv = choose_pivot<VM, SDV>(R, G);
+        if (piv != 0) {
+          swap_rows(R, Qv, piv);
+          obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+        }
+        double Sxx[6], rx3[3], fac[LD::NFAC];
+        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, C.O->dc, Sxx, rx3, fac);
+        if (pose_free) {
+          Q[sym_idx<NYV>(IX, IX)] += Sxx[0]; Q[sym_idx<NYV>(IX, IY)] += Sxx[1]; Q[sym_idx<NYV>(IX, IP)] += Sxx[2];
+          Q[sym_idx<NYV>(IY, IY)] += Sxx[3]; Q[sym_idx<NYV>(IY, IP)] += Sxx[4]; Q[sym_idx<NYV>(IP, IP)] += Sxx[5];
+          q[IX] += rx3[0]; q[IY] += rx3[1]; q[IP] += rx3[2];
+        }
+#pragma unroll
+        for (int e = 0; e < LD::NFAC; ++e) WV(LF, j * C.L.nfac + e, k) = fac[e];
+      }
+    }
+    // ---- (D) time-scale variable: objective (N+1)(0.5 t + t^2) (:89) and its (N+1) bound pairs ----
+    if (k == 0 && !fix) {
+      const double m = (double)(N + 1);
+      const double gl = t - 0.8, gu = 1.2 - t;
+      fobj += m * (0.5 * t + t * t);
+      Q[sym_idx<NYV>(IT, IT)] += 2.0 * m + m * (S.zTL / gl + S.zTU / gu) + dw;
+      q[IT] += m * (0.5 + 2.0 * t) + m * (-mu_b / gl + mu_b / gu);
+      if (do_err) {
+        rz_t += m * (0.5 + 2.0 * t) - m * (S.zTL - S.zTU);
+        cmax = dmax(cmax, dmax(gl * S.zTL, gu * S.zTU));
+        cmin = dmin_(cmin, dmin_(gl * S.zTL, gu * S.zTU));
+        sum_z += m * (S.zTL + S.zTU);
+        phi -= m * mu_b * (log(gl) + log(gu));
+      }
+    }
+    if (do_err) {
+      if (pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
+      WV(RED, R_DUAL, k) = e_dual; WV(RED, R_PR, k) = e_pr; WV(RED, R_CMAX, k) = cmax; WV(RED, R_CMIN, k) = cmin;
+      WV(RED, R_SY, k) = sum_y; WV(RED, R_SZ, k) = sum_z; WV(RED, R_TH, k) = th; WV(RED, R_PHI, k) = phi + fobj;
+      WV(RED, R_RT, k) = rz_t; WV(RED, R_F, k) = fobj;
+    }
+    if (do_asm) {
+      WV(RED, R_OK, k) = (double)ok;
+      if (has_u) {
+#pragma unroll
+        for (int e = 0; e < NQ; ++e) WV(QS, e, k) = Q[e];
+#pragma unroll
+        for (int e = 0; e < NYV; ++e) WV(qs, e, k) = q[e];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          WV(DYN, 5 * i + 0, k) = dyn.fx[i][0]; WV(DYN, 5 * i + 1, k) = dyn.fx[i][1]; WV(DYN, 5 * i + 2, k) = dyn.ft[i];
+          WV(DYN, 5 * i + 3, k) = dyn.fu[i][0]; WV(DYN, 5 * i + 4, k) = dyn.fu[i][1];
+          WV(R4, i, k) = r4[i];
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // K3: stage-banded KKT solve.  Backward Riccati sweep, root (dt), forward roll-out.  Serial per problem.
+  //     returns 1 if every pivot is positive (KKT inertia (n, m, 0)).
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static int kkt_solve(const PkCtx& C) {
+    const ParkProblem& P = *C.P;
+    ProbState& S = *C.S;
+    const int N = P.N;
+    const bool fix = P.fix_time != 0;
+    constexpr int NP = NSV * (NSV + 1) / 2;
+    double Pn[NP], pn[NSV];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) Pn[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSV; ++i) pn[i] = 0.0;
+    // terminal value: regularised end-point rows  x_N == xF  (ParkingSignedDist.jl:128-131)
+    const double rho = 1.0 / C.O->dc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { Pn[sym_idx<NSV>(i, i)] = rho; pn[i] = -WV(PI, i, N - 1); }
+    int ok = 1;
+    for (int k = N - 1; k >= 0; --k) {
+      // P_{k+1}, p_{k+1} are needed by the forward sweep (multipliers)
+#pragma unroll
+      for (int e = 0; e < NP; ++e) WV(RP, e, k + 1) = Pn[e];
+#pragma unroll
+      for (int e = 0; e < NSV; ++e) WV(RP, NP + e, k + 1) = pn[e];
+      DynOut d;
+      double r4[4], Q[NQ], q[NYV];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        d.fx[i][0] = WV(DYN, 5 * i + 0, k); d.fx[i][1] = WV(DYN, 5 * i + 1, k); d.ft[i] = WV(DYN, 5 * i + 2, k);
+        d.fu[i][0] = WV(DYN, 5 * i + 3, k); d.fu[i][1] = WV(DYN, 5 * i + 4, k);
+        r4[i] = WV(R4, i, k);
+      }
+#pragma unroll
+      for (int e = 0; e < NQ; ++e) Q[e] = WV(QS, e, k);
+#pragma unroll
+      for (int e = 0; e < NYV; ++e) q[e] = WV(qs, e, k);
+      double Pk[NP], pk[NSV];
+      RicStage G;
+      ok &= riccati_step(d, r4, Q, q, Pn, pn, Pk, pk, G);
+#pragma unroll
+      for (int j = 0; j < NSV; ++j) { WV(RK, j, k) = G.K[0][j]; WV(RK, NSV + j, k) = G.K[1][j]; }
+      WV(RK, 14, k) = G.kf[0]; WV(RK, 15, k) = G.kf[1];
+#pragma unroll
+      for (int e = 0; e < NP; ++e) Pn[e] = Pk[e];
+#pragma unroll
+      for (int e = 0; e < NSV; ++e) pn[e] = pk[e];
+    }
+    // root: x_0, w_0 fixed; dt free (variable time)
+    double dt = 0.0;
+    if (!fix) {
+      double ptt = Pn[sym_idx<NSV>(IT, IT)];
+      if (!(ptt > 0.0)) { ok = 0; ptt = 1e300; }
+      dt = -pn[IT] / ptt;
+    }
+    S.dt = dt;
+    // forward
+    double s[NSV] = {0, 0, 0, 0, 0, 0, dt};
+    for (int k = 0; k < N; ++k) {
+      double u0 = WV(RK, 14, k), u1 = WV(RK, 15, k);
+#pragma unroll
+      for (int j = 0; j < NSV; ++j) { u0 += WV(RK, j, k) * s[j]; u1 += WV(RK, NSV + j, k) * s[j]; }
+      WA(dDE, k) = u0; WA(dAC, k) = u1;
+      double sn[NSV];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sn[i] = WV(R4, i, k) + WV(DYN, 5 * i + 0, k) * s[IP] + WV(DYN, 5 * i + 1, k) * s[IV] + WV(DYN, 5 * i + 2, k) * s[IT] +
+                WV(DYN, 5 * i + 3, k) * u0 + WV(DYN, 5 * i + 4, k) * u1;
+      }
+      sn[0] += s[IX]; sn[1] += s[IY];
+      sn[IWD] = u0; sn[IWA] = u1; sn[IT] = s[IT];
+      // new multiplier of the dynamics row k:  pi+ = -(P_{k+1} s_{k+1} + p_{k+1})_x
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double acc = WV(RP, NP + i, k + 1);
+#pragma unroll
+        for (int l = 0; l < NSV; ++l) acc += WV(RP, sym_idx_any<NSV>(i, l), k + 1) * sn[l];
+        WV(PIn, i, k) = -acc;
+      }
+      if (k + 1 < N) { WA(dX, k + 1) = sn[0]; WA(dY, k + 1) = sn[1]; WA(dPS, k + 1) = sn[2]; WA(dVL, k + 1) = sn[3]; }
+#pragma unroll
+      for (int i = 0; i < NSV; ++i) s[i] = sn[i];
+    }
+    WA(dX, 0) = 0.0; WA(dY, 0) = 0.0; WA(dPS, 0) = 0.0; WA(dVL, 0) = 0.0;
+    WA(dX, N) = 0.0; WA(dY, N) = 0.0; WA(dPS, N) = 0.0; WA(dVL, N) = 0.0;
+    WA(dDE, N) = 0.0; WA(dAC, N) = 0.0;
+    return ok;
+  }
+
+  // fraction-to-the-boundary helpers
+  OBCA_HD static void ftb(double gap, double dgap, double tau, double& amax) {
+    if (dgap < 0.0) amax = dmin_(amax, -tau * gap / dgap);
+  }
+  // dual step of a bound multiplier z with primal gap `gap` whose gap moves by dgap
+  OBCA_HD static double dzb(double z, double gap, double dgap, double mu_b) { return mu_b / gap - z - z / gap * dgap; }
+
+  // ---------------------------------------------------------------------------------------------------
+  // K4a: recover local steps, slack steps; step-length partials; directional derivative of the barrier objective
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void recover_stage(const PkCtx& C, int k) {
+    const ParkProblem& P = *C.P;
+    const ProbState& S = *C.S;
+    const int N = P.N;
+    const bool fix = P.fix_time != 0;
+    const double mu_b = S.mu, dw = S.dw, tau = S.tau;
+    const bool pose_free = (k >= 1 && k <= N - 1);
+    const double t = fix ? 1.0 : S.t;
+    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k), v = WA(VL, k);
+    const double dX = WA(dX, k), dY = WA(dY, k), dP = WA(dPS, k), dV = WA(dVL, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+    double apr = 1.0, adu = 1.0, dphi = 0.0;
+    if (pose_free) {
+      const double ex = X - C.in.rx[k], ey = Y - C.in.ry[k], ep = ps - C.in.ryaw[k];
+      const double aXl = X - P.xyb[0], aXu = P.xyb[1] - X, aYl = Y - P.xyb[2], aYu = P.xyb[3] - Y, aVl = v + 1.0, aVu = 2.0 - v;
+      ftb(aXl, dX, tau, apr); ftb(aXu, -dX, tau, apr); ftb(aYl, dY, tau, apr); ftb(aYu, -dY, tau, apr);
+      ftb(aVl, dV, tau, apr); ftb(aVu, -dV, tau, apr);
+      double z;
+      z = WA(ZXL, k); ftb(z, dzb(z, aXl, dX, mu_b), tau, adu);
+      z = WA(ZXU, k); ftb(z, dzb(z, aXu, -dX, mu_b), tau, adu);
+      z = WA(ZYL, k); ftb(z, dzb(z, aYl, dY, mu_b), tau, adu);
+      z = WA(ZYU, k); ftb(z, dzb(z, aYu, -dY, mu_b), tau, adu);
+      z = WA(ZVL, k); ftb(z, dzb(z, aVl, dV, mu_b), tau, adu);
+      z = WA(ZVU, k); ftb(z, dzb(z, aVu, -dV, mu_b), tau, adu);
+      dphi += (2e-3 * ex - mu_b / aXl + mu_b / aXu) * dX + (2e-3 * ey - mu_b / aYl + mu_b / aYu) * dY +
+              2.0 * P.w_yaw * ep * dP + (2e-4 * v - mu_b / aVl + mu_b / aVu) * dV;
+    }
+    if (k < N) {
+      const double de = WA(DE, k), ac = WA(AC, k), dD = WA(dDE, k), dA = WA(dAC, k);
+      const double wd = k > 0 ? WA(DE, k - 1) : 0.0, wa = k > 0 ? WA(AC, k - 1) : 0.0;
+      const double dwd = k > 0 ? WA(dDE, k - 1) : 0.0, dwa = k > 0 ? WA(dAC, k - 1) : 0.0;
+      const double h = t * P.Ts, ih = 1.0 / h, ih2 = ih * ih, it = 1.0 / t;
+      const double ed = de - wd, ea = ac - wa;
+      const double T = 0.1 * (ed * ed + ea * ea) * ih2;
+      const double aDl = de + 0.6, aDu = 0.6 - de, aAl = ac + 0.4, aAu = 0.4 - ac;
+      ftb(aDl, dD, tau, apr); ftb(aDu, -dD, tau, apr); ftb(aAl, dA, tau, apr); ftb(aAu, -dA, tau, apr);
+      double z;
+      z = WA(ZDL, k); ftb(z, dzb(z, aDl, dD, mu_b), tau, adu);
+      z = WA(ZDU, k); ftb(z, dzb(z, aDu, -dD, mu_b), tau, adu);
+      z = WA(ZAL, k); ftb(z, dzb(z, aAl, dA, mu_b), tau, adu);
+      z = WA(ZAU, k); ftb(z, dzb(z, aAu, -dA, mu_b), tau, adu);
+      // rate slack
+      const double gr = (wd - de) * ih;
+      const double rs = WA(RS, k);
+      const double gl = rs + 0.6, gu = 0.6 - rs;
+      const double drs = (dwd - dD) * ih - (fix ? 0.0 : gr * it * S.dt) + (gr - rs);
+      WA(dRS, k) = drs;
+      ftb(gl, drs, tau, apr); ftb(gu, -drs, tau, apr);
+      z = WA(RVL, k); ftb(z, dzb(z, gl, drs, mu_b), tau, adu);
+      z = WA(RVU, k); ftb(z, dzb(z, gu, -drs, mu_b), tau, adu);
+      dphi += (0.02 * de + 0.2 * ed * ih2 - mu_b / aDl + mu_b / aDu) * dD + (2.0 * P.w_a * ac + 0.2 * ea * ih2 - mu_b / aAl + mu_b / aAu) * dA +
+              (-0.2 * ed * ih2) * dwd + (-0.2 * ea * ih2) * dwa + (fix ? 0.0 : -2.0 * T * it * S.dt) +
+              (-mu_b / gl + mu_b / gu) * drs;
+    }
+    for (int j = 0; j < P.nOb; ++j) {
+      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
+      load_rows(C, j, R);
+      load_vars(C, k, j, R, Qv);
+      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      const int piv = choose_pivot<VM, SDV>(R, G);
+      if (piv != 0) {
+        swap_rows(R, Qv, piv);
+        obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      }
+      double fac[LD::NFAC];
+#pragma unroll
+      for (int e = 0; e < LD::NFAC; ++e) fac[e] = WV(LF, j * C.L.nfac + e, k);
+      ObsStep<VM> St;
+      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, fac, dX, dY, dP, St);
+      // un-permute lambda
+      if (piv != 0) {
+#pragma unroll
+        for (int i = 1; i < VM; ++i)
+          if (i == piv) {
+            double tmp = St.dlam[0]; St.dlam[0] = St.dlam[i]; St.dlam[i] = tmp;
+            tmp = Qv.lam[0]; Qv.lam[0] = Qv.lam[i]; Qv.lam[i] = tmp;
+            tmp = Qv.zlam[0]; Qv.zlam[0] = Qv.zlam[i]; Qv.zlam[i] = tmp;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < VM; ++i) {
+        if (i < R.v) {
+          WV(dLAM, P.voff[j] + i, k) = St.dlam[i];
+          ftb(Qv.lam[i], St.dlam[i], tau, apr);
+          ftb(Qv.zlam[i], dzb(Qv.zlam[i], Qv.lam[i], St.dlam[i], mu_b), tau, adu);
+          dphi += -mu_b / Qv.lam[i] * St.dlam[i];
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        WV(dMU, 4 * j + m, k) = St.dmu[m];
+        ftb(Qv.mu[m], St.dmu[m], tau, apr);
+        ftb(Qv.zmu[m], dzb(Qv.zmu[m], Qv.mu[m], St.dmu[m], mu_b), tau, adu);
+        dphi += -mu_b / Qv.mu[m] * St.dmu[m];
+      }
+      if (SDV) {
+        WV(dSL, j, k) = St.dsl; WV(YNn, j, k) = St.yn_new;
+        dphi += (1e2 + 2e4 * Qv.sl) * St.dsl;
+      }
+      WV(YRn, 2 * j, k) = St.yr1_new; WV(YRn, 2 * j + 1, k) = St.yr2_new;
+      WV(dSD, j, k) = St.dsd;
+      {
+        const double gap = Qv.sd - P.dmin;
+        ftb(gap, St.dsd, tau, apr);
+        ftb(Qv.vd, dzb(Qv.vd, gap, St.dsd, mu_b), tau, adu);
+        dphi += -mu_b / gap * St.dsd;
+      }
+      if (!SDV) {
+        WV(dSN, j, k) = St.dsn;
+        const double gap = 1.0 - Qv.sn;
+        ftb(gap, -St.dsn, tau, apr);
+        ftb(Qv.vn, dzb(Qv.vn, gap, -St.dsn, mu_b), tau, adu);
+        dphi += mu_b / gap * St.dsn;
+      }
+    }
+    if (k == 0 && !fix) {
+      const double m = (double)(N + 1);
+      const double gl = t - 0.8, gu = 1.2 - t;
+      ftb(gl, S.dt, tau, apr); ftb(gu, -S.dt, tau, apr);
+      ftb(S.zTL, dzb(S.zTL, gl, S.dt, mu_b), tau, adu);
+      ftb(S.zTU, dzb(S.zTU, gu, -S.dt, mu_b), tau, adu);
+      dphi += m * (0.5 + 2.0 * t - mu_b / gl + mu_b / gu) * S.dt;
+    }
+    WV(RED, R_APR, k) = apr; WV(RED, R_ADU, k) = adu; WV(RED, R_DPHI, k) = dphi;
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // K4b: merit-function partials at the trial point z + alpha dz  (theta = ||c||_1, phi = barrier objective)
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void merit_stage(const PkCtx& C, int k, double alpha) {
+    const ParkProblem& P = *C.P;
+    const ProbState& S = *C.S;
+    const int N = P.N;
+    const bool fix = P.fix_time != 0;
+    const double mu_b = S.mu;
+    const bool pose_free = (k >= 1 && k <= N - 1);
+    const double t = fix ? 1.0 : S.t + alpha * S.dt;
+    const double X = WA(X, k) + alpha * WA(dX, k), Y = WA(Y, k) + alpha * WA(dY, k);
+    const double ps = WA(PS, k) + alpha * WA(dPS, k), v = WA(VL, k) + alpha * WA(dVL, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+    double th = 0.0, phi = 0.0;
+    bool bad = false;
+    {
+      const double ex = X - C.in.rx[k], ey = Y - C.in.ry[k], ep = ps - C.in.ryaw[k];
+      phi += 1e-4 * v * v + 1e-3 * ex * ex + 1e-3 * ey * ey + P.w_yaw * ep * ep;
+      if (pose_free) {
+        const double g6[6] = {X - P.xyb[0], P.xyb[1] - X, Y - P.xyb[2], P.xyb[3] - Y, v + 1.0, 2.0 - v};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); phi -= mu_b * log(g6[i]); }
+      }
+    }
+    if (k < N) {
+      const double de = WA(DE, k) + alpha * WA(dDE, k), ac = WA(AC, k) + alpha * WA(dAC, k);
+      const double wd = k > 0 ? WA(DE, k - 1) + alpha * WA(dDE, k - 1) : 0.0;
+      const double wa = k > 0 ? WA(AC, k - 1) + alpha * WA(dAC, k - 1) : 0.0;
+      const double h = t * P.Ts, ih = 1.0 / h;
+      const double ed = de - wd, ea = ac - wa;
+      phi += 0.01 * de * de + P.w_a * ac * ac + 0.1 * (ed * ed + ea * ea) * ih * ih;
+      const double rs = WA(RS, k) + alpha * WA(dRS, k);
+      const double g6[6] = {de + 0.6, 0.6 - de, ac + 0.4, 0.4 - ac, rs + 0.6, 0.6 - rs};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); phi -= mu_b * log(g6[i]); }
+      th += dabs((wd - de) * ih - rs);
+      DynOut dyn;
+      dyn_eval(P, X, Y, ps, v, de, ac, t, dyn, nullptr, nullptr);
+      double xn[4];
+      if (k + 1 == N) { xn[0] = C.in.xF[0]; xn[1] = C.in.xF[1]; xn[2] = C.in.xF[2]; xn[3] = C.in.xF[3]; }
+      else {
+        xn[0] = WA(X, k + 1) + alpha * WA(dX, k + 1); xn[1] = WA(Y, k + 1) + alpha * WA(dY, k + 1);
+        xn[2] = WA(PS, k + 1) + alpha * WA(dPS, k + 1); xn[3] = WA(VL, k + 1) + alpha * WA(dVL, k + 1);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) th += dabs(dyn.f[i] - xn[i]);
+    }
+    for (int j = 0; j < P.nOb; ++j) {
+      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
+      load_rows(C, j, R);
+#pragma unroll
+      for (int i = 0; i < VM; ++i) {
+        const bool on = i < R.v;
+        Qv.lam[i] = on ? WV(LAM, P.voff[j] + i, k) + alpha * WV(dLAM, P.voff[j] + i, k) : 1.0;
+        Qv.zlam[i] = 0.0;
+        if (on) { bad |= !(Qv.lam[i] > 0.0); phi -= mu_b * log(Qv.lam[i]); }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        Qv.mu[m] = WV(MU, 4 * j + m, k) + alpha * WV(dMU, 4 * j + m, k);
+        Qv.zmu[m] = 0.0;
+        bad |= !(Qv.mu[m] > 0.0); phi -= mu_b * log(Qv.mu[m]);
+      }
+      Qv.sl = SDV ? WV(SL, j, k) + alpha * WV(dSL, j, k) : 0.0;
+      Qv.sd = WV(SD, j, k) + alpha * WV(dSD, j, k);
+      Qv.sn = SDV ? 0.0 : WV(SN, j, k) + alpha * WV(dSN, j, k);
+      Qv.yn = Qv.yr1 = Qv.yr2 = Qv.vd = Qv.vn = 0.0;
+      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
+      if (SDV) phi += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
+      { const double gap = Qv.sd - P.dmin; bad |= !(gap > 0.0); phi -= mu_b * log(gap); }
+      if (!SDV) { const double gap = 1.0 - Qv.sn; bad |= !(gap > 0.0); phi -= mu_b * log(gap); }
+    }
+    if (k == 0 && !fix) {
+      const double m = (double)(N + 1);
+      const double gl = t - 0.8, gu = 1.2 - t;
+      bad |= !(gl > 0.0) || !(gu > 0.0);
+      phi += m * (0.5 * t + t * t) - m * mu_b * (log(gl) + log(gu));
+    }
+    WV(RED, R_TH, k) = th;
+    WV(RED, R_PHI, k) = bad ? 1e300 : phi;
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // K4c: accept the step (primal alpha, dual a_du, equality multipliers a_y) + Ipopt's multiplier safeguard
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static double clipz(double z, double gap, double mu_b, double ks) {
+    return dmax(dmin_(z, ks * mu_b / gap), mu_b / (ks * gap));
+  }
+  OBCA_HD static void upd_pair(double& q, double dq, double& zl, double& zu, double lo, double hi, double alpha,
+                               double adu, double mu_b, double ks) {
+    const double gl = q - lo, gu = hi - q;
+    const double dzl = dzb(zl, gl, dq, mu_b), dzu = dzb(zu, gu, -dq, mu_b);
+    q += alpha * dq; zl += adu * dzl; zu += adu * dzu;
+    zl = clipz(zl, q - lo, mu_b, ks); zu = clipz(zu, hi - q, mu_b, ks);
+  }
+  OBCA_HD static void update_stage(const PkCtx& C, int k) {
+    const ParkProblem& P = *C.P;
+    const ProbState& S = *C.S;
+    const int N = P.N;
+    const double mu_b = S.mu, ks = C.O->kappa_sigma;
+    const double alpha = S.alpha, adu = S.a_du, ay = dmin_(S.alpha, S.a_du);   // alpha_for_y = min (:41)
+    const bool pose_free = (k >= 1 && k <= N - 1);
+    if (pose_free) {
+      double q, zl, zu;
+      q = WA(X, k); zl = WA(ZXL, k); zu = WA(ZXU, k);
+      upd_pair(q, WA(dX, k), zl, zu, P.xyb[0], P.xyb[1], alpha, adu, mu_b, ks);
+      WA(X, k) = q; WA(ZXL, k) = zl; WA(ZXU, k) = zu;
+      q = WA(Y, k); zl = WA(ZYL, k); zu = WA(ZYU, k);
+      upd_pair(q, WA(dY, k), zl, zu, P.xyb[2], P.xyb[3], alpha, adu, mu_b, ks);
+      WA(Y, k) = q; WA(ZYL, k) = zl; WA(ZYU, k) = zu;
+      q = WA(VL, k); zl = WA(ZVL, k); zu = WA(ZVU, k);
+      upd_pair(q, WA(dVL, k), zl, zu, -1.0, 2.0, alpha, adu, mu_b, ks);
+      WA(VL, k) = q; WA(ZVL, k) = zl; WA(ZVU, k) = zu;
+      WA(PS, k) += alpha * WA(dPS, k);
+    }
+    if (k < N) {
+      double q, zl, zu;
+      q = WA(DE, k); zl = WA(ZDL, k); zu = WA(ZDU, k);
+      upd_pair(q, WA(dDE, k), zl, zu, -0.6, 0.6, alpha, adu, mu_b, ks);
+      WA(DE, k) = q; WA(ZDL, k) = zl; WA(ZDU, k) = zu;
+      q = WA(AC, k); zl = WA(ZAL, k); zu = WA(ZAU, k);
+      upd_pair(q, WA(dAC, k), zl, zu, -0.4, 0.4, alpha, adu, mu_b, ks);
+      WA(AC, k) = q; WA(ZAL, k) = zl; WA(ZAU, k) = zu;
+      q = WA(RS, k); zl = WA(RVL, k); zu = WA(RVU, k);
+      upd_pair(q, WA(dRS, k), zl, zu, -0.6, 0.6, alpha, adu, mu_b, ks);
+      WA(RS, k) = q; WA(RVL, k) = zl; WA(RVU, k) = zu;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) WV(PI, i, k) += ay * (WV(PIn, i, k) - WV(PI, i, k));
+    }
+    for (int r = 0; r < P.V; ++r) {
+      double q = WV(LAM, r, k), z = WV(ZLAM, r, k);
+      const double dq = WV(dLAM, r, k);
+      const double dz = dzb(z, q, dq, mu_b);
+      q += alpha * dq; z += adu * dz;
+      WV(LAM, r, k) = q; WV(ZLAM, r, k) = clipz(z, q, mu_b, ks);
+    }
+    for (int r = 0; r < 4 * P.nOb; ++r) {
+      double q = WV(MU, r, k), z = WV(ZMU, r, k);
+      const double dq = WV(dMU, r, k);
+      const double dz = dzb(z, q, dq, mu_b);
+      q += alpha * dq; z += adu * dz;
+      WV(MU, r, k) = q; WV(ZMU, r, k) = clipz(z, q, mu_b, ks);
+    }
+    for (int j = 0; j < P.nOb; ++j) {
+      if (SDV) {
+        WV(SL, j, k) += alpha * WV(dSL, j, k);
+        WV(YN, j, k) += ay * (WV(YNn, j, k) - WV(YN, j, k));
+      }
+      WV(YR, 2 * j, k) += ay * (WV(YRn, 2 * j, k) - WV(YR, 2 * j, k));
+      WV(YR, 2 * j + 1, k) += ay * (WV(YRn, 2 * j + 1, k) - WV(YR, 2 * j + 1, k));
+      {
+        double s = WV(SD, j, k), z = WV(VD, j, k);
+        const double ds = WV(dSD, j, k);
+        const double dz = dzb(z, s - P.dmin, ds, mu_b);
+        s += alpha * ds; z += adu * dz;
+        WV(SD, j, k) = s; WV(VD, j, k) = clipz(z, s - P.dmin, mu_b, ks);
+      }
+      if (!SDV) {
+        double s = WV(SN, j, k), z = WV(VN, j, k);
+        const double ds = WV(dSN, j, k);
+        const double dz = dzb(z, 1.0 - s, -ds, mu_b);
+        s += alpha * ds; z += adu * dz;
+        WV(SN, j, k) = s; WV(VN, j, k) = clipz(z, 1.0 - s, mu_b, ks);
+      }
+    }
+  }
+
+  // write the solution of stage k in the reference's output layout
+  OBCA_HD static void store_stage(const PkCtx& C, int k, const PkOutputs& o) {
+    const ParkProblem& P = *C.P;
+    const int N = P.N, NS = N + 1;
+    o.xp[4 * k + 0] = WA(X, k); o.xp[4 * k + 1] = WA(Y, k); o.xp[4 * k + 2] = WA(PS, k); o.xp[4 * k + 3] = WA(VL, k);
+    if (k < N) { o.up[2 * k + 0] = WA(DE, k); o.up[2 * k + 1] = WA(AC, k); }
+    o.ts[k] = P.fix_time ? 1.0 : C.S->t;
+    for (int r = 0; r < P.V; ++r) o.lp[(size_t)P.V * k + r] = WV(LAM, r, k);
+    for (int r = 0; r < 4 * P.nOb; ++r) o.np[(size_t)4 * P.nOb * k + r] = WV(MU, r, k);
+    if (SDV && o.sl) for (int j = 0; j < P.nOb; ++j) o.sl[(size_t)P.nOb * k + j] = WV(SL, j, k);
+    if (o.duals) {
+      double* d = o.duals;
+      if (k < N) for (int i = 0; i < 4; ++i) d[4 * k + i] = WV(PI, i, k);
+      d += 4 * N;
+      for (int r = 0; r < 2 * P.nOb; ++r) d[(size_t)2 * P.nOb * k + r] = WV(YR, r, k);
+      d += (size_t)2 * P.nOb * NS;
+      for (int j = 0; j < P.nOb; ++j) d[(size_t)P.nOb * k + j] = SDV ? WV(YN, j, k) : WV(VN, j, k);
+      d += (size_t)P.nOb * NS;
+      for (int j = 0; j < P.nOb; ++j) d[(size_t)P.nOb * k + j] = WV(VD, j, k);
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // serial helpers (thread 0)
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void reduce_errors(const PkCtx& C) {
+    ProbState& S = *C.S;
+    const int NS = C.P->N + 1;
+    double e_dual = 0, e_pr = 0, cmax = 0, cmin = 1e300, sy = 0, sz = 0, th = 0, ph = 0, rt = 0, f = 0;
+    for (int k = 0; k < NS; ++k) {
+      e_dual = dmax(e_dual, WV(RED, R_DUAL, k)); e_pr = dmax(e_pr, WV(RED, R_PR, k));
+      cmax = dmax(cmax, WV(RED, R_CMAX, k)); cmin = dmin_(cmin, WV(RED, R_CMIN, k));
+      sy += WV(RED, R_SY, k); sz += WV(RED, R_SZ, k); th += WV(RED, R_TH, k); ph += WV(RED, R_PHI, k);
+      rt += WV(RED, R_RT, k); f += WV(RED, R_F, k);
+    }
+    if (!C.P->fix_time) e_dual = dmax(e_dual, dabs(rt));
+    S.e_dual = e_dual; S.e_pr = e_pr; S.e_cmax = cmax; S.e_cmin = cmin; S.sum_y = sy; S.sum_z = sz;
+    S.th_k = th; S.ph_k = ph; S.rz_t = rt; S.f_k = f;
+  }
+  // number of multipliers (for Ipopt's s_d, s_c scaling)
+  OBCA_HD static void mult_counts(const ParkProblem& P, double& n_mult, double& n_bmult) {
+    const int N = P.N, NS = N + 1;
+    double nb = 6.0 * (N - 1) + 4.0 * N + (P.V + 4.0 * P.nOb) * NS + (P.fix_time ? 0.0 : 2.0 * NS);   // variable bounds
+    nb += 2.0 * N + (double)P.nOb * NS + (P.signed_dist ? 0.0 : (double)P.nOb * NS);                   // slack bounds
+    const double mE = 4.0 * N + 2.0 * P.nOb * NS + (P.signed_dist ? (double)P.nOb * NS : 0.0);
+    const double mI = N + (double)P.nOb * NS + (P.signed_dist ? 0.0 : (double)P.nOb * NS);
+    n_bmult = nb; n_mult = nb + mE + mI;
+  }
+  OBCA_HD static double err_mu(const PkCtx& C, double mu_t) {
+    const ProbState& S = *C.S;
+    const IpmOpts& O = *C.O;
+    double n_mult, n_bmult;
+    mult_counts(*C.P, n_mult, n_bmult);
+    const double sd = dmax(O.s_max, (S.sum_y + S.sum_z) / n_mult) / O.s_max;
+    const double sc = dmax(O.s_max, S.sum_z / n_bmult) / O.s_max;
+    const double comp = dmax(S.e_cmax - mu_t, mu_t - S.e_cmin);
+    return dmax(dmax(S.e_dual / sd, S.e_pr), comp / sc);
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // the solve: all threads of the CTA call this with the same context
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void solve(const PkCtx& C) {
+    const ParkProblem& P = *C.P;
+    const IpmOpts& O = *C.O;
+    ProbState& S = *C.S;
+    const int N = P.N, NS = N + 1;
+    const bool fix = P.fix_time != 0;
+
+    OBCA_SERIAL {
+      S.t = fix ? 1.0 : push_lo(1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
+      S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
+      S.mu = O.mu_init; S.tau = dmax(O.tau_min, 1.0 - O.mu_init);
+      S.dw = 0.0; S.dw_last = 0.0; S.nfilt = 0; S.status = 0; S.iters = 0; S.n_fact = 0;
+    }
+    OBCA_SYNC();
+    OBCA_FOR_STAGES(k, NS) init_stage(C, k);
+    OBCA_SYNC();
+    OBCA_FOR_STAGES(k, NS) init_slacks(C, k);
+    OBCA_SYNC();
+
+    bool first = true;
+    for (int it = 0;; ++it) {
+      // ---- K1: evaluate (errors + assembly with the current mu and dw = 0) ----
+      OBCA_SERIAL { S.dw = 0.0; }
+      OBCA_SYNC();
+      OBCA_FOR_STAGES(k, NS) stage_eval(C, k, true, true);
+      OBCA_SYNC();
+      OBCA_SERIAL {
+        reduce_errors(C);
+        if (first) {
+          S.theta_max = 1e4 * dmax(1.0, S.th_k);
+          S.theta_min = 1e-4 * dmax(1.0, S.th_k);
+        }
+        S.e0 = err_mu(C, 0.0);
+        S.iters = it;
+        S.flag = 0;
+        if (S.e0 <= O.tol && S.e_dual <= O.dual_inf_tol && S.e_pr <= O.constr_viol_tol && S.e_cmax <= O.compl_inf_tol) {
+          S.status = 1; S.flag = 1;
+        } else if (it >= O.max_iter) {
+          S.status = 0; S.flag = 1;
+        } else {
+          // monotone barrier update
+          bool changed = false;
+          while (S.mu > O.mu_min && err_mu(C, S.mu) <= O.kappa_eps * S.mu) {
+            S.mu = dmax(O.mu_min, dmin_(O.kappa_mu * S.mu, pow(S.mu, O.theta_mu)));
+            S.tau = dmax(O.tau_min, 1.0 - S.mu);
+            changed = true;
+          }
+          if (changed) { S.nfilt = 0; S.flag = 2; }
+        }
+      }
+      first = false;
+      OBCA_SYNC();
+      if (S.flag == 1) break;
+      if (S.flag == 2) {   // mu changed: the barrier terms of the stage models (and phi) are stale
+        OBCA_FOR_STAGES(k, NS) stage_eval(C, k, true, true);
+        OBCA_SYNC();
+        OBCA_SERIAL { reduce_errors(C); }
+        OBCA_SYNC();
+      }
+      // ---- K3 with inertia correction (Ipopt Algorithm IC) ----
+      bool tried0 = false;
+      for (;;) {
+        OBCA_SERIAL {
+          int ok = 1;
+          for (int k = 0; k < NS; ++k) ok &= (WV(RED, R_OK, k) != 0.0);
+          if (ok) ok = kkt_solve(C);
+          S.n_fact++;
+          S.ok = ok;
+          if (!ok) {
+            if (S.dw == 0.0) S.dw = (S.dw_last == 0.0) ? O.dw_first : dmax(O.dw_min, O.kw_minus * S.dw_last);
+            else S.dw *= (S.dw_last == 0.0) ? O.kw_plus_first : O.kw_plus;
+            if (S.dw > O.dw_max) { S.status = -2; S.ok = -1; }
+          } else if (S.dw > 0.0) {
+            S.dw_last = S.dw;
+          }
+        }
+        OBCA_SYNC();
+        if (S.ok != 0) break;
+        OBCA_FOR_STAGES(k, NS) stage_eval(C, k, false, true);
+        OBCA_SYNC();
+        (void)tried0;
+      }
+      if (S.ok < 0) break;
+      // ---- K4: recover, step lengths, filter line search ----
+      OBCA_FOR_STAGES(k, NS) recover_stage(C, k);
+      OBCA_SYNC();
+      OBCA_SERIAL {
+        double apr = 1.0, adu = 1.0, dphi = 0.0;
+        for (int k = 0; k < NS; ++k) {
+          apr = dmin_(apr, WV(RED, R_APR, k)); adu = dmin_(adu, WV(RED, R_ADU, k)); dphi += WV(RED, R_DPHI, k);
+        }
+        S.a_pr = apr; S.a_du = adu; S.dphi = dphi;
+        const double th = S.th_k;
+        if (dphi < 0.0 && th <= S.theta_min)
+          S.a_min = O.gamma_alpha * dmin_(O.gamma_theta, dmin_(O.gamma_phi * th / (-dphi), O.delta * pow(th, O.s_theta) / pow(-dphi, O.s_phi)));
+        else if (dphi < 0.0)
+          S.a_min = O.gamma_alpha * dmin_(O.gamma_theta, O.gamma_phi * th / (-dphi));
+        else
+          S.a_min = O.gamma_alpha * O.gamma_theta;
+        S.alpha = apr;
+        S.flag = 0;
+      }
+      OBCA_SYNC();
+      for (int nbt = 0;; ++nbt) {
+        const double alpha = S.alpha;
+        OBCA_FOR_STAGES(k, NS) merit_stage(C, k, alpha);
+        OBCA_SYNC();
+        OBCA_SERIAL {
+          double th = 0.0, ph = 0.0;
+          for (int k = 0; k < NS; ++k) { th += WV(RED, R_TH, k); ph += WV(RED, R_PHI, k); }
+          S.th_t = th; S.ph_t = ph;
+          bool in_filter = th >= S.theta_max || !(ph < 1e299);
+          for (int i = 0; i < S.nfilt && !in_filter; ++i) in_filter = (th >= S.filt_th[i] && ph >= S.filt_ph[i]);
+          bool accepted = false, ftype = false;
+          if (!in_filter) {
+            const bool sw = S.dphi < 0.0 && alpha * pow(-S.dphi, O.s_phi) > O.delta * pow(S.th_k, O.s_theta);
+            if (S.th_k <= S.theta_min && sw) {
+              if (ph <= S.ph_k + O.eta_phi * alpha * S.dphi + 10.0 * 2.220446049250313e-16 * dabs(S.ph_k)) { accepted = true; ftype = true; }
+            } else {
+              if (th <= (1.0 - O.gamma_theta) * S.th_k || ph <= S.ph_k - O.gamma_phi * S.th_k) accepted = true;
+            }
+          }
+          if (accepted) {
+            S.flag = 1;
+            if (!ftype && S.nfilt < 64) {
+              S.filt_th[S.nfilt] = (1.0 - O.gamma_theta) * S.th_k;
+              S.filt_ph[S.nfilt] = S.ph_k - O.gamma_phi * S.th_k;
+              S.nfilt++;
+            }
+          } else {
+            S.alpha = 0.5 * alpha;
+            if (S.alpha < S.a_min || nbt + 1 >= O.max_backtrack) { S.flag = -1; S.status = -1; }
+          }
+        }
+        OBCA_SYNC();
+        if (S.flag != 0) break;
+      }
+      if (S.flag < 0) break;
+      // ---- accept ----
+      OBCA_FOR_STAGES(k, NS) update_stage(C, k);
+      OBCA_SERIAL {
+        if (!fix) {
+          double q = S.t, zl = S.zTL, zu = S.zTU;
+          upd_pair(q, S.dt, zl, zu, 0.8, 1.2, S.alpha, S.a_du, S.mu, O.kappa_sigma);
+          S.t = q; S.zTL = zl; S.zTU = zu;
+        }
+      }
+      OBCA_SYNC();
+    }
+  }
+};
+
+}  // namespace obca

@@ -1,0 +1,171 @@
+"""Host-side input producers for the OBCA hot path (NOT on the GPU path).
+
+* ``obst_hrep``           -- twin of AutonomousParking/obstHrep.jl:31-102 (vertices -> stacked H-rep).
+* ``reverse_parking_*``   -- scenario constants of AutonomousParking/main.jl:36-213 ("backwards").
+* ``warmstart_reverse``   -- deterministic geometric warm start (straight / left arc / reverse right arc /
+  reverse straight) standing in for the Hybrid A* + veloSmooth pipeline of main.jl:217-248, which is
+  out of scope this round.  Produces the same artefacts main.jl hands to
+  ParkingSignedDist: rx, ry, ryaw (N+1), xWS (N+1)x4, uWS Nx2.
+* ``reverse_parking_batch`` -- BASELINE config 2: randomised start poses, numpy default_rng(seed).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def obst_hrep(nOb, vOb, lOb):
+    """obstHrep.jl:31-102.  vOb = vertex counts (incl. repeated/last vertex), lOb = list of vertex lists."""
+    vOb = [int(v) for v in np.asarray(vOb).ravel()]
+    if nOb != len(lOb):
+        print("ERROR in number of obstacles")           # obstHrep.jl:34-36 (prints, does not throw)
+    rows = sum(vOb) - nOb
+    A_all = np.zeros((rows, 2)); b_all = np.zeros((rows, 1))
+    r = 0
+    for i in range(nOb):
+        for j in range(vOb[i] - 1):
+            v1 = np.asarray(lOb[i][j], float).ravel(); v2 = np.asarray(lOb[i][j + 1], float).ravel()
+            if v1[0] == v2[0]:                           # vertical edge, :57-64
+                if v2[1] < v1[1]:
+                    A_tmp, b_tmp = [1.0, 0.0], v1[0]
+                else:
+                    A_tmp, b_tmp = [-1.0, 0.0], -v1[0]
+            elif v1[1] == v2[1]:                         # horizontal edge, :65-72
+                if v1[0] < v2[0]:
+                    A_tmp, b_tmp = [0.0, 1.0], v1[1]
+                else:
+                    A_tmp, b_tmp = [0.0, -1.0], -v1[1]
+            else:                                        # general edge (not normalised), :73-85
+                ab = np.linalg.solve(np.array([[v1[0], 1.0], [v2[0], 1.0]]), np.array([v1[1], v2[1]]))
+                a_, b_ = ab
+                if v1[0] < v2[0]:
+                    A_tmp, b_tmp = [-a_, 1.0], b_
+                else:
+                    A_tmp, b_tmp = [a_, -1.0], -b_
+            A_all[r] = A_tmp; b_all[r, 0] = b_tmp
+            r += 1
+    return A_all, b_all
+
+
+# ----------------------------------------------------------------------------------------------
+# scenario constants (main.jl)
+# ----------------------------------------------------------------------------------------------
+EGO = np.array([3.7, 1.0, 1.0, 1.0])          # main.jl:73
+WHEELBASE = 2.7                               # main.jl:63
+XYBOUNDS = np.array([-15.0, 15.0, 1.0, 10.0])  # main.jl:210
+
+
+def reverse_parking_scenario():
+    """main.jl:99-108 ("backwards"): obstacles, H-rep, goal, Ts (variable time)."""
+    nOb = 3
+    vOb = [3, 3, 2]
+    lOb = [[[-20, 5], [-1.3, 5], [-1.3, -5]],
+           [[1.3, -5], [1.3, 5], [20, 5]],
+           [[20, 11], [-20, 11]]]
+    A, b = obst_hrep(nOb, vOb, lOb)
+    return dict(nOb=nOb, vOb=np.array(vOb) - 1, A=A, b=b, xF=np.array([0.0, 1.3, math.pi / 2, 0.0]),
+                Ts=0.6, Ts_fix=0.55, L=WHEELBASE, ego=EGO.copy(), XYbounds=XYBOUNDS.copy(), lOb=lOb)
+
+
+def parallel_parking_scenario(n_obstacles=3):
+    """main.jl:154-162 ("parallel").  The reference lists 4 obstacles; BASELINE config 3 keeps the first 3."""
+    lOb = [[[-20, 5], [-3.0, 5], [-3.0, 0]],
+           [[3.0, 0], [3.0, 5], [20, 5]],
+           [[-3, 2.5], [3, 2.5]],
+           [[20, 11], [-20, 11]]][:n_obstacles]
+    vOb = [3, 3, 2, 2][:n_obstacles]
+    A, b = obst_hrep(n_obstacles, vOb, lOb)
+    return dict(nOb=n_obstacles, vOb=np.array(vOb) - 1, A=A, b=b,
+                xF=np.array([-WHEELBASE / 2, 4.0, 0.0, 0.0]), Ts=0.9, Ts_fix=0.95, L=WHEELBASE,
+                ego=EGO.copy(), XYbounds=XYBOUNDS.copy(), lOb=lOb)
+
+
+# ----------------------------------------------------------------------------------------------
+# geometric warm start
+# ----------------------------------------------------------------------------------------------
+def _integrate_path(x, y, yaw, segs, L):
+    """segs: list of (signed_length, curvature).  Returns a function s -> (x,y,yaw,delta,dir) over total |length|."""
+    knots = []
+    s_acc = 0.0
+    for (ln, kap) in segs:
+        knots.append((s_acc, abs(ln), math.copysign(1.0, ln) if ln != 0 else 1.0, kap, x, y, yaw))
+        d = ln
+        if abs(kap) < 1e-12:
+            x, y = x + d * math.cos(yaw), y + d * math.sin(yaw)
+        else:
+            x += (math.sin(yaw + kap * d) - math.sin(yaw)) / kap
+            y -= (math.cos(yaw + kap * d) - math.cos(yaw)) / kap
+            yaw += kap * d
+        s_acc += abs(ln)
+    return knots, s_acc, (x, y, yaw)
+
+
+def _eval_knot(knot, ds, L):
+    _, _, sgn, kap, x, y, yaw = knot
+    d = sgn * ds
+    if abs(kap) < 1e-12:
+        return x + d * math.cos(yaw), y + d * math.sin(yaw), yaw, 0.0
+    xn = x + (math.sin(yaw + kap * d) - math.sin(yaw)) / kap
+    yn = y - (math.cos(yaw + kap * d) - math.cos(yaw)) / kap
+    return xn, yn, yaw + kap * d, math.atan(L * kap)
+
+
+def warmstart_from_segments(x0, segs, N, Ts, L):
+    """Rest-to-rest smoothstep speed profile on every segment; segment durations ~ (length + 1 m)."""
+    knots, total, _ = _integrate_path(x0[0], x0[1], x0[2], segs, L)
+    T = N * Ts
+    w = np.array([k[1] + 1.0 for k in knots]); dur = T * w / w.sum()
+    t_edges = np.concatenate([[0.0], np.cumsum(dur)])
+    tt = np.arange(N + 1) * Ts
+    xWS = np.zeros((N + 1, 4)); uWS = np.zeros((N, 2))
+    for i, t in enumerate(tt):
+        q = min(np.searchsorted(t_edges, t, side="right") - 1, len(knots) - 1)
+        tau = min(max((t - t_edges[q]) / dur[q], 0.0), 1.0)
+        ln, sgn = knots[q][1], knots[q][2]
+        ds = ln * (3 * tau ** 2 - 2 * tau ** 3)
+        v = sgn * ln / dur[q] * 6 * tau * (1 - tau)
+        acc = sgn * ln / dur[q] ** 2 * 6 * (1 - 2 * tau)
+        x, y, yaw, de = _eval_knot(knots[q], ds, L)
+        xWS[i] = [x, y, yaw, v]
+        if i < N:
+            uWS[i] = [de, acc]
+    return xWS, uWS
+
+
+def warmstart_reverse(x0, xF, N, Ts, L, y_e=3.8, R0=4.5):
+    """Warm start for the reverse-parking slot of main.jl:99-108 (goal pose heading +y, slot below y=5)."""
+    X0, Y0 = float(x0[0]), float(x0[1])
+    segs = []
+    if Y0 - y_e >= R0:                      # single reverse arc
+        R = Y0 - y_e
+        x_s = xF[0] + R
+        segs.append((x_s - X0, 0.0))
+        segs.append((-R * (math.pi / 2), -1.0 / R))
+    else:                                   # forward-left arc to heading alpha, then reverse-right arc to pi/2
+        R = R0
+        ca = (Y0 + R - y_e) / (2 * R)
+        alpha = math.acos(min(1.0, ca))
+        x_s = xF[0] + R - 2 * R * math.sin(alpha)
+        segs.append((x_s - X0, 0.0))
+        segs.append((R * alpha, 1.0 / R))
+        segs.append((-R * (math.pi / 2 - alpha), -1.0 / R))
+    segs.append((-(y_e - xF[1]), 0.0))
+    segs = [sg for sg in segs if abs(sg[0]) > 1e-9]
+    xWS, uWS = warmstart_from_segments([X0, Y0, float(x0[2])], segs, N, Ts, L)
+    xWS[0] = x0; xWS[-1] = xF               # exact end poses (main.jl path starts/ends on x0/xF)
+    return xWS[:, 0].copy(), xWS[:, 1].copy(), xWS[:, 2].copy(), xWS, uWS
+
+
+def reverse_parking_batch(B, N=80, seed=0):
+    """BASELINE.json config 2: X0~U(-10,10), Y0~U(6.5,9.5), psi0=v0=0 (ranges of main.jl:165-168)."""
+    sc = reverse_parking_scenario()
+    rng = np.random.default_rng(seed)
+    X0 = rng.uniform(-10, 10, B); Y0 = rng.uniform(6.5, 9.5, B)
+    x0 = np.stack([X0, Y0, np.zeros(B), np.zeros(B)], 1)
+    rx = np.zeros((B, N + 1)); ry = np.zeros((B, N + 1)); ryaw = np.zeros((B, N + 1))
+    xWS = np.zeros((B, N + 1, 4)); uWS = np.zeros((B, N, 2))
+    for i in range(B):
+        rx[i], ry[i], ryaw[i], xWS[i], uWS[i] = warmstart_reverse(x0[i], sc["xF"], N, sc["Ts"], sc["L"])
+    sc.update(B=B, N=N, x0=x0, rx=rx, ry=ry, ryaw=ryaw, xWS=xWS, uWS=uWS)
+    return sc

@@ -1,0 +1,155 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+Restatement of AutonomousParking/DualMultWS.jl:29-86.  The reference model is
+separable: no row couples two different (stage i, obstacle j) pairs
+(DualMultWS.jl:57-75), so it is solved here as (N+1)*nOb independent programs
+
+    max  d = -g'mu + (A_j t_i - b_j)'lam                      (:72-73, objective :52)
+    s.t. (A_j'lam)_1^2 + (A_j'lam)_2^2 <= 1                   (:65)
+         mu1-mu3 + c*p1 + s*p2 = 0, mu2-mu4 - s*p1 + c*p2 = 0  (:68-69)
+         lam >= 0, mu >= 0                                     (:54-55)
+
+two ways: (a) scipy SLSQP on the restated program; (b) closed-form geometry --
+the optimum d* equals the Euclidean distance between the ego rectangle at pose
+i and polyhedron j (0 when they overlap), SURVEY.md section 8c.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.optimize import minimize
+
+
+def ego_geometry(ego):
+    ego = np.asarray(ego, float).ravel()
+    W_ev = ego[1] + ego[3]; L_ev = ego[0] + ego[2]                 # DualMultWS.jl:39-40
+    g = np.array([L_ev / 2, W_ev / 2, L_ev / 2, W_ev / 2])         # :42
+    offset = (ego[0] + ego[2]) / 2 - ego[2]                         # :45
+    return g, offset
+
+
+def solve_one(Aj, bj, pose, g, offset):
+    """SLSQP solve of one (i,j) program; returns lam, mu, d."""
+    v = Aj.shape[0]
+    X, Y, psi = pose
+    c, s = np.cos(psi), np.sin(psi)
+    tc = np.array([X + c * offset, Y + s * offset])
+    rho = Aj @ tc - bj
+
+    def unpack(q):
+        return q[:v], q[v:v + 4]
+
+    def negd(q):
+        lam, mu = unpack(q)
+        return -(-g @ mu + rho @ lam)
+
+    def negd_grad(q):
+        return -np.concatenate([rho, -g])
+
+    def eq(q):
+        lam, mu = unpack(q)
+        p = Aj.T @ lam
+        return np.array([mu[0] - mu[2] + c * p[0] + s * p[1], mu[1] - mu[3] - s * p[0] + c * p[1]])
+
+    def ineq(q):
+        lam, _ = unpack(q)
+        p = Aj.T @ lam
+        return 1.0 - p @ p
+
+    best = None
+    for q0 in (np.zeros(v + 4), np.full(v + 4, 0.3)):
+        r = minimize(negd, q0, jac=negd_grad, method="SLSQP", bounds=[(0, None)] * (v + 4),
+                     constraints=[dict(type="eq", fun=eq), dict(type="ineq", fun=ineq)],
+                     options=dict(ftol=1e-14, maxiter=500))
+        if best is None or r.fun < best.fun - 1e-12:
+            best = r
+    lam, mu = unpack(best.x)
+    return lam, mu, -best.fun
+
+
+def dualmultws(N, nOb, vOb, A, b, rx, ry, ryaw, ego):
+    """Same call surface as DualMultWS.jl:29 (+ explicit ego, a global in the reference, :39).
+    Returns lp (N+1)xsum(vOb), np (N+1)x4nOb (already transposed like :81-84) and d (N+1)xnOb."""
+    vOb = [int(x) for x in np.asarray(vOb).ravel()]
+    A = np.asarray(A, float).reshape(-1, 2); b = np.asarray(b, float).ravel()
+    g, offset = ego_geometry(ego)
+    V = sum(vOb); off = np.concatenate([[0], np.cumsum(vOb)]).astype(int)
+    lp = np.zeros((N + 1, V)); npp = np.zeros((N + 1, 4 * nOb)); d = np.zeros((N + 1, nOb))
+    for i in range(N + 1):
+        for j in range(nOb):
+            lam, mu, dd = solve_one(A[off[j]:off[j + 1]], b[off[j]:off[j + 1]], (rx[i], ry[i], ryaw[i]), g, offset)
+            lp[i, off[j]:off[j + 1]] = lam; npp[i, 4 * j:4 * j + 4] = mu; d[i, j] = dd
+    return lp, npp, d
+
+
+# ------------------------------------------------------------------------------------------
+# closed-form check: distance between the ego rectangle and {y : Aj y <= bj}
+# ------------------------------------------------------------------------------------------
+def _rect_corners(pose, g, offset):
+    X, Y, psi = pose
+    c, s = np.cos(psi), np.sin(psi)
+    ctr = np.array([X + c * offset, Y + s * offset])
+    R = np.array([[c, -s], [s, c]])
+    loc = np.array([[g[0], g[1]], [-g[2], g[1]], [-g[2], -g[3]], [g[0], -g[3]]])
+    return ctr + loc @ R.T
+
+
+def _pt_seg(p, a, b_):
+    ab = b_ - a
+    t = np.clip(((p - a) @ ab) / max(ab @ ab, 1e-300), 0.0, 1.0)
+    return np.linalg.norm(p - (a + t * ab))
+
+
+def _pt_poly_dist(p, Aj, bj, big=1e4):
+    """distance from point to polyhedron {A y <= b} with <=2 rows (half-plane or wedge) or general via projection."""
+    viol = Aj @ p - bj
+    if (viol <= 0).all():
+        return 0.0
+    v = Aj.shape[0]
+    cands = []
+    for r in range(v):                                   # project on each face, keep if feasible
+        a = Aj[r]; q = p - a * (a @ p - bj[r]) / (a @ a)
+        if (Aj @ q - bj <= 1e-9).all():
+            cands.append(np.linalg.norm(p - q))
+    for r1 in range(v):                                  # vertices
+        for r2 in range(r1 + 1, v):
+            M = Aj[[r1, r2]]
+            if abs(np.linalg.det(M)) > 1e-12:
+                q = np.linalg.solve(M, bj[[r1, r2]])
+                if (Aj @ q - bj <= 1e-9).all():
+                    cands.append(np.linalg.norm(p - q))
+    return min(cands)
+
+
+def rect_poly_distance(pose, Aj, bj, g, offset):
+    """min distance rectangle <-> polyhedron; 0 when intersecting.  Vertex-edge enumeration."""
+    C = _rect_corners(pose, g, offset)
+    # intersection test by sampling the rectangle boundary + vertices of the polyhedron inside the rectangle
+    best = min(_pt_poly_dist(c_, Aj, bj) for c_ in C)
+    # polyhedron vertices against rectangle edges
+    v = Aj.shape[0]
+    verts = []
+    for r1 in range(v):
+        for r2 in range(r1 + 1, v):
+            M = Aj[[r1, r2]]
+            if abs(np.linalg.det(M)) > 1e-12:
+                q = np.linalg.solve(M, bj[[r1, r2]])
+                if (Aj @ q - bj <= 1e-9).all():
+                    verts.append(q)
+    X, Y, psi = pose
+    c, s = np.cos(psi), np.sin(psi)
+    ctr = np.array([X + c * offset, Y + s * offset])
+    R = np.array([[c, -s], [s, c]])
+    for q in verts:
+        ql = R.T @ (q - ctr)
+        inside = (-g[2] <= ql[0] <= g[0]) and (-g[3] <= ql[1] <= g[1])
+        if inside:
+            return 0.0
+        for e in range(4):
+            best = min(best, _pt_seg(q, C[e], C[(e + 1) % 4]))
+    # edges crossing: sample rectangle edges densely for feasibility (cheap and adequate for <=2 rows)
+    for e in range(4):
+        for t in np.linspace(0, 1, 33):
+            p = C[e] + t * (C[(e + 1) % 4] - C[e])
+            if (Aj @ p - bj <= 0).all():
+                return 0.0
+    return best

@@ -1,0 +1,108 @@
+"""ctypes loader for the DEVELOPMENT emulation of one solver CTA (tests/emul/emul.cpp).  Test tool only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libobca_emul.so")
+
+
+class IpmOpts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double), ("mu_min", C.c_double),
+                ("kappa_eps", C.c_double), ("kappa_mu", C.c_double), ("theta_mu", C.c_double), ("tau_min", C.c_double),
+                ("kappa1", C.c_double), ("kappa2", C.c_double), ("kappa_sigma", C.c_double), ("s_max", C.c_double),
+                ("dual_inf_tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
+                ("dw_min", C.c_double), ("dw_first", C.c_double), ("dw_max", C.c_double), ("kw_minus", C.c_double),
+                ("kw_plus", C.c_double), ("kw_plus_first", C.c_double),
+                ("gamma_theta", C.c_double), ("gamma_phi", C.c_double), ("delta", C.c_double), ("s_theta", C.c_double),
+                ("s_phi", C.c_double), ("eta_phi", C.c_double), ("gamma_alpha", C.c_double),
+                ("max_backtrack", C.c_int), ("dc", C.c_double)]
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "emul.cpp")] + [os.path.join(HERE, "../../obca_b200/csrc", f)
+                                                for f in os.listdir(os.path.join(HERE, "../../obca_b200/csrc"))
+                                                if f.endswith((".cuh", ".h"))]
+    if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-o", SO,
+                               os.path.join(HERE, "emul.cpp")])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def default_opts():
+    o = IpmOpts()
+    lib().emul_default_opts(C.byref(o))
+    return o
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def solve_batch(sc, fixTime=0, variant="sd", opts=None, lWS=None, nWS=None, dump=False):
+    """sc: dict from obca_b200.scenarios (B, N, x0, xF, rx, ry, ryaw, xWS (B,N+1,4), uWS (B,N,2), ...)."""
+    B, N, nOb = sc["B"], sc["N"], sc["nOb"]
+    NS = N + 1
+    vOb = np.ascontiguousarray(sc["vOb"], dtype=np.int32)
+    V = int(vOb.sum())
+    A = np.asfortranarray(sc["A"], dtype=float); b = np.ascontiguousarray(sc["b"], dtype=float).ravel()
+    x0 = np.ascontiguousarray(sc["x0"], dtype=float)
+    xF = np.ascontiguousarray(np.broadcast_to(sc["xF"], (B, 4)), dtype=float)
+    rx = np.ascontiguousarray(sc["rx"]); ry = np.ascontiguousarray(sc["ry"]); ryaw = np.ascontiguousarray(sc["ryaw"])
+    xWS = np.ascontiguousarray(np.transpose(sc["xWS"], (0, 2, 1)))      # per problem: (N+1)x4 column-major == [4][N+1]
+    uWS = np.ascontiguousarray(np.transpose(sc["uWS"], (0, 2, 1)))      # [2][N]
+    lWSa = np.ascontiguousarray(np.transpose(lWS, (0, 2, 1)))           # (B, NS, V) -> [V][NS]
+    nWSa = np.ascontiguousarray(np.transpose(nWS, (0, 2, 1)))
+    sd = 1 if variant == "sd" else 0
+    xp = np.zeros((B, NS, 4)); up = np.zeros((B, N, 2)); ts = np.zeros((B, NS))
+    lp = np.zeros((B, NS, V)); npp = np.zeros((B, NS, 4 * nOb)); sl = np.zeros((B, NS, nOb))
+    nd = 4 * N + 4 * nOb * NS
+    duals = np.zeros((B, nd))
+    status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32); err = np.zeros(B); nfact = np.zeros(B, np.int32)
+    W = None
+    if dump:
+        tot = lib().emul_layout_total(N, nOb, _p(vOb), sd)
+        W = np.zeros(tot)
+    f = lib().emul_parking_solve_batch
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_double] + [C.c_void_p] * 9 + \
+                 [C.c_int, C.c_int, C.c_void_p] + [C.c_void_p] * 12
+    rc = f(B, N, nOb, _p(vOb), _p(A), _p(b), _p(x0), _p(xF), float(sc["Ts"] if not fixTime else sc.get("Ts_fix", sc["Ts"])),
+           float(sc["L"]), _p(np.ascontiguousarray(sc["ego"], dtype=float)),
+           _p(np.ascontiguousarray(sc["XYbounds"], dtype=float)), _p(rx), _p(ry), _p(ryaw), _p(xWS), _p(uWS), _p(lWSa),
+           _p(nWSa), int(fixTime), sd, C.cast(C.byref(opts), C.c_void_p) if opts is not None else None,
+           _p(xp), _p(up), _p(ts), _p(lp), _p(npp), _p(sl), _p(duals), _p(status), _p(iters), _p(err), _p(nfact), _p(W))
+    assert rc == 0, rc
+    return dict(xp=xp, up=up, ts=ts, lp=lp, np=npp, sl=sl, duals=duals, status=status, iters=iters, err=err,
+                nfact=nfact, W=W)
+
+
+def dualmultws_batch(sc):
+    B, N, nOb = sc["B"], sc["N"], sc["nOb"]
+    NS = N + 1
+    vOb = np.ascontiguousarray(sc["vOb"], dtype=np.int32); V = int(vOb.sum())
+    A = np.asfortranarray(sc["A"], dtype=float); b = np.ascontiguousarray(sc["b"], dtype=float).ravel()
+    lp = np.zeros((B, V, NS)); npp = np.zeros((B, 4 * nOb, NS)); d = np.zeros((B, nOb, NS)); its = np.zeros((B, nOb, NS), np.int32)
+    f = lib().emul_dualmultws_batch
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 11
+    rc = f(B, N, nOb, _p(vOb), _p(A), _p(b), _p(np.ascontiguousarray(sc["ego"], dtype=float)),
+           _p(np.ascontiguousarray(sc["rx"])), _p(np.ascontiguousarray(sc["ry"])), _p(np.ascontiguousarray(sc["ryaw"])),
+           _p(lp), _p(npp), _p(d), _p(its))
+    assert rc == 0
+    # return in (B, NS, V) "row = stage" orientation like DualMultWS.jl:81-84
+    return np.transpose(lp, (0, 2, 1)).copy(), np.transpose(npp, (0, 2, 1)).copy(), np.transpose(d, (0, 2, 1)).copy(), its
