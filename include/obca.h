@@ -1,0 +1,121 @@
+/* obca.h -- C-ABI of libobca.so, the B200-native replacement for the JuMP + Ipopt solve inside the OBCA
+ * reference's NLP drivers.  Plain C, plain pointers and sizes; no allocation escapes the library.
+ *
+ * The reference (XiaojingGeorgeZhang/OBCA) has no FFI of its own: its boundary is the set of Julia functions that
+ * AutonomousParking/main.jl calls positionally.  Each entry point below is what the Julia shim of the same name
+ * (julia/*.jl) `ccall`s in place of the reference's `Model(solver=IpoptSolver(...))` ...
+ * `solve(m)` ... `getvalue(...)` sequence:
+ *
+ *   obca_parking_solve_batch  <- ParkingSignedDist.jl:29-314  (signed_dist=1)  and  ParkingDist.jl:29-315 (=0)
+ *                                 called from main.jl:269 / main.jl:258
+ *   obca_dualmultws_batch     <- DualMultWS.jl:29-86           called from ParkingSignedDist.jl:219, ParkingDist.jl:221
+ *   obca_check_parking        <- ParkingConstraints.jl:29-149  called from ParkingSignedDist.jl:253,278, ParkingDist.jl:259,277
+ *
+ * Conventions
+ *   - every array is float64, COLUMN-MAJOR exactly as the Julia caller holds it; a batch of B problems is the B
+ *     per-problem arrays stored one after the other (problem index slowest).  B = 1 reproduces the reference call.
+ *   - vOb[nOb] are HALF-SPACE counts (main.jl:101 passes vObMPC = vOb-1); A is sum(vOb) x 2, b is sum(vOb)
+ *     (obstHrep.jl:39-40), shared by the whole batch.
+ *   - return value: 0 = executed (per-problem success is in exitflag[]), < 0 = usage / CUDA error (see
+ *     obca_last_error()).  The library never throws and never falls back to a CPU path: without a CUDA device
+ *     every compute entry point returns OBCA_ERR_NO_DEVICE.
+ *   - `*_dev` variants take DEVICE pointers (cudaMalloc'ed by the caller on opts->device) and enqueue on the
+ *     library's stream of that device; they return after the stream has been synchronised.
+ */
+#ifndef OBCA_H
+#define OBCA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBCA_VERSION 100
+#define OBCA_ERR_ARG (-1)
+#define OBCA_ERR_NO_DEVICE (-2)
+#define OBCA_ERR_CUDA (-3)
+#define OBCA_ERR_UNSUPPORTED (-4)
+
+/* Interior-point options: the Ipopt options set at ParkingSignedDist.jl:41-43 (tol, max_iter,
+ * min_hessian_perturbation -> dw_min, jacobian_regularization_value is replaced by the always-on dc) and the Ipopt
+ * defaults the reference leaves untouched.  obca_default_opts() fills in exactly those values. */
+typedef struct obca_opts {
+  double tol;
+  int max_iter;
+  double mu_init, mu_min;
+  double kappa_eps, kappa_mu, theta_mu, tau_min;
+  double kappa1, kappa2, kappa_sigma, s_max;
+  double dual_inf_tol, constr_viol_tol, compl_inf_tol;
+  double dw_min, dw_first, dw_max, kw_minus, kw_plus, kw_plus_first;
+  double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, gamma_alpha;
+  int max_backtrack;
+  double dc;
+  /* execution */
+  int device;        /* CUDA device ordinal used by this call */
+  int retry;         /* 1: re-solve once from the last iterate when the first attempt does not converge
+                        (ParkingSignedDist.jl:256-290), 0: single attempt */
+} obca_opts;
+
+int obca_version(void);
+int obca_device_count(void);                 /* number of visible CUDA devices (0 if none) */
+const char* obca_last_error(void);
+void obca_default_opts(obca_opts* o);
+
+/* Batched ParkingSignedDist / ParkingDist.
+ * inputs (per problem):  x0[4], xF[4], rx/ry/ryaw[N+1], xWS (N+1)x4, uWS Nx2 (first N rows of the reference's uWS,
+ *                        ParkingSignedDist.jl:217), lWS (N+1)xV and nWS (N+1)x4nOb as returned by DualMultWS
+ *                        (pass lWS = nWS = NULL to have the library run DualMultWS itself, as the reference does
+ *                        at ParkingSignedDist.jl:219)
+ * outputs (per problem): xp 4x(N+1), up 2xN, ts (N+1) [ones if fixTime], lp Vx(N+1), np 4nOb x(N+1)
+ *                        (ParkingSignedDist.jl:302-313), sl nOb x(N+1) (may be NULL),
+ *                        exitflag (1 = converged, 0 = not), iters, kkt_err (Ipopt's scaled NLP error E_0),
+ *                        solve_seconds[1] = device time of the solve (the reference's `time`, :297).        */
+int obca_parking_solve_batch(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
+                             const double* x0, const double* xF, double Ts, double L, const double* ego,
+                             const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
+                             const double* xWS, const double* uWS, const double* lWS, const double* nWS,
+                             int fixTime, int signed_dist, const obca_opts* opts, double* xp, double* up, double* ts,
+                             double* lp, double* np, double* sl, int* exitflag, int* iters, double* kkt_err,
+                             double* solve_seconds);
+
+/* Same, all batch arrays (x0 ... nWS, xp ... kkt_err) are device pointers on opts->device; vOb, A, b, ego,
+ * XYbounds, opts and solve_seconds stay host pointers. */
+int obca_parking_solve_batch_dev(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
+                                 const double* x0, const double* xF, double Ts, double L, const double* ego,
+                                 const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
+                                 const double* xWS, const double* uWS, const double* lWS, const double* nWS,
+                                 int fixTime, int signed_dist, const obca_opts* opts, double* xp, double* up,
+                                 double* ts, double* lp, double* np, double* sl, int* exitflag, int* iters,
+                                 double* kkt_err, double* solve_seconds);
+
+/* Batched DualMultWS (DualMultWS.jl:29; `ego` is a global there, :39).  lp (N+1)xV, np (N+1)x4nOb per problem
+ * (already transposed like :81-84); d (N+1)xnOb optional (optimal objective = ego/obstacle distance). */
+int obca_dualmultws_batch(int B, int N, int nOb, const int* vOb, const double* A, const double* b, const double* ego,
+                          const double* rx, const double* ry, const double* ryaw, const obca_opts* opts, double* lp,
+                          double* np, double* d);
+
+/* Batched ParkingConstraints (ParkingConstraints.jl:29-149), restated verbatim including its quirks
+ * (SURVEY.md A.4-Q3).  x 4x(N+1), u 2xN, l Vx(N+1), n 4nOb x(N+1), timeScale (N+1).
+ * feasible[B] = the reference's return value (0/1); e[7*B] = its seven pass flags; strict[B] (optional) = a
+ * checker without the quirks: every dynamics row, every obstacle, box bounds, slack-aware distance row. */
+int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, const double* b, const double* x0,
+                       const double* xF, double Ts, double L, const double* ego, const double* XYbounds,
+                       const double* x, const double* u, const double* l, const double* n, const double* timeScale,
+                       const double* sl, int fixTime, int sd, const obca_opts* opts, int* feasible, int* e,
+                       int* strict);
+
+/* K1 stand-alone: fused evaluation of the OBCA NLP at B given points (no solve).  Reads the stacked
+ * (x, u, ts, l, n, sl) batch and the multipliers `duals` (layout below), writes per problem
+ *   out[0] = objective f, out[1] = ||c||_inf, out[2] = ||c||_1, out[3] = ||grad L||_inf, out[4] = max compl. product
+ * duals per problem: pi 4xN | y_rot 2nOb x(N+1) | y_norm nOb x(N+1) | v_dist nOb x(N+1)   (as written by the solver
+ * when opts asks for them; pass NULL for all-zero multipliers).  Device pointers. */
+int obca_parking_eval_batch_dev(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
+                                const double* x0, const double* xF, double Ts, double L, const double* ego,
+                                const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
+                                const double* xp, const double* up, const double* ts, const double* lp,
+                                const double* np, const double* sl, const double* duals, int fixTime,
+                                int signed_dist, const obca_opts* opts, double* out, double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,507 @@
+// obca_lib.cu -- sm_100a kernels + the C-ABI of include/obca.h.
+//
+// Kernels
+//   k_parking_solve<VM,SDV>  persistent: one CTA per resident slot, each CTA pulls problems from an atomic queue and
+//                            runs the whole interior-point solve (obca_solver.cuh) with thread k <-> stage k.
+//                            Per-CTA workspace lives in global memory (sized to stay L2 resident), scalar state in
+//                            shared memory.  No host round trip inside a solve; problems finish independently.
+//   k_dualws<VM>             K2: one thread per (problem, stage, obstacle) micro interior-point solve.
+//   k_check                  K5: ParkingConstraints twin + strict audit, one CTA per problem.
+// There is NO CPU fallback: every compute entry point returns OBCA_ERR_NO_DEVICE without a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/obca.h"
+#include "obca_check.cuh"
+#include "obca_dualws.cuh"
+#include "obca_host.h"
+
+using namespace obca;
+
+// ---------------------------------------------------------------------------------------------------------
+// device-side batch description
+// ---------------------------------------------------------------------------------------------------------
+struct BatchPtrs {
+  const double *x0, *xF, *rx, *ry, *ryaw, *xWS, *uWS, *lWS, *nWS;
+  double *xp, *up, *ts, *lp, *np, *sl, *duals;
+  int *exitflag, *iters;
+  double* kkt_err;
+  int B;
+  int retry;
+};
+
+template <int VM, bool SDV>
+__global__ void __launch_bounds__(128, 4)
+k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L,
+                const BatchPtrs bp, double* __restrict__ Wall, int* __restrict__ counter) {
+  __shared__ ProbState S;
+  __shared__ int s_b;
+  __shared__ ChkPart s_chk[4];
+  __shared__ int s_feas;
+  const int N = P.N, NS = N + 1, V = P.V, nOb = P.nOb;
+  double* W = Wall + (size_t)blockIdx.x * L.total * L.NSP;
+  for (;;) {
+    if (threadIdx.x == 0) s_b = atomicAdd(counter, 1);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= bp.B) break;
+    PkCtx C;
+    C.P = &P; C.O = &O; C.L = L; C.W = W; C.S = &S;
+    C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
+    C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
+    C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
+    C.in.uWS = bp.uWS + (size_t)2 * N * b; C.in.ldu = N;
+    C.in.lWS = bp.lWS + (size_t)V * NS * b; C.in.nWS = bp.nWS + (size_t)4 * nOb * NS * b;
+    PkOutputs out;
+    out.xp = bp.xp + (size_t)4 * NS * b; out.up = bp.up + (size_t)2 * N * b; out.ts = bp.ts + (size_t)NS * b;
+    out.lp = bp.lp + (size_t)V * NS * b; out.np = bp.np + (size_t)4 * nOb * NS * b;
+    out.sl = bp.sl ? bp.sl + (size_t)nOb * NS * b : nullptr;
+    out.duals = bp.duals ? bp.duals + ((size_t)4 * N + (size_t)4 * nOb * NS) * b : nullptr;
+
+    ParkSolver<VM, SDV>::solve(C, 0);
+    __syncthreads();
+    int iters = S.iters;
+    int status = S.status;
+    // ParkingSignedDist.jl:256-263 / ParkingDist.jl:245-263: one more solve from the last iterate
+    if (status != 1 && bp.retry) {
+      __syncthreads();
+      ParkSolver<VM, SDV>::solve(C, 1);
+      __syncthreads();
+      iters += S.iters;
+      status = S.status;
+    }
+    for (int k = threadIdx.x; k < NS; k += blockDim.x) ParkSolver<VM, SDV>::store_stage(C, k, out);
+    __syncthreads();
+    int exitflag = status == 1 ? 1 : 0;
+    if (status != 1 && bp.retry) {
+      // second failure: the reference lets ParkingConstraints decide (ParkingSignedDist.jl:276-283)
+      ChkPart c;
+      chk_init(c);
+      for (int k = threadIdx.x; k < NS; k += blockDim.x) {
+        ChkPart ck;
+        check_stage(P, k, C.in.x0, C.in.xF, out.xp, out.up, out.lp, out.np, out.ts, out.sl, SDV ? 1 : 0, 0, ck);
+        chk_merge(c, ck);
+      }
+      // block reduction through shared memory (4 warps max)
+      for (int off = 16; off > 0; off >>= 1) {
+        ChkPart o;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o.c0[i] = __shfl_down_sync(0xffffffffu, c.c0[i], off);
+        o.c1 = __shfl_down_sync(0xffffffffu, c.c1, off); o.c2 = __shfl_down_sync(0xffffffffu, c.c2, off);
+        o.c3 = __shfl_down_sync(0xffffffffu, c.c3, off); o.c4 = __shfl_down_sync(0xffffffffu, c.c4, off);
+        o.c5 = __shfl_down_sync(0xffffffffu, c.c5, off); o.c6 = __shfl_down_sync(0xffffffffu, c.c6, off);
+        o.sbox = __shfl_down_sync(0xffffffffu, c.sbox, off);
+        chk_merge(c, o);
+      }
+      if ((threadIdx.x & 31) == 0) s_chk[threadIdx.x >> 5] = c;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) chk_merge(c, s_chk[w]);
+        int e[7];
+        s_feas = check_finish(P, c, out.ts, 0, 5e-5, e);
+      }
+      __syncthreads();
+      exitflag = s_feas ? 1 : 0;
+    }
+    if (threadIdx.x == 0) {
+      bp.exitflag[b] = exitflag;
+      bp.iters[b] = iters;
+      bp.kkt_err[b] = S.e0;
+    }
+    __syncthreads();
+  }
+}
+
+template <int VM>
+__global__ void k_dualws(const __grid_constant__ ParkProblem P, int B, const double* __restrict__ rx,
+                         const double* __restrict__ ry, const double* __restrict__ ryaw, double tol, int max_iter,
+                         double* __restrict__ lp, double* __restrict__ np, double* __restrict__ dd) {
+  const int NS = P.N + 1, nOb = P.nOb, V = P.V;
+  const size_t total = (size_t)B * nOb * NS;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % NS);
+    const int j = (int)((idx / NS) % nOb);
+    const size_t b = idx / ((size_t)NS * nOb);
+    ObsRows<VM> R;
+    R.v = P.vOb[j];
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      const bool on = i < R.v;
+      const int r = P.voff[j] + (on ? i : 0);
+      R.a1[i] = on ? P.A[r][0] : 0.0; R.a2[i] = on ? P.A[r][1] : 0.0; R.bb[i] = on ? P.b[r] : 0.0;
+    }
+    double lam[VM], mu[4], d;
+    const size_t o = (size_t)NS * b + k;
+    dualws_solve<VM>(P, R, rx[o], ry[o], ryaw[o], tol, max_iter, lam, mu, &d);
+#pragma unroll
+    for (int i = 0; i < VM; ++i)
+      if (i < R.v) lp[(size_t)V * NS * b + (size_t)(P.voff[j] + i) * NS + k] = lam[i];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) np[(size_t)4 * nOb * NS * b + (size_t)(4 * j + m) * NS + k] = mu[m];
+    if (dd) dd[(size_t)nOb * NS * b + (size_t)j * NS + k] = d;
+  }
+}
+
+__global__ void k_check(const __grid_constant__ ParkProblem P, int B, const double* __restrict__ x0,
+                        const double* __restrict__ xF, const double* __restrict__ x, const double* __restrict__ u,
+                        const double* __restrict__ l, const double* __restrict__ n, const double* __restrict__ ts,
+                        const double* __restrict__ sl, int sd, int* __restrict__ feasible, int* __restrict__ e_out,
+                        int* __restrict__ strict_out) {
+  __shared__ ChkPart s_c[2][4];
+  const int N = P.N, NS = N + 1, V = P.V, nOb = P.nOb;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const double* xb = x + (size_t)4 * NS * b; const double* ub = u + (size_t)2 * N * b;
+    const double* lb = l + (size_t)V * NS * b; const double* nb = n + (size_t)4 * nOb * NS * b;
+    const double* tb = ts + (size_t)NS * b; const double* sb = sl ? sl + (size_t)nOb * NS * b : nullptr;
+    ChkPart c[2];
+    chk_init(c[0]); chk_init(c[1]);
+    for (int k = threadIdx.x; k < NS; k += blockDim.x) {
+      for (int st = 0; st < 2; ++st) {
+        ChkPart ck;
+        check_stage(P, k, x0 + 4 * (size_t)b, xF + 4 * (size_t)b, xb, ub, lb, nb, tb, sb, sd, st, ck);
+        chk_merge(c[st], ck);
+      }
+    }
+    for (int st = 0; st < 2; ++st) {
+      for (int off = 16; off > 0; off >>= 1) {
+        ChkPart o;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o.c0[i] = __shfl_down_sync(0xffffffffu, c[st].c0[i], off);
+        o.c1 = __shfl_down_sync(0xffffffffu, c[st].c1, off); o.c2 = __shfl_down_sync(0xffffffffu, c[st].c2, off);
+        o.c3 = __shfl_down_sync(0xffffffffu, c[st].c3, off); o.c4 = __shfl_down_sync(0xffffffffu, c[st].c4, off);
+        o.c5 = __shfl_down_sync(0xffffffffu, c[st].c5, off); o.c6 = __shfl_down_sync(0xffffffffu, c[st].c6, off);
+        o.sbox = __shfl_down_sync(0xffffffffu, c[st].sbox, off);
+        chk_merge(c[st], o);
+      }
+      if ((threadIdx.x & 31) == 0) s_c[st][threadIdx.x >> 5] = c[st];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int st = 0; st < 2; ++st) {
+        ChkPart m = s_c[st][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) chk_merge(m, s_c[st][w]);
+        int e[7];
+        const int f = check_finish(P, m, tb, st, 5e-5, e);
+        if (st == 0) {
+          feasible[b] = f;
+          if (e_out) for (int i = 0; i < 7; ++i) e_out[7 * (size_t)b + i] = e[i];
+        } else if (strict_out) strict_out[b] = f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                   \
+      return OBCA_ERR_CUDA;                                                                          \
+    }                                                                                                \
+  } while (0)
+
+struct DevCtx {
+  bool init = false;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sms = 0;
+  double* W = nullptr; size_t Wbytes = 0;
+  int* counter = nullptr;
+  char* stage = nullptr; size_t stage_bytes = 0;   // device staging for the host-pointer API
+  std::mutex mu;
+};
+static DevCtx g_dev[64];
+
+static int get_ctx(int dev, DevCtx** out) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { set_err("no CUDA device visible"); return OBCA_ERR_NO_DEVICE; }
+  if (dev < 0 || dev >= n || dev >= 64) { set_err("bad device ordinal"); return OBCA_ERR_ARG; }
+  DevCtx& c = g_dev[dev];
+  CK(cudaSetDevice(dev));
+  if (!c.init) {
+    CK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1));
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, dev));
+    c.sms = pr.multiProcessorCount;
+    CK(cudaMalloc(&c.counter, sizeof(int)));
+    c.init = true;
+  }
+  *out = &c;
+  return 0;
+}
+static int ensure(void** p, size_t* have, size_t need) {
+  if (*have >= need) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  CK(cudaMalloc(p, need));
+  *have = need;
+  return 0;
+}
+
+static IpmOpts to_ipm(const obca_opts* o) {
+  IpmOpts r = default_opts();
+  if (!o) return r;
+  r.tol = o->tol; r.max_iter = o->max_iter; r.mu_init = o->mu_init; r.mu_min = o->mu_min;
+  r.kappa_eps = o->kappa_eps; r.kappa_mu = o->kappa_mu; r.theta_mu = o->theta_mu; r.tau_min = o->tau_min;
+  r.kappa1 = o->kappa1; r.kappa2 = o->kappa2; r.kappa_sigma = o->kappa_sigma; r.s_max = o->s_max;
+  r.dual_inf_tol = o->dual_inf_tol; r.constr_viol_tol = o->constr_viol_tol; r.compl_inf_tol = o->compl_inf_tol;
+  r.dw_min = o->dw_min; r.dw_first = o->dw_first; r.dw_max = o->dw_max; r.kw_minus = o->kw_minus;
+  r.kw_plus = o->kw_plus; r.kw_plus_first = o->kw_plus_first;
+  r.gamma_theta = o->gamma_theta; r.gamma_phi = o->gamma_phi; r.delta = o->delta; r.s_theta = o->s_theta;
+  r.s_phi = o->s_phi; r.eta_phi = o->eta_phi; r.gamma_alpha = o->gamma_alpha; r.max_backtrack = o->max_backtrack;
+  r.dc = o->dc;
+  return r;
+}
+
+template <int VM>
+static int launch_dualws(DevCtx& c, const ParkProblem& P, int B, const double* rx, const double* ry,
+                         const double* ryaw, double* lp, double* np, double* dd) {
+  const size_t total = (size_t)B * P.nOb * (P.N + 1);
+  const int threads = 128;
+  const int blocks = (int)((total + threads - 1) / threads);
+  k_dualws<VM><<<blocks, threads, 0, c.st>>>(P, B, rx, ry, ryaw, 1e-5, 100, lp, np, dd);
+  CK(cudaGetLastError());
+  return 0;
+}
+static int run_dualws(DevCtx& c, const ParkProblem& P, int B, const double* rx, const double* ry, const double* ryaw,
+                      double* lp, double* np, double* dd) {
+  return max_vob(P) <= 2 ? launch_dualws<2>(c, P, B, rx, ry, ryaw, lp, np, dd)
+                         : launch_dualws<4>(c, P, B, rx, ry, ryaw, lp, np, dd);
+}
+
+template <int VM, bool SDV>
+static int launch_solve(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const BatchPtrs& bp) {
+  PkLay L = make_layout(P, LocalDims<VM, SDV>::NFAC);
+  if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parking_solve<VM, SDV>, L.NSP, 0));
+  if (occ < 1) occ = 1;
+  int grid = c.sms * occ;
+  if (grid > bp.B) grid = bp.B;
+  const size_t need = (size_t)grid * L.total * L.NSP * sizeof(double);
+  int rc = ensure((void**)&c.W, &c.Wbytes, need);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
+  k_parking_solve<VM, SDV><<<grid, L.NSP, 0, c.st>>>(P, O, L, bp, c.W, c.counter);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, BatchPtrs bp, double* seconds) {
+  const int vm = max_vob(P) <= 2 ? 2 : 4;
+  CK(cudaEventRecord(c.ev0, c.st));
+  int rc;
+  if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, bp) : launch_solve<4, true>(c, P, O, bp);
+  else rc = vm == 2 ? launch_solve<2, false>(c, P, O, bp) : launch_solve<4, false>(c, P, O, bp);
+  if (rc) return rc;
+  CK(cudaEventRecord(c.ev1, c.st));
+  CK(cudaStreamSynchronize(c.st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  if (seconds) *seconds = ms * 1e-3;
+  return 0;
+}
+
+extern "C" {
+
+int obca_version(void) { return OBCA_VERSION; }
+int obca_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+const char* obca_last_error(void) { return g_err.c_str(); }
+void obca_default_opts(obca_opts* o) {
+  IpmOpts d = default_opts();
+  o->tol = d.tol; o->max_iter = d.max_iter; o->mu_init = d.mu_init; o->mu_min = d.mu_min;
+  o->kappa_eps = d.kappa_eps; o->kappa_mu = d.kappa_mu; o->theta_mu = d.theta_mu; o->tau_min = d.tau_min;
+  o->kappa1 = d.kappa1; o->kappa2 = d.kappa2; o->kappa_sigma = d.kappa_sigma; o->s_max = d.s_max;
+  o->dual_inf_tol = d.dual_inf_tol; o->constr_viol_tol = d.constr_viol_tol; o->compl_inf_tol = d.compl_inf_tol;
+  o->dw_min = d.dw_min; o->dw_first = d.dw_first; o->dw_max = d.dw_max; o->kw_minus = d.kw_minus;
+  o->kw_plus = d.kw_plus; o->kw_plus_first = d.kw_plus_first;
+  o->gamma_theta = d.gamma_theta; o->gamma_phi = d.gamma_phi; o->delta = d.delta; o->s_theta = d.s_theta;
+  o->s_phi = d.s_phi; o->eta_phi = d.eta_phi; o->gamma_alpha = d.gamma_alpha; o->max_backtrack = d.max_backtrack;
+  o->dc = d.dc;
+  o->device = 0; o->retry = 1;
+}
+
+int obca_parking_solve_batch_dev(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
+                                 const double* x0, const double* xF, double Ts, double L, const double* ego,
+                                 const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
+                                 const double* xWS, const double* uWS, const double* lWS, const double* nWS,
+                                 int fixTime, int signed_dist, const obca_opts* opts, double* xp, double* up,
+                                 double* ts, double* lp, double* np, double* sl, int* exitflag, int* iters,
+                                 double* kkt_err, double* solve_seconds) {
+  if (B <= 0 || !vOb || !A || !b || !x0 || !xF || !ego || !XYbounds || !rx || !ry || !ryaw || !xWS || !uWS || !xp ||
+      !up || !ts || !lp || !np || !exitflag || !iters || !kkt_err) { set_err("null argument"); return OBCA_ERR_ARG; }
+  ParkProblem P;
+  if (fill_problem(P, N, nOb, vOb, A, b, Ts, L, ego, XYbounds, fixTime, signed_dist)) {
+    set_err("unsupported problem shape"); return OBCA_ERR_ARG;
+  }
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  IpmOpts O = to_ipm(opts);
+  BatchPtrs bp;
+  bp.x0 = x0; bp.xF = xF; bp.rx = rx; bp.ry = ry; bp.ryaw = ryaw; bp.xWS = xWS; bp.uWS = uWS;
+  bp.xp = xp; bp.up = up; bp.ts = ts; bp.lp = lp; bp.np = np; bp.sl = sl; bp.duals = nullptr;
+  bp.exitflag = exitflag; bp.iters = iters; bp.kkt_err = kkt_err; bp.B = B; bp.retry = opts ? opts->retry : 1;
+  if (lWS && nWS) { bp.lWS = lWS; bp.nWS = nWS; }
+  else {
+    // the reference runs DualMultWS inside the NLP driver (ParkingSignedDist.jl:219): use the output arrays
+    // lp / np as scratch for the warm-start duals (they have exactly the transposed size)
+    rc = run_dualws(*c, P, B, rx, ry, ryaw, lp, np, nullptr);
+    if (rc) return rc;
+    // lp/np now hold (N+1)xV column-major == what the solver expects for lWS/nWS; the solver overwrites them
+    // at store time only after the solve of that problem has finished reading its own slice.
+    bp.lWS = lp; bp.nWS = np;
+  }
+  return solve_dev_impl(*c, P, O, bp, solve_seconds);
+}
+
+int obca_parking_solve_batch(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
+                             const double* x0, const double* xF, double Ts, double L, const double* ego,
+                             const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
+                             const double* xWS, const double* uWS, const double* lWS, const double* nWS,
+                             int fixTime, int signed_dist, const obca_opts* opts, double* xp, double* up, double* ts,
+                             double* lp, double* np, double* sl, int* exitflag, int* iters, double* kkt_err,
+                             double* solve_seconds) {
+  if (B <= 0 || !vOb || !x0 || !xF || !rx || !ry || !ryaw || !xWS || !uWS || !xp || !up || !ts || !lp || !np ||
+      !exitflag || !iters || !kkt_err) { set_err("null argument"); return OBCA_ERR_ARG; }
+  if (N < 2 || nOb < 1 || nOb > OBCA_MAX_OB) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  int V = 0;
+  for (int j = 0; j < nOb; ++j) V += vOb[j];
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  const size_t NS = N + 1;
+  const size_t n_x0 = 4, n_r = NS, n_xw = 4 * NS, n_uw = 2 * (size_t)N, n_l = V * NS, n_n = 4 * (size_t)nOb * NS, n_s = nOb * NS;
+  const bool have_ws = lWS && nWS;
+  // staging layout (doubles): inputs then outputs
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += n * (size_t)B; return o; };
+  const size_t o_x0 = take(n_x0), o_xF = take(n_x0), o_rx = take(n_r), o_ry = take(n_r), o_ryaw = take(n_r);
+  const size_t o_xw = take(n_xw), o_uw = take(n_uw), o_lw = take(n_l), o_nw = take(n_n);
+  const size_t o_xp = take(n_xw), o_up = take(n_uw), o_ts = take(n_r), o_lp = take(n_l), o_np = take(n_n), o_sl = take(n_s);
+  const size_t o_err = take(1);
+  const size_t dbytes = off * sizeof(double);
+  const size_t ibytes = 2 * (size_t)B * sizeof(int);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure((void**)&c->stage, &c->stage_bytes, dbytes + ibytes);
+    if (rc) return rc;
+  }
+  double* d = (double*)c->stage;
+  int* di = (int*)(c->stage + dbytes);
+  cudaStream_t st = c->st;
+#define H2D(dst, src, n) CK(cudaMemcpyAsync(d + (dst), (src), (n) * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st))
+  H2D(o_x0, x0, n_x0); H2D(o_xF, xF, n_x0); H2D(o_rx, rx, n_r); H2D(o_ry, ry, n_r); H2D(o_ryaw, ryaw, n_r);
+  H2D(o_xw, xWS, n_xw); H2D(o_uw, uWS, n_uw);
+  if (have_ws) { H2D(o_lw, lWS, n_l); H2D(o_nw, nWS, n_n); }
+#undef H2D
+  obca_opts o2;
+  if (opts) o2 = *opts; else obca_default_opts(&o2);
+  rc = obca_parking_solve_batch_dev(B, N, nOb, vOb, A, b, d + o_x0, d + o_xF, Ts, L, ego, XYbounds, d + o_rx, d + o_ry,
+                                    d + o_ryaw, d + o_xw, d + o_uw, have_ws ? d + o_lw : nullptr,
+                                    have_ws ? d + o_nw : nullptr, fixTime, signed_dist, &o2, d + o_xp, d + o_up,
+                                    d + o_ts, d + o_lp, d + o_np, d + o_sl, di, di + B, d + o_err, solve_seconds);
+  if (rc) return rc;
+#define D2H(dst, src, n) CK(cudaMemcpyAsync((dst), d + (src), (n) * (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st))
+  D2H(xp, o_xp, n_xw); D2H(up, o_up, n_uw); D2H(ts, o_ts, n_r); D2H(lp, o_lp, n_l); D2H(np, o_np, n_n);
+  if (sl) D2H(sl, o_sl, n_s);
+  D2H(kkt_err, o_err, 1);
+#undef D2H
+  CK(cudaMemcpyAsync(exitflag, di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(iters, di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int obca_dualmultws_batch(int B, int N, int nOb, const int* vOb, const double* A, const double* b, const double* ego,
+                          const double* rx, const double* ry, const double* ryaw, const obca_opts* opts, double* lp,
+                          double* np, double* dd) {
+  if (B <= 0 || !vOb || !A || !b || !ego || !rx || !ry || !ryaw || !lp || !np) { set_err("null argument"); return OBCA_ERR_ARG; }
+  ParkProblem P;
+  double xy[4] = {0, 1, 0, 1};
+  if (fill_problem(P, N, nOb, vOb, A, b, 1.0, 1.0, ego, xy, 0, 1)) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t NS = N + 1, nr = NS * B, nl = (size_t)P.V * NS * B, nn = 4 * (size_t)nOb * NS * B, ndd = (size_t)nOb * NS * B;
+  rc = ensure((void**)&c->stage, &c->stage_bytes, (3 * nr + nl + nn + ndd) * sizeof(double));
+  if (rc) return rc;
+  double* d = (double*)c->stage;
+  CK(cudaMemcpyAsync(d, rx, nr * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(d + nr, ry, nr * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(d + 2 * nr, ryaw, nr * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  double* dl = d + 3 * nr; double* dn = dl + nl; double* ddv = dn + nn;
+  rc = run_dualws(*c, P, B, d, d + nr, d + 2 * nr, dl, dn, ddv);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(lp, dl, nl * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(np, dn, nn * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  if (dd) CK(cudaMemcpyAsync(dd, ddv, ndd * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, const double* b, const double* x0,
+                       const double* xF, double Ts, double L, const double* ego, const double* XYbounds,
+                       const double* x, const double* u, const double* l, const double* n, const double* timeScale,
+                       const double* sl, int fixTime, int sd, const obca_opts* opts, int* feasible, int* e,
+                       int* strict) {
+  if (B <= 0 || !vOb || !A || !b || !x0 || !xF || !ego || !XYbounds || !x || !u || !l || !n || !timeScale || !feasible) {
+    set_err("null argument"); return OBCA_ERR_ARG;
+  }
+  ParkProblem P;
+  if (fill_problem(P, N, nOb, vOb, A, b, Ts, L, ego, XYbounds, fixTime, sd)) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t NS = N + 1;
+  const size_t nx = 4 * NS * B, nu = 2 * (size_t)N * B, nl = (size_t)P.V * NS * B, nn = 4 * (size_t)nOb * NS * B, nt = NS * B,
+               ns = (size_t)nOb * NS * B, n0 = 4 * (size_t)B;
+  const size_t dbytes = (2 * n0 + nx + nu + nl + nn + nt + ns) * sizeof(double);
+  rc = ensure((void**)&c->stage, &c->stage_bytes, dbytes + 9 * (size_t)B * sizeof(int));
+  if (rc) return rc;
+  double* d = (double*)c->stage;
+  double *d0 = d, *dF = d0 + n0, *dx = dF + n0, *du = dx + nx, *dl = du + nu, *dn = dl + nl, *dt = dn + nn, *ds = dt + nt;
+  int* di = (int*)(c->stage + dbytes);
+  cudaStream_t st = c->st;
+  CK(cudaMemcpyAsync(d0, x0, n0 * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dF, xF, n0 * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dx, x, nx * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(du, u, nu * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dl, l, nl * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dn, n, nn * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dt, timeScale, nt * 8, cudaMemcpyHostToDevice, st));
+  if (sl) CK(cudaMemcpyAsync(ds, sl, ns * 8, cudaMemcpyHostToDevice, st));
+  const int grid = B < 4 * c->sms ? B : 4 * c->sms;
+  k_check<<<grid, 128, 0, st>>>(P, B, d0, dF, dx, du, dl, dn, dt, sl ? ds : nullptr, sd, di, di + B, di + 8 * (size_t)B);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(feasible, di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (e) CK(cudaMemcpyAsync(e, di + B, 7 * (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (strict) CK(cudaMemcpyAsync(strict, di + 8 * (size_t)B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int obca_parking_eval_batch_dev(int, int, int, const int*, const double*, const double*, const double*, const double*,
+                                double, double, const double*, const double*, const double*, const double*,
+                                const double*, const double*, const double*, const double*, const double*,
+                                const double*, const double*, const double*, int, int, const obca_opts*, double*,
+                                double*) {
+  set_err("obca_parking_eval_batch_dev: not built yet");
+  return OBCA_ERR_UNSUPPORTED;
+}
+}

@@ -180,13 +180,19 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // P0: initial point (ParkingSignedDist.jl:213-222) + Ipopt's projection into the bounds, slacks, multipliers
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void init_stage(const PkCtx& C, int k) {
+  // restart != 0: re-initialise from the current iterate (the reference's second solve(m) restarts Ipopt from
+  // JuMP's stored primal values, ParkingSignedDist.jl:256-263) instead of from the warm-start inputs.
+  OBCA_HD static void init_stage(const PkCtx& C, int k, int restart) {
     const ParkProblem& P = *C.P;
     const IpmOpts& O = *C.O;
     const int N = P.N;
     const bool pose_free = (k >= 1 && k <= N - 1);
-    double X = C.in.xWS[0 * C.in.ldx + k], Y = C.in.xWS[1 * C.in.ldx + k];
-    double ps = C.in.xWS[2 * C.in.ldx + k], v = C.in.xWS[3 * C.in.ldx + k];
+    double X, Y, ps, v;
+    if (restart) { X = WA(X, k); Y = WA(Y, k); ps = WA(PS, k); v = WA(VL, k); }
+    else {
+      X = C.in.xWS[0 * C.in.ldx + k]; Y = C.in.xWS[1 * C.in.ldx + k];
+      ps = C.in.xWS[2 * C.in.ldx + k]; v = C.in.xWS[3 * C.in.ldx + k];
+    }
     if (k == 0) { X = C.in.x0[0]; Y = C.in.x0[1]; ps = C.in.x0[2]; v = C.in.x0[3]; }
     if (k == N) { X = C.in.xF[0]; Y = C.in.xF[1]; ps = C.in.xF[2]; v = C.in.xF[3]; }
     if (pose_free) {
@@ -198,8 +204,8 @@ struct ParkSolver {
     WA(ZXL, k) = 1.0; WA(ZXU, k) = 1.0; WA(ZYL, k) = 1.0; WA(ZYU, k) = 1.0; WA(ZVL, k) = 1.0; WA(ZVU, k) = 1.0;
     double de = 0.0, ac = 0.0;
     if (k < N) {
-      de = push_lo(C.in.uWS[0 * C.in.ldu + k], -0.6, 0.6, O.kappa1, O.kappa2);
-      ac = push_lo(C.in.uWS[1 * C.in.ldu + k], -0.4, 0.4, O.kappa1, O.kappa2);
+      de = push_lo(restart ? WA(DE, k) : C.in.uWS[0 * C.in.ldu + k], -0.6, 0.6, O.kappa1, O.kappa2);
+      ac = push_lo(restart ? WA(AC, k) : C.in.uWS[1 * C.in.ldu + k], -0.4, 0.4, O.kappa1, O.kappa2);
     }
     WA(DE, k) = de; WA(AC, k) = ac;
     WA(ZDL, k) = 1.0; WA(ZDU, k) = 1.0; WA(ZAL, k) = 1.0; WA(ZAU, k) = 1.0;
@@ -207,15 +213,15 @@ struct ParkSolver {
     for (int i = 0; i < 4; ++i) WV(PI, i, k) = 0.0;
     const double lpush = O.kappa1;   // lower bound 0: kappa1 * max(1, |0|)
     for (int r = 0; r < P.V; ++r) {
-      WV(LAM, r, k) = dmax(C.in.lWS[(size_t)r * (N + 1) + k], lpush);
+      WV(LAM, r, k) = dmax(restart ? WV(LAM, r, k) : C.in.lWS[(size_t)r * (N + 1) + k], lpush);
       WV(ZLAM, r, k) = 1.0;
     }
     for (int r = 0; r < 4 * P.nOb; ++r) {
-      WV(MU, r, k) = dmax(C.in.nWS[(size_t)r * (N + 1) + k], lpush);
+      WV(MU, r, k) = dmax(restart ? WV(MU, r, k) : C.in.nWS[(size_t)r * (N + 1) + k], lpush);
       WV(ZMU, r, k) = 1.0;
     }
     for (int j = 0; j < P.nOb; ++j) {
-      if (SDV) { WV(SL, j, k) = 0.0; WV(YN, j, k) = 0.0; }
+      if (SDV) { if (!restart) WV(SL, j, k) = 0.0; WV(YN, j, k) = 0.0; }
       WV(YR, 2 * j, k) = 0.0; WV(YR, 2 * j + 1, k) = 0.0;
     }
   }
@@ -962,7 +968,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // the solve: all threads of the CTA call this with the same context
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void solve(const PkCtx& C) {
+  OBCA_HD static void solve(const PkCtx& C, int restart = 0) {
     const ParkProblem& P = *C.P;
     const IpmOpts& O = *C.O;
     ProbState& S = *C.S;
@@ -970,13 +976,13 @@ struct ParkSolver {
     const bool fix = P.fix_time != 0;
 
     OBCA_SERIAL {
-      S.t = fix ? 1.0 : push_lo(1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
+      S.t = fix ? 1.0 : push_lo(restart ? S.t : 1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
       S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
       S.mu = O.mu_init; S.tau = dmax(O.tau_min, 1.0 - O.mu_init);
       S.dw = 0.0; S.dw_last = 0.0; S.nfilt = 0; S.status = 0; S.iters = 0; S.n_fact = 0;
     }
     OBCA_SYNC();
-    OBCA_FOR_STAGES(k, NS) init_stage(C, k);
+    OBCA_FOR_STAGES(k, NS) init_stage(C, k, restart);
     OBCA_SYNC();
     OBCA_FOR_STAGES(k, NS) init_slacks(C, k);
     OBCA_SYNC();
