@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- OBCA trajectories/sec on BASELINE config 2 (reverse parking, N=80, 3 obstacles, batch 4096 per GPU).
+
+A "step" = one pass of the hot path over one batch of synthetic problems: DualMultWS (K2) + the batched
+interior-point solve (K1/K3/K4 fused in the persistent kernel) of ParkingSignedDist for B randomised start poses.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); the batch is sharded by rank (weak scaling: B per GPU),
+nothing is exchanged on the solve path, one all-reduce carries the counters.  Rank 0 prints ONE JSON line.
+
+  value      converged trajectories / s, inputs resident in HBM, device time from CUDA events on the library's
+             stream (max over ranks)
+  e2e        same metric through the reference-facing C-ABI call with pinned HOST buffers (H2D + D2H inside)
+  roofline   dominant kernel (k_parking_solve) against the measured HBM peak, algorithmic bytes of SURVEY 8(d)
+  cpu_baseline / --impl reference : the oracle port (IPOPT stand-in, oracle/ipm_ref.py sparse path) on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_HORIZON = 80
+WORKLOAD = "reverse-parking SD var-time, N=80, 3 obstacles vOb=[2,2,1] (BASELINE config 2)"
+# fused K1 (J/H never reach HBM): 8*(2n+2m+n_par), n=2185, m=1460, n_par=243
+ALG_BYTES_PER_EVAL = 8 * (2 * 2185 + 2 * 1460 + 243)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_solve_one(args):
+    i, seed = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"; os.environ["OMP_NUM_THREADS"] = "1"
+    from obca_b200.scenarios import reverse_parking_batch
+    from oracle import ipm_ref
+    from oracle.parking_solve import solve_parking
+    sc = _cpu_solve_one.sc if hasattr(_cpu_solve_one, "sc") else reverse_parking_batch(64, N_HORIZON, seed)
+    _cpu_solve_one.sc = sc
+    t0 = time.time()
+    out, res, _ = solve_parking(sc["x0"][i], sc["xF"], N_HORIZON, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"],
+                                sc["vOb"], sc["A"], sc["b"], sc["rx"][i], sc["ry"][i], sc["ryaw"][i], 0, sc["xWS"][i],
+                                sc["uWS"][i], "sd", None, None, ipm_ref.IpmOptions(linsolve="sparse"))
+    return int(res.status == 1), res.iters, time.time() - t0
+
+
+def cpu_arm(n_problems, cores):
+    """Oracle port (IPOPT stand-in: same NLP, same warm starts, tol 1e-5, max_iter 200; includes DualMultWS and the
+    model build, like one call of ParkingSignedDist) on `cores` worker processes."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_solve_one, [(i % 64, 0) for i in range(n_problems)], chunksize=1)
+    wall = time.time() - t0
+    conv = sum(r[0] for r in res)
+    return conv / wall, wall, conv, float(np.mean([r[1] for r in res])), float(np.mean([r[2] for r in res]))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = cores
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_arm(cores, cores)
+    t0 = time.time(); conv = 0; its = []
+    for _ in range(args.steps):
+        v, wall, c, it, _ = cpu_arm(per_step, cores)
+        conv += c; its.append(it)
+    wall = time.time() - t0
+    val = conv / wall
+    line = {"impl": "reference", "metric": "OBCA trajs/sec, reverse-parking N=80 3-obs batch", "value": val, "unit": "traj/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": "traj/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} problems/step of the same batch (seed 0), one per worker process; "
+                                       "oracle/ipm_ref.py sparse LDL' path = IPOPT stand-in, not IPOPT"},
+            "e2e": {"value": val, "unit": "traj/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev = dev; self.stop = False; self.sm = []; self.reasons = set(); self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def gpu_arm(args):
+    import torch
+    import obca_b200
+    from obca_b200 import scenarios
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = obca_b200.lib()
+    B, N, NS = args.batch, N_HORIZON, N_HORIZON + 1
+    sc = scenarios.reverse_parking_batch(B, N, seed=rank)          # independent problems per rank (batch shard)
+    nOb, V = sc["nOb"], int(np.sum(sc["vOb"]))
+    vOb = np.ascontiguousarray(sc["vOb"], np.int32); A = np.asfortranarray(sc["A"]); b = np.ascontiguousarray(sc["b"]).ravel()
+    ego = np.ascontiguousarray(sc["ego"]); xyb = np.ascontiguousarray(sc["XYbounds"])
+    host_in = dict(x0=sc["x0"], xF=np.broadcast_to(sc["xF"], (B, 4)), rx=sc["rx"], ry=sc["ry"], ryaw=sc["ryaw"],
+                   xWS=np.transpose(sc["xWS"], (0, 2, 1)), uWS=np.transpose(sc["uWS"], (0, 2, 1)))
+    hin = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).pin_memory() for k, v in host_in.items()}
+    din = {k: v.cuda(non_blocking=True) for k, v in hin.items()}
+    shapes = dict(xp=(B, NS, 4), up=(B, N, 2), ts=(B, NS), lp=(B, NS, V), np=(B, NS, 4 * nOb), sl=(B, NS, nOb), err=(B,))
+    dout = {k: torch.zeros(s, dtype=torch.float64, device="cuda") for k, s in shapes.items()}
+    hout = {k: torch.zeros(s, dtype=torch.float64).pin_memory() for k, s in shapes.items()}
+    dflag = torch.zeros(B, dtype=torch.int32, device="cuda"); dit = torch.zeros(B, dtype=torch.int32, device="cuda")
+    hflag = torch.zeros(B, dtype=torch.int32).pin_memory(); hit = torch.zeros(B, dtype=torch.int32).pin_memory()
+    opts = obca_b200.default_opts(device=local, retry=1)
+    sec = np.zeros(1)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    NP = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def step_dev():
+        rc = lib.obca_parking_solve_batch_dev(C.c_int(B), C.c_int(N), C.c_int(nOb), NP(vOb), NP(A), NP(b), P(din["x0"]), P(din["xF"]),
+                                              C.c_double(sc["Ts"]), C.c_double(sc["L"]), NP(ego), NP(xyb), P(din["rx"]), P(din["ry"]),
+                                              P(din["ryaw"]), P(din["xWS"]), P(din["uWS"]), None, None, C.c_int(0), C.c_int(1),
+                                              C.byref(opts), P(dout["xp"]), P(dout["up"]), P(dout["ts"]), P(dout["lp"]), P(dout["np"]),
+                                              P(dout["sl"]), P(dflag), P(dit), P(dout["err"]), NP(sec))
+        assert rc == 0, lib.obca_last_error()
+        return float(sec[0])
+
+    def step_host():
+        rc = lib.obca_parking_solve_batch(C.c_int(B), C.c_int(N), C.c_int(nOb), NP(vOb), NP(A), NP(b), P(hin["x0"]), P(hin["xF"]),
+                                          C.c_double(sc["Ts"]), C.c_double(sc["L"]), NP(ego), NP(xyb), P(hin["rx"]), P(hin["ry"]),
+                                          P(hin["ryaw"]), P(hin["xWS"]), P(hin["uWS"]), None, None, C.c_int(0), C.c_int(1),
+                                          C.byref(opts), P(hout["xp"]), P(hout["up"]), P(hout["ts"]), P(hout["lp"]), P(hout["np"]),
+                                          P(hout["sl"]), P(hflag), P(hit), P(hout["err"]), NP(sec))
+        assert rc == 0, lib.obca_last_error()
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    step_host()
+    # ---- device-resident timing ----
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_(); torch.cuda.synchronize()
+        dev_s += step_dev()
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    conv = int(dflag.sum().item()); it_sum = int(dit.sum().item()); it_max = int(dit.max().item())
+    evals = it_sum + B
+    # ---- end-to-end through the host-pointer C-ABI ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop = True; sampler.join()
+    conv_h = int(hflag.sum().item())
+    stats = torch.tensor([dev_s, e2e_s, wall_s], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([conv, conv_h, it_sum, evals], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)     # time = max over ranks
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)       # the one collective: throughput counters over NVLink
+    dev_s, e2e_s, wall_s = [float(x) for x in stats.tolist()]
+    conv_all, conv_h_all, it_all, evals_all = [float(x) for x in cnt.tolist()]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    hbm, how = peaks()
+    value = conv_all / (dev_s / args.steps)
+    e2e_val = conv_h_all / (e2e_s / args.steps)
+    kernel_s = dev_s / args.steps                        # k_parking_solve dominates the event-bracketed step
+    achieved = (evals_all / world) * ALG_BYTES_PER_EVAL / kernel_s / 1e9
+    h2d = sum(int(v.numel()) * 8 for v in hin.values())
+    d2h = sum(int(v.numel()) * 8 for v in hout.values()) + 8 * B
+    line = {"metric": "OBCA trajs/sec, reverse-parking N=80 3-obs batch", "value": value, "unit": "traj/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+                       "l2": "256 MB flush between timed steps", "tol": 1e-5, "max_iter": 200,
+                       "converged_frac": conv_all / (B * world), "iters_mean": it_all / (B * world), "iters_max_rank0": it_max,
+                       "wall_ms_per_step": 1e3 * wall_s / args.steps},
+            "clocks": sampler.result(),
+            "e2e": {"value": e2e_val, "unit": "traj/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_parking_solve<2,true>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": None,
+                         "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x (iterations+1) per problem (SURVEY 8d, fused K1); "
+                                 f"peak {how}; the persistent solver is FP64/latency bound, see DESIGN.md"}}
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, wall, c, it, per = cpu_arm(cores, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": "port",
+                                "sample": f"{cores} problems of the same batch (seed 0), {wall:.1f} s wall, mean {per:.1f} s/solve, "
+                                          f"mean {it:.0f} iterations; oracle/ipm_ref.py sparse path = IPOPT stand-in, not IPOPT"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--impl", default="obca")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

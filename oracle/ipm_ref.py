@@ -62,6 +62,12 @@ class IpmOptions:
     dc_rows: np.ndarray | None = None   # boolean mask over equality rows
     dc_value: float = 1e-9
     verbose: bool = False
+    # "dense": LAPACK dsytrf (Bunch-Kaufman) on the dense KKT matrix -- the validation path.
+    # "sparse": SuperLU in symmetric mode with diagonal pivoting (K = L D L', inertia = signs of D by Sylvester's
+    #           law); falls back to "dense" whenever SuperLU had to pivot off the diagonal or the solve residual is
+    #           poor.  This is the generic sparse-direct path (what Ipopt does with MUMPS) used for CPU timing.
+    linsolve: str = "dense"
+    order: np.ndarray | None = None     # symmetric ordering of the (n + mE) KKT unknowns for the sparse path
 
 
 @dataclass
@@ -80,13 +86,50 @@ class IpmResult:
     log: list = field(default_factory=list)
 
 
+class _SparseLDL:
+    """SuperLU, symmetric mode, diagonal pivots only -> K = P'(L D L')P ; inertia from sign(diag(U))."""
+
+    def __init__(self, K, order=None):
+        from scipy.sparse.linalg import splu
+        self.order = order
+        self.K = K.tocsc() if order is None else K.tocsr()[order][:, order].tocsc()
+        self.ok = False
+        try:
+            self.lu = splu(self.K, permc_spec="NATURAL" if order is not None else "MMD_AT_PLUS_A",
+                           diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+        except RuntimeError:
+            return
+        if not np.array_equal(self.lu.perm_r, self.lu.perm_c):
+            return
+        d = self.lu.U.diagonal()
+        self.npos = int((d > 0).sum()); self.nneg = int((d < 0).sum()); self.nzero = int((d == 0).sum())
+        self.ok = True
+
+    def solve(self, rhs):
+        if self.order is not None:
+            rhs = rhs[self.order]
+        x = self._solve(rhs)
+        if self.order is not None:
+            y = np.empty_like(x); y[self.order] = x
+            return y
+        return x
+
+    def _solve(self, rhs):
+        x = self.lu.solve(rhs)
+        for _ in range(2):
+            x = x + self.lu.solve(rhs - self.K @ x)
+        self.resid = np.abs(rhs - self.K @ x).max() / max(1.0, np.abs(rhs).max())
+        return x
+
+
 def _push(x, lo, hi, k1, k2):
     """Ipopt initial-point projection (section 3.6 of the paper)."""
     x = x.copy()
-    both = np.isfinite(lo) & np.isfinite(hi)
+    lo = np.where(np.isfinite(lo), lo, -1e300); hi = np.where(np.isfinite(hi), hi, 1e300)
+    both = (lo > -1e299) & (hi < 1e299)
     pl = np.where(both, np.minimum(k1 * np.maximum(1, np.abs(lo)), k2 * (hi - lo)), k1 * np.maximum(1, np.abs(lo)))
     pu = np.where(both, np.minimum(k1 * np.maximum(1, np.abs(hi)), k2 * (hi - lo)), k1 * np.maximum(1, np.abs(hi)))
-    fl = np.isfinite(lo); fu = np.isfinite(hi)
+    fl = lo > -1e299; fu = hi < 1e299
     x[fl] = np.maximum(x[fl], (lo + pl)[fl])
     x[fu] = np.minimum(x[fu], (hi - pu)[fu])
     return x
@@ -216,22 +259,44 @@ def solve(nlp, z0, opt: IpmOptions | None = None, yE0=None) -> IpmResult:
         gf = nlp.grad(z)
         bz = gf - np.where(hasL, mu / a, 0.0) + np.where(hasU, mu / b_, 0.0)
         gam = -np.where(sHasL, mu / c, 0.0) + np.where(sHasU, mu / d, 0.0)
-        H0 = (W + sps.diags(Sz) + JI.T @ sps.diags(Ss) @ JI).toarray()
-        JEd = JE.toarray()
+        H0s = (W + sps.diags(Sz) + JI.T @ sps.diags(Ss) @ JI).tocsc()
         rhs = np.concatenate([-(bz + JI.T @ (gam + Ss * cI)), -cE - dc * yE])
+        use_sparse = o.linsolve == "sparse"
+        if not use_sparse:
+            H0 = H0s.toarray(); JEd = JE.toarray()
         # ---- inertia correction (Algorithm IC) ----
         dw = 0.0
         ok = False
         first = True
+        fac = None
         while True:
-            K = np.zeros((n + mE, n + mE))
-            K[:n, :n] = H0 + dw * np.eye(n)
-            K[n:, :n] = JEd
-            K[n:, n:] = -np.diag(dc)
-            ldu, ipiv, npos, nneg, nzero = _ldl_inertia(K)
-            if npos == n and nneg == mE and nzero == 0:
-                ok = True
-                break
+            sol = None
+            if use_sparse:
+                Ks = sps.bmat([[H0s + dw * sps.identity(n), JE.T], [JE, -sps.diags(dc + 0.0)]], format="csc")
+                fac = _SparseLDL(Ks, o.order)
+                if fac.ok and fac.npos == n and fac.nneg == mE and fac.nzero == 0:
+                    sol = fac.solve(rhs)
+                    if fac.resid < 1e-9:
+                        ok = True
+                        break
+                    sol = None
+                if not fac.ok or sol is None and fac.npos == n and fac.nneg == mE:
+                    # SuperLU pivoted off the diagonal or lost accuracy: decide with the dense Bunch-Kaufman path
+                    H0 = H0s.toarray(); JEd = JE.toarray()
+                    use_dense_now = True
+                else:
+                    use_dense_now = False
+            else:
+                use_dense_now = True
+            if use_dense_now:
+                K = np.zeros((n + mE, n + mE))
+                K[:n, :n] = H0 + dw * np.eye(n)
+                K[n:, :n] = JEd
+                K[n:, n:] = -np.diag(dc)
+                ldu, ipiv, npos, nneg, nzero = _ldl_inertia(K)
+                if npos == n and nneg == mE and nzero == 0:
+                    ok = True
+                    break
             if first:
                 dw = o.dw_first if dw_last == 0.0 else max(o.dw_min, o.kw_minus * dw_last)
                 first = False
@@ -244,11 +309,12 @@ def solve(nlp, z0, opt: IpmOptions | None = None, yE0=None) -> IpmResult:
             break
         if dw > 0:
             dw_last = dw
-        sol, info = lapack.dsytrs(ldu, ipiv, rhs, lower=1)
-        # one step of iterative refinement
-        Kfull = np.tril(K) + np.tril(K, -1).T
-        res = rhs - Kfull @ sol
-        sol = sol + lapack.dsytrs(ldu, ipiv, res, lower=1)[0]
+        if sol is None:
+            sol, info = lapack.dsytrs(ldu, ipiv, rhs, lower=1)
+            # one step of iterative refinement
+            Kfull = np.tril(K) + np.tril(K, -1).T
+            res = rhs - Kfull @ sol
+            sol = sol + lapack.dsytrs(ldu, ipiv, res, lower=1)[0]
         dz = sol[:n]; yEn = sol[n:]
         ds = JI @ dz + cI
         dzL = np.where(hasL, mu / a - zLm - zLm / a * dz, 0.0)

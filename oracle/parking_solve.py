@@ -10,7 +10,7 @@ import time
 import numpy as np
 
 from . import ipm_ref
-from .dualmultws_ref import dualmultws
+from .dualmultws_ref import dualmultws, dualmultws_ipm
 from .parking_nlp import build_parking_nlp, initial_point
 
 
@@ -36,15 +36,38 @@ def dc_mask(nlp):
     return m
 
 
+def stage_order(nlp):
+    """Stage-interleaved symmetric ordering of the KKT unknowns (variables of stage k, then the equality rows whose
+    last variable lives in stage k): keeps the LDL' factor banded.  Used by ipm_ref's sparse path."""
+    lay = nlp.lay
+    vs = np.zeros(nlp.n, int)
+    NS = lay.NS
+    vs[lay.oX:lay.oX + 4 * NS] = np.repeat(np.arange(NS), 4)
+    if not lay.fixTime:
+        vs[lay.oT:lay.oT + NS] = np.arange(NS)
+    vs[lay.oU:lay.oU + 2 * lay.N] = np.repeat(np.arange(lay.N), 2)
+    vs[lay.oL:lay.oN] = np.repeat(np.arange(NS), lay.V)
+    vs[lay.oN:lay.oS] = np.repeat(np.arange(NS), 4 * lay.nOb)
+    if lay.variant == "sd":
+        vs[lay.oS:] = np.repeat(np.arange(NS), lay.nOb)
+    rs = np.zeros(nlp.mE, int)
+    for fam in nlp.eq:
+        rs[fam.row0:fam.row0 + fam.n] = vs[fam.idx].max(axis=1)
+    key = np.concatenate([2 * vs, 2 * rs + 1])
+    return np.argsort(key, kind="stable")
+
+
 def solve_parking(x0, xF, N, Ts, L, ego, XYbounds, nOb, vOb, A, b, rx, ry, ryaw, fixTime, xWS, uWS,
                   variant="sd", lWS=None, nWS=None, opts=None, verbose=False):
     nlp = solver_view(build_parking_nlp(x0, xF, N, Ts, L, ego, XYbounds, nOb, vOb, A, b, rx, ry, ryaw,
                                         fixTime, variant))
     if lWS is None:
-        lWS, nWS, _ = dualmultws(N, nOb, vOb, A, b, rx, ry, ryaw, ego)       # ParkingSignedDist.jl:219
+        lWS, nWS, _, _ = dualmultws_ipm(N, nOb, vOb, A, b, rx, ry, ryaw, ego)   # ParkingSignedDist.jl:219
     z0 = initial_point(nlp.lay, xWS, uWS, lWS, nWS)
     o = opts or ipm_ref.IpmOptions()
     o.dc_rows = dc_mask(nlp)
+    if o.linsolve == "sparse":
+        o.order = stage_order(nlp)
     o.verbose = verbose
     t0 = time.time()
     res = ipm_ref.solve(nlp, z0, o)

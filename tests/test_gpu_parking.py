@@ -1,0 +1,191 @@
+"""GPU parity tests (pytest -m gpu, run on the B200 box).  Everything goes through the C-ABI of libobca.so
+(obca_b200.parking is a ctypes shim) and is compared with the oracle: golden solutions of the IPOPT stand-in, the
+independent reference-formulation KKT certificate, the verbatim ParkingConstraints, closed-form DualMultWS answers,
+and -- at the full BASELINE batch size -- size-independent properties."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+T = lambda a: np.transpose(a, (0, 2, 1))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import obca_b200
+    if obca_b200.lib().obca_device_count() < 1:
+        pytest.fail("pytest -m gpu needs a CUDA device (libobca has no CPU fallback)")
+    from obca_b200 import parking
+    return parking
+
+
+def solve(P, sc, fix=0, sd=1, lWS=None, nWS=None, opts=None):
+    Ts = sc["Ts_fix"] if fix else sc["Ts"]
+    return P.parking_solve_batch(sc["x0"], sc["xF"], sc["N"], Ts, sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"],
+                                 sc["A"], sc["b"], sc["rx"], sc["ry"], sc["ryaw"], fix, sc["xWS"], sc["uWS"], sd, lWS, nWS, opts)
+
+
+def test_dualmultws_known_answers_and_distances(P, cfg2):
+    from obca_b200 import scenarios
+    from oracle import dualmultws_ref
+    sc = scenarios.reverse_parking_scenario()
+    poses = np.array([[-6, 9.5, 0.0], [0, 1.3, np.pi / 2], [5, 9.5, 0.3], [-3.0, 4.0, 0.2]])
+    Nn = len(poses) - 1
+    lp, npp, d = P.dualmultws_batch(Nn, 3, sc["vOb"], sc["A"], sc["b"], poses[None, :, 0], poses[None, :, 1], poses[None, :, 2],
+                                    sc["ego"], want_d=True)
+    assert abs(d[0, 0, 2] - 0.5) < 1e-5 and abs(d[0, 0, 0] - 3.5) < 1e-5            # SURVEY 8c KATs
+    assert abs(d[0, 1, 0] - 0.3) < 1e-5 and abs(d[0, 2, 1] - 3.2491433042) < 1e-5
+    assert np.allclose(lp[0, 2, 2:4], [0, 1], atol=1e-4) and np.allclose(npp[0, 2, 4:8], [0, 0, 0.2955202, 0.9553365], atol=1e-4)
+    assert abs(d[0, 3, 0]) < 1e-5                                                      # overlapping pose -> 0
+    lp, npp, d = P.dualmultws_batch(80, 3, cfg2["vOb"], cfg2["A"], cfg2["b"], cfg2["rx"], cfg2["ry"], cfg2["ryaw"], cfg2["ego"], want_d=True)
+    g, off = dualmultws_ref.ego_geometry(cfg2["ego"])
+    A = cfg2["A"]; b = cfg2["b"].ravel(); vo = np.concatenate([[0], np.cumsum(cfg2["vOb"])])
+    for i in range(cfg2["B"]):
+        for k in range(0, 81, 5):
+            for j in range(3):
+                ref = dualmultws_ref.rect_poly_distance((cfg2["rx"][i, k], cfg2["ry"][i, k], cfg2["ryaw"][i, k]),
+                                                        A[vo[j]:vo[j + 1]], b[vo[j]:vo[j + 1]], g, off)
+                assert abs(ref - d[i, k, j]) < 2e-5
+    assert (lp >= 0).all() and (npp >= 0).all()
+
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("_"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_matches_oracle_golden(P, cfg2, case):
+    """Same inputs (incl. the oracle's DualMultWS warm start) -> same KKT point as the IPOPT stand-in.
+    Tolerance: two interior-point runs stopped at tol = 1e-5 sit O(mu) ~ 1e-5 apart on the central path."""
+    g = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    i, variant, fix = int(g["index"]), str(g["variant"]), int(g["fixTime"])
+    sub = dict(cfg2); sub.update(B=1, x0=cfg2["x0"][i:i + 1], rx=cfg2["rx"][i:i + 1], ry=cfg2["ry"][i:i + 1],
+                                 ryaw=cfg2["ryaw"][i:i + 1], xWS=cfg2["xWS"][i:i + 1], uWS=cfg2["uWS"][i:i + 1])
+    r = solve(P, sub, fix, 1 if variant == "sd" else 0, g["lWS"][None], g["nWS"][None])
+    assert r["exitflag"][0] == 1
+    assert np.abs(r["xp"][0] - g["xp"]).max() < 2e-4 and np.abs(r["up"][0] - g["up"]).max() < 2e-4
+    assert np.abs(r["ts"][0] - g["ts"]).max() < 1e-5
+    assert np.abs(r["lp"][0] - g["lp"]).max() < 5e-3 and np.abs(r["np"][0] - g["np"]).max() < 5e-3
+
+
+@pytest.mark.parametrize("variant,fix", [("sd", 0), ("d", 0), ("sd", 1), ("d", 1)])
+def test_solutions_are_kkt_points_and_pass_reference_checker(P, cfg2, variant, fix):
+    from oracle import checkers, kkt_check
+    sd = 1 if variant == "sd" else 0
+    r = solve(P, cfg2, fix, sd)
+    assert r["exitflag"].sum() >= cfg2["B"] - 1
+    Ts = cfg2["Ts_fix"] if fix else cfg2["Ts"]
+    feas, e7, strict = P.check_parking_batch(cfg2["x0"], cfg2["xF"], 80, Ts, cfg2["L"], cfg2["ego"], cfg2["XYbounds"], 3, cfg2["vOb"],
+                                             cfg2["A"], cfg2["b"], r["xp"], r["up"], r["lp"], r["np"], r["ts"], fix, sd, r["sl"])
+    for i in range(cfg2["B"]):
+        if not r["exitflag"][i]:
+            continue
+        ok, e = checkers.ParkingConstraints(cfg2["x0"][i], cfg2["xF"], 80, Ts, cfg2["L"], cfg2["ego"], cfg2["XYbounds"], 3, cfg2["vOb"],
+                                            cfg2["A"], cfg2["b"], r["xp"][i], r["up"][i], r["lp"][i], r["np"][i], r["ts"][i], fix, sd,
+                                            return_e=True)
+        assert ok == feas[i] and (e == e7[i]).all()          # GPU twin == verbatim oracle checker
+        ok2, worst = checkers.strict_check(cfg2["x0"][i], cfg2["xF"], 80, Ts, cfg2["L"], cfg2["ego"], cfg2["XYbounds"], 3, cfg2["vOb"],
+                                           cfg2["A"], cfg2["b"], r["xp"][i], r["up"][i], r["lp"][i], r["np"][i], r["ts"][i], fix, sd,
+                                           r["sl"][i] if sd else None)
+        assert ok2 == strict[i] == 1, worst
+        if sd == 0 or True:
+            assert ok == 1 or sd == 1, e                     # SD may legitimately penetrate (slack); Dist must be collision-free
+    for i in (0, 5):
+        if r["exitflag"][i]:
+            e = kkt_check.reference_kkt_error(cfg2, i, r, variant, fix)
+            assert e["E0"] < 1e-4 and e["constr_viol"] < 1e-4          # north_star: 1e-4 relative KKT residual
+            assert abs(e["E0"] - r["kkt_err"][i]) < 2e-5
+
+
+def test_checker_flags_corrupted_solutions(P, cfg2):
+    from oracle import checkers
+    r = solve(P, cfg2)
+    x = r["xp"].copy(); u = r["up"].copy(); l = r["lp"].copy(); n = r["np"].copy(); ts = r["ts"].copy()
+    u[0, 1, 3] = 0.45          # |a| > 0.4            -> e[0]
+    x[1, 0, 0] += 1e-3         # start pose           -> e[1]
+    x[2, 3, 40] += 1e-2        # v-row of dynamics    -> e[3]
+    ts[3, 5] += 1e-3           # diff(timeScale)      -> e[4]
+    n[4, 8, 10] += 0.5         # rot row, last obst.  -> e[6]
+    feas, e7, _ = P.check_parking_batch(cfg2["x0"], cfg2["xF"], 80, cfg2["Ts"], cfg2["L"], cfg2["ego"], cfg2["XYbounds"], 3, cfg2["vOb"],
+                                        cfg2["A"], cfg2["b"], x, u, l, n, ts, 0, 1, r["sl"])
+    for i in range(cfg2["B"]):
+        ok, e = checkers.ParkingConstraints(cfg2["x0"][i], cfg2["xF"], 80, cfg2["Ts"], cfg2["L"], cfg2["ego"], cfg2["XYbounds"], 3,
+                                            cfg2["vOb"], cfg2["A"], cfg2["b"], x[i], u[i], l[i], n[i], ts[i], 0, 1, return_e=True)
+        assert ok == feas[i] and (e == e7[i]).all(), (i, e, e7[i])
+    assert feas[:5].sum() == 0 and e7[0, 0] == 0 and e7[1, 1] == 0 and e7[2, 3] == 0 and e7[3, 4] == 0 and e7[4, 6] == 0
+
+
+def test_single_problem_call_surface(P, cfg2):
+    """B = 1 through the reference-named functions (ParkingSignedDist.jl:29 / ParkingDist.jl:29 / DualMultWS.jl:29)."""
+    import obca_b200
+    i = 0
+    args = (cfg2["x0"][i][None], cfg2["xF"][None], 80, cfg2["Ts"], cfg2["L"], cfg2["ego"], cfg2["XYbounds"], 3, cfg2["vOb"][None],
+            cfg2["A"], cfg2["b"], cfg2["rx"][i], cfg2["ry"][i], cfg2["ryaw"][i], 0, cfg2["xWS"][i], cfg2["uWS"][i])
+    xp, up, tsp, exitflag, t, lp, npp = obca_b200.ParkingSignedDist(*args)
+    assert xp.shape == (4, 81) and up.shape == (2, 80) and tsp.shape == (81,) and lp.shape == (5, 81) and npp.shape == (12, 81)
+    assert exitflag == 1 and t > 0
+    assert obca_b200.ParkingConstraints(*args[:11], xp, up, lp, npp, tsp, 0, 1) in (0, 1)
+    xp2, up2, ts2, ef2, t2, lp2, np2 = obca_b200.ParkingDist(*args)
+    assert ef2 == 1 and obca_b200.ParkingConstraints(*args[:11], xp2, up2, lp2, np2, ts2, 0, 0) == 1
+    obca_b200.parking.ego = cfg2["ego"]
+    l0, n0 = obca_b200.DualMultWS(80, 3, cfg2["vOb"], cfg2["A"], cfg2["b"], cfg2["rx"][i], cfg2["ry"][i], cfg2["ryaw"][i])
+    assert l0.shape == (81, 5) and n0.shape == (81, 12)
+    # fixed time returns ones(1, N+1) (ParkingSignedDist.jl:304-305)
+    a = list(args); a[3] = cfg2["Ts_fix"]; a[14] = 1
+    out = obca_b200.ParkingSignedDist(*a)
+    assert np.array_equal(np.asarray(out[2]).ravel(), np.ones(81)) and out[3] == 1
+
+
+def test_four_obstacle_parallel_scenario_and_ragged_rows(P):
+    """main.jl:154-157 parallel-parking obstacle set (4 obstacles, vOb=[2,2,1,1]) exercises nOb != 3."""
+    from obca_b200 import scenarios
+    from oracle import dualmultws_ref
+    sc = scenarios.parallel_parking_scenario(4)
+    B, N = 4, 40
+    rng = np.random.default_rng(3)
+    rx = rng.uniform(-8, 8, (B, N + 1)); ry = rng.uniform(6.5, 9.5, (B, N + 1)); ryaw = rng.uniform(-0.5, 0.5, (B, N + 1))
+    lp, npp, d = P.dualmultws_batch(N, 4, sc["vOb"], sc["A"], sc["b"], rx, ry, ryaw, sc["ego"], want_d=True)
+    g, off = dualmultws_ref.ego_geometry(sc["ego"])
+    A = sc["A"]; b = sc["b"].ravel(); vo = np.concatenate([[0], np.cumsum(sc["vOb"])])
+    for k in range(0, N + 1, 7):
+        for j in range(4):
+            ref = dualmultws_ref.rect_poly_distance((rx[1, k], ry[1, k], ryaw[1, k]), A[vo[j]:vo[j + 1]], b[vo[j]:vo[j + 1]], g, off)
+            assert abs(ref - d[1, k, j]) < 2e-5
+
+
+def test_full_batch_properties(P):
+    """BASELINE config 2 at full size (B = 4096): size-independent properties instead of per-problem oracles."""
+    from obca_b200 import scenarios
+    sc = scenarios.reverse_parking_batch(4096, 80, 0)
+    r = solve(P, sc)
+    conv = r["exitflag"] == 1
+    assert conv.mean() >= 0.99
+    assert (r["kkt_err"][conv] <= 1e-5).all()
+    feas, e7, strict = P.check_parking_batch(sc["x0"], sc["xF"], 80, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"],
+                                             sc["b"], r["xp"], r["up"], r["lp"], r["np"], r["ts"], 0, 1, r["sl"])
+    assert strict[conv].mean() >= 0.999
+    assert np.abs(r["xp"][:, :, 0] - sc["x0"]).max() < 1e-12 and np.abs(r["xp"][conv][:, :, -1] - sc["xF"]).max() < 5e-5
+    assert (r["ts"] >= 0.8 - 1e-9).all() and (r["ts"] <= 1.2 + 1e-9).all() and np.abs(np.diff(r["ts"], axis=1)).max() == 0
+    assert (r["lp"] > 0).all() and (r["np"] > 0).all()
+    # determinism: same batch -> bitwise identical output; permuting the batch permutes the output
+    r2 = solve(P, sc)
+    assert np.array_equal(r["xp"], r2["xp"]) and np.array_equal(r["iters"], r2["iters"])
+    perm = np.random.default_rng(0).permutation(4096)
+    scp = dict(sc); scp.update(x0=sc["x0"][perm], rx=sc["rx"][perm], ry=sc["ry"][perm], ryaw=sc["ryaw"][perm], xWS=sc["xWS"][perm], uWS=sc["uWS"][perm])
+    r3 = solve(P, scp)
+    assert np.array_equal(r3["xp"], r["xp"][perm])
+
+
+def test_usage_errors_do_not_throw(P, cfg2):
+    import ctypes as C
+    import obca_b200
+    lib = obca_b200.lib()
+    bad_v = np.array([9, 1, 1], np.int32)     # more half-spaces than the kernels support
+    with pytest.raises(obca_b200.ObcaError):
+        P.dualmultws_batch(80, 3, bad_v, np.zeros((11, 2)), np.zeros(11), cfg2["rx"], cfg2["ry"], cfg2["ryaw"], cfg2["ego"])
+    o = obca_b200.default_opts(device=63)
+    with pytest.raises(obca_b200.ObcaError):
+        solve(P, cfg2, opts=o)
