@@ -48,7 +48,11 @@ def peaks():
 # ----------------------------------------------------------------------------------------------------------
 def _cpu_solve_one(args):
     i, seed = args
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"; os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)                      # one BLAS/OpenMP thread per worker process
+    except Exception:
+        pass
     from obca_b200.scenarios import reverse_parking_batch
     from oracle import ipm_ref
     from oracle.parking_solve import solve_parking
@@ -74,11 +78,18 @@ def cpu_arm(n_problems, cores):
     return conv / wall, wall, conv, float(np.mean([r[1] for r in res])), float(np.mean([r[2] for r in res]))
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     per_step = cores
     for _ in range(args.warmup if args.warmup < 1 else 1):
         cpu_arm(cores, cores)
@@ -248,8 +259,14 @@ def gpu_arm(args):
                          "frac": achieved / hbm, "traffic": None,
                          "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x (iterations+1) per problem (SURVEY 8d, fused K1); "
                                  f"peak {how}; the persistent solver is FP64/latency bound, see DESIGN.md"}}
+    prof = (C.c_ulonglong * 8)()
+    if lib.obca_last_profile(C.c_int(local), prof) == 0:
+        names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]
+        tot = float(sum(prof[i] for i in range(6))) or 1.0
+        line["phase_share"] = {n: round(prof[i] / tot, 4) for i, n in enumerate(names)}
+        line["phase_counts"] = {"merit_evals": int(prof[6]), "k1_evals": int(prof[7])}
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         v, wall, c, it, per = cpu_arm(cores, cores)
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": "port",
                                 "sample": f"{cores} problems of the same batch (seed 0), {wall:.1f} s wall, mean {per:.1f} s/solve, "

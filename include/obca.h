@@ -103,6 +103,11 @@ int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, c
                        const double* sl, int fixTime, int sd, const obca_opts* opts, int* feasible, int* e,
                        int* strict);
 
+/* Per-phase device cycle counters of the last obca_parking_solve_batch[_dev] on `device`, summed over the batch
+ * (thread 0 of every CTA, clock64): out8 = {eval (K1), kkt (K3), recover, merit, update, serial sections,
+ * #merit evaluations, #K1 evaluations}.  Diagnostic only. */
+int obca_last_profile(int device, unsigned long long* out8);
+
 /* K1 stand-alone: fused evaluation of the OBCA NLP at B given points (no solve).  Reads the stacked
  * (x, u, ts, l, n, sl) batch and the multipliers `duals` (layout below), writes per problem
  *   out[0] = objective f, out[1] = ||c||_inf, out[2] = ||c||_1, out[3] = ||grad L||_inf, out[4] = max compl. product

@@ -32,13 +32,20 @@ struct BatchPtrs {
   double* kkt_err;
   int B;
   int retry;
+  unsigned long long* prof;   // optional: 8 per-phase cycle counters summed over the batch (device pointer)
 };
 
+#ifndef OBCA_MIN_BLOCKS
+#define OBCA_MIN_BLOCKS 4
+#endif
 template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, OBCA_MIN_BLOCKS)
 k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L,
                 const BatchPtrs bp, double* __restrict__ Wall, int* __restrict__ counter) {
+  extern __shared__ double s_ric[];     // (N+1) x RSTRIDE stage slots of the KKT solve
   __shared__ ProbState S;
+  __shared__ double s_tile[72];          // T = P Phi tile of the KKT sweep
+  __shared__ double s_red[4 * 12];      // block_reduce scratch (4 warps x sizeof(EvalPart))
   __shared__ int s_b;
   __shared__ ChkPart s_chk[4];
   __shared__ int s_feas;
@@ -50,7 +57,7 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
     const int b = s_b;
     if (b >= bp.B) break;
     PkCtx C;
-    C.P = &P; C.O = &O; C.L = L; C.W = W; C.S = &S;
+    C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = s_ric; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
     C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
     C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
     C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
@@ -111,6 +118,8 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
       bp.exitflag[b] = exitflag;
       bp.iters[b] = iters;
       bp.kkt_err[b] = S.e0;
+      if (bp.prof)
+        for (int i = 0; i < 8; ++i) atomicAdd(bp.prof + i, (unsigned long long)S.prof[i]);
     }
     __syncthreads();
   }
@@ -217,6 +226,8 @@ struct DevCtx {
   int sms = 0;
   double* W = nullptr; size_t Wbytes = 0;
   int* counter = nullptr;
+  unsigned long long* prof = nullptr;
+  unsigned long long prof_host[8] = {0};
   char* stage = nullptr; size_t stage_bytes = 0;   // device staging for the host-pointer API
   std::mutex mu;
 };
@@ -235,6 +246,7 @@ static int get_ctx(int dev, DevCtx** out) {
     CK(cudaGetDeviceProperties(&pr, dev));
     c.sms = pr.multiProcessorCount;
     CK(cudaMalloc(&c.counter, sizeof(int)));
+    CK(cudaMalloc(&c.prof, 8 * sizeof(unsigned long long)));
     c.init = true;
   }
   *out = &c;
@@ -284,8 +296,10 @@ template <int VM, bool SDV>
 static int launch_solve(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const BatchPtrs& bp) {
   PkLay L = make_layout(P, LocalDims<VM, SDV>::NFAC);
   if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)(P.N + 1) * RSTRIDE * sizeof(double);
+  CK(cudaFuncSetAttribute(k_parking_solve<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parking_solve<VM, SDV>, L.NSP, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parking_solve<VM, SDV>, L.NSP, smem));
   if (occ < 1) occ = 1;
   int grid = c.sms * occ;
   if (grid > bp.B) grid = bp.B;
@@ -293,19 +307,26 @@ static int launch_solve(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const
   int rc = ensure((void**)&c.W, &c.Wbytes, need);
   if (rc) return rc;
   CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
-  k_parking_solve<VM, SDV><<<grid, L.NSP, 0, c.st>>>(P, O, L, bp, c.W, c.counter);
+  k_parking_solve<VM, SDV><<<grid, L.NSP, smem, c.st>>>(P, O, L, bp, c.W, c.counter);
   CK(cudaGetLastError());
   return 0;
 }
 
 static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, BatchPtrs bp, double* seconds) {
   const int vm = max_vob(P) <= 2 ? 2 : 4;
-  CK(cudaEventRecord(c.ev0, c.st));
+  CK(cudaMemsetAsync(c.prof, 0, 8 * sizeof(unsigned long long), c.st));
+  bp.prof = c.prof;
   int rc;
+#ifdef OBCA_FAST_BUILD   // development builds: only the config-2 instantiation
+  if (!(P.signed_dist && vm == 2)) { set_err("fast build: only <2,true>"); return OBCA_ERR_UNSUPPORTED; }
+  rc = launch_solve<2, true>(c, P, O, bp);
+#else
   if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, bp) : launch_solve<4, true>(c, P, O, bp);
   else rc = vm == 2 ? launch_solve<2, false>(c, P, O, bp) : launch_solve<4, false>(c, P, O, bp);
+#endif
   if (rc) return rc;
   CK(cudaEventRecord(c.ev1, c.st));
+  CK(cudaMemcpyAsync(c.prof_host, c.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st));
   CK(cudaStreamSynchronize(c.st));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
@@ -358,6 +379,7 @@ int obca_parking_solve_batch_dev(int B, int N, int nOb, const int* vOb, const do
   bp.x0 = x0; bp.xF = xF; bp.rx = rx; bp.ry = ry; bp.ryaw = ryaw; bp.xWS = xWS; bp.uWS = uWS;
   bp.xp = xp; bp.up = up; bp.ts = ts; bp.lp = lp; bp.np = np; bp.sl = sl; bp.duals = nullptr;
   bp.exitflag = exitflag; bp.iters = iters; bp.kkt_err = kkt_err; bp.B = B; bp.retry = opts ? opts->retry : 1;
+  CK(cudaEventRecord(c->ev0, c->st));      // the timed region covers DualMultWS (K2) + the solve
   if (lWS && nWS) { bp.lWS = lWS; bp.nWS = nWS; }
   else {
     // the reference runs DualMultWS inside the NLP driver (ParkingSignedDist.jl:219): use the output arrays
@@ -493,6 +515,12 @@ int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, c
   if (e) CK(cudaMemcpyAsync(e, di + B, 7 * (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (strict) CK(cudaMemcpyAsync(strict, di + 8 * (size_t)B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int obca_last_profile(int device, unsigned long long* out8) {
+  if (device < 0 || device >= 64 || !out8 || !g_dev[device].init) { set_err("no profile"); return OBCA_ERR_ARG; }
+  for (int i = 0; i < 8; ++i) out8[i] = g_dev[device].prof_host[i];
   return 0;
 }
 

@@ -129,7 +129,7 @@ OBCA_HD int choose_pivot(const ObsRows<VM>& R, const ObsGeom<VM>& G) {
 // ------------------------------------------------------------------------------------------------------------
 template <int VM, bool SDV>
 OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVars<VM>& Q, const ObsGeom<VM>& G,
-                         double mu_b, double dw, double dc, double* Sxx, double* rx, double* fac) {
+                         double mu_b, double dw, double dc, double* Sxx, double* rx, double* fac, int fs) {
   typedef LocalDims<VM, SDV> D;
   constexpr int ND = D::ND;
   double M[D::NM];
@@ -268,16 +268,16 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
   Sxx[0] = M[sym_idx<ND>(D::I_X, D::I_X)]; Sxx[1] = M[sym_idx<ND>(D::I_X, D::I_Y)]; Sxx[2] = M[sym_idx<ND>(D::I_X, D::I_P)];
   Sxx[3] = M[sym_idx<ND>(D::I_Y, D::I_Y)]; Sxx[4] = M[sym_idx<ND>(D::I_Y, D::I_P)]; Sxx[5] = M[sym_idx<ND>(D::I_P, D::I_P)];
   rx[0] = r[D::I_X]; rx[1] = r[D::I_Y]; rx[2] = r[D::I_P];
-  // factor: rows 0..NLT-1 of the upper triangle, then their rhs
+  // factor: rows 0..NLT-1 of the upper triangle, then their rhs  (fac is strided by fs: workspace arrays)
   {
     int q = 0;
 #pragma unroll
     for (int i = 0; i < D::NLT; ++i) {
 #pragma unroll
-      for (int c_ = i; c_ < ND; ++c_) fac[q++] = M[sym_idx<ND>(i, c_)];
+      for (int c_ = i; c_ < ND; ++c_) { fac[(size_t)q * fs] = M[sym_idx<ND>(i, c_)]; ++q; }
     }
 #pragma unroll
-    for (int i = 0; i < D::NLT; ++i) fac[q++] = r[i];
+    for (int i = 0; i < D::NLT; ++i) { fac[(size_t)q * fs] = r[i]; ++q; }
   }
   return ok;
 }
@@ -292,36 +292,34 @@ struct ObsStep {
 
 template <int VM, bool SDV>
 OBCA_HD void obs_recover(const ParkProblem& P, const ObsRows<VM>& R, const ObsVars<VM>& Q, const ObsGeom<VM>& G,
-                         double mu_b, double dw, const double* fac, double dX, double dY, double dP,
+                         double mu_b, double dw, const double* fac, int fs, double dX, double dY, double dP,
                          ObsStep<VM>& S) {
   typedef LocalDims<VM, SDV> D;
   constexpr int ND = D::ND;
   double x[ND];
   x[D::I_X] = dX; x[D::I_Y] = dY; x[D::I_P] = dP;
-  // offsets of row i inside fac
-  int roff[D::NLT];
-  {
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < D::NLT; ++i) { roff[i] = q; q += ND - i; }
-  }
-  const double* rh = fac + (D::NM - 6);
+  // row i of the factor starts at roff(i) = sum_{r<i} (ND - r); the rhs follows the NM - 6 matrix entries
+#define OBCA_ROFF(i) ((i) * ND - ((i) * ((i) - 1)) / 2)
+#define OBCA_FAC(e) fac[(size_t)(e) * fs]
+  constexpr int RH = D::NM - 6;
   constexpr int first = SDV ? 2 : 0;
 #pragma unroll
   for (int i = D::NLT - 1; i >= first; --i) {
-    double acc = -rh[i];
+    double acc = -OBCA_FAC(RH + i);
 #pragma unroll
-    for (int c_ = i + 1; c_ < ND; ++c_) acc -= fac[roff[i] + (c_ - i)] * x[c_];
-    x[i] = acc * fac[roff[i]];   // stored inverse pivot
+    for (int c_ = i + 1; c_ < ND; ++c_) acc -= OBCA_FAC(OBCA_ROFF(i) + (c_ - i)) * x[c_];
+    x[i] = acc * OBCA_FAC(OBCA_ROFF(i));   // stored inverse pivot
   }
   if (SDV) {
-    double b0 = -rh[0], b1 = -rh[1];
+    double b0 = -OBCA_FAC(RH + 0), b1 = -OBCA_FAC(RH + 1);
 #pragma unroll
-    for (int c_ = 2; c_ < ND; ++c_) { b0 -= fac[roff[0] + c_] * x[c_]; b1 -= fac[roff[1] + (c_ - 1)] * x[c_]; }
-    const double i00 = fac[roff[0]], i01 = fac[roff[0] + 1], i11 = fac[roff[1]];
+    for (int c_ = 2; c_ < ND; ++c_) { b0 -= OBCA_FAC(OBCA_ROFF(0) + c_) * x[c_]; b1 -= OBCA_FAC(OBCA_ROFF(1) + (c_ - 1)) * x[c_]; }
+    const double i00 = OBCA_FAC(OBCA_ROFF(0)), i01 = OBCA_FAC(OBCA_ROFF(0) + 1), i11 = OBCA_FAC(OBCA_ROFF(1));
     x[0] = i00 * b0 + i01 * b1;
     x[1] = i01 * b0 + i11 * b1;
   }
+#undef OBCA_ROFF
+#undef OBCA_FAC
   const double g3 = P.g[2], g4 = P.g[3];
   double t3d = x[D::I_MU1] + G.e2 * dP, t4d = x[D::I_MU2] - G.e1 * dP;
   double Gd = (-P.g[0] - g3) * x[D::I_MU1] + (-P.g[1] - g4) * x[D::I_MU2] + G.p1 * dX + G.p2 * dY +

@@ -21,13 +21,73 @@
 #define OBCA_FOR_STAGES(k, ns) for (int k = threadIdx.x; k < (ns); k += blockDim.x)
 #define OBCA_SYNC() __syncthreads()
 #define OBCA_SERIAL if (threadIdx.x == 0)
+// phase profiling: thread 0 charges the cycles since the last mark to counter i (call right after a barrier)
+#define OBCA_PROF(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); S.prof[i] += t_ - S.tmark; S.tmark = t_; } } while (0)
+#define OBCA_PROF_COUNT(i) do { if (threadIdx.x == 0) S.prof[i] += 1; } while (0)
 #else
+#define OBCA_PROF(i)
+#define OBCA_PROF_COUNT(i)
 #define OBCA_FOR_STAGES(k, ns) for (int k = 0; k < (ns); ++k)
 #define OBCA_SYNC()
 #define OBCA_SERIAL
 #endif
 
 namespace obca {
+
+// ---- per-stage partial results that are reduced over the stages of one problem ----
+struct EvalPart {   // KKT-error / merit pieces
+  double e_dual, e_pr, cmax, cmin, sy, sz, th, phi, rt, f;
+  int ok;
+};
+struct StepPart { double apr, adu, dphi; };
+struct MeritPart { double th, phi; };
+OBCA_HD void part_init(EvalPart& p) { p.e_dual = 0; p.e_pr = 0; p.cmax = 0; p.cmin = 1e300; p.sy = 0; p.sz = 0; p.th = 0; p.phi = 0; p.rt = 0; p.f = 0; p.ok = 1; }
+OBCA_HD void part_init(StepPart& p) { p.apr = 1.0; p.adu = 1.0; p.dphi = 0.0; }
+OBCA_HD void part_init(MeritPart& p) { p.th = 0.0; p.phi = 0.0; }
+OBCA_HD void part_merge(EvalPart& a, const EvalPart& b) {
+  a.e_dual = dmax(a.e_dual, b.e_dual); a.e_pr = dmax(a.e_pr, b.e_pr); a.cmax = dmax(a.cmax, b.cmax); a.cmin = dmin_(a.cmin, b.cmin);
+  a.sy += b.sy; a.sz += b.sz; a.th += b.th; a.phi += b.phi; a.rt += b.rt; a.f += b.f; a.ok &= b.ok;
+}
+OBCA_HD void part_merge(StepPart& a, const StepPart& b) { a.apr = dmin_(a.apr, b.apr); a.adu = dmin_(a.adu, b.adu); a.dphi += b.dphi; }
+OBCA_HD void part_merge(MeritPart& a, const MeritPart& b) { a.th += b.th; a.phi += b.phi; }
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ EvalPart part_shfl(const EvalPart& p, int off) {
+  EvalPart o;
+  o.e_dual = __shfl_down_sync(0xffffffffu, p.e_dual, off); o.e_pr = __shfl_down_sync(0xffffffffu, p.e_pr, off);
+  o.cmax = __shfl_down_sync(0xffffffffu, p.cmax, off); o.cmin = __shfl_down_sync(0xffffffffu, p.cmin, off);
+  o.sy = __shfl_down_sync(0xffffffffu, p.sy, off); o.sz = __shfl_down_sync(0xffffffffu, p.sz, off);
+  o.th = __shfl_down_sync(0xffffffffu, p.th, off); o.phi = __shfl_down_sync(0xffffffffu, p.phi, off);
+  o.rt = __shfl_down_sync(0xffffffffu, p.rt, off); o.f = __shfl_down_sync(0xffffffffu, p.f, off);
+  o.ok = __shfl_down_sync(0xffffffffu, p.ok, off);
+  return o;
+}
+__device__ __forceinline__ StepPart part_shfl(const StepPart& p, int off) {
+  StepPart o;
+  o.apr = __shfl_down_sync(0xffffffffu, p.apr, off); o.adu = __shfl_down_sync(0xffffffffu, p.adu, off);
+  o.dphi = __shfl_down_sync(0xffffffffu, p.dphi, off);
+  return o;
+}
+__device__ __forceinline__ MeritPart part_shfl(const MeritPart& p, int off) {
+  MeritPart o;
+  o.th = __shfl_down_sync(0xffffffffu, p.th, off); o.phi = __shfl_down_sync(0xffffffffu, p.phi, off);
+  return o;
+}
+// deterministic block reduction (fixed shuffle tree, then warp 0..3 in order); result valid in thread 0.
+// Contains one __syncthreads().  `scratch`: shared memory, >= 4 * sizeof(EvalPart) bytes.
+template <typename T>
+__device__ __forceinline__ void block_reduce(T& v, void* scratch) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { T o = part_shfl(v, off); part_merge(v, o); }
+  T* sc = reinterpret_cast<T*>(scratch);
+  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) part_merge(v, sc[w]);
+}
+#define OBCA_REDUCE(v) block_reduce(v, C.red_scratch)
+#else
+#define OBCA_REDUCE(v)
+#endif
 
 // ---- workspace layout: every entry is an array of NSP doubles indexed by stage ----
 struct PkLay {
@@ -41,13 +101,10 @@ struct PkLay {
   int dX, dY, dPS, dVL, dDE, dAC, dLAM, dMU, dSL;
   int PIn, YNn, YRn, dSD, dSN, dRS;
   // KKT workspace
-  int QS, qs, DYN, R4, RK, RP, LF;
+  int LF;
   int nfac;
-  // reductions
-  int RED;
   int total;
 };
-enum { R_DUAL = 0, R_PR, R_CMAX, R_CMIN, R_SY, R_SZ, R_TH, R_PHI, R_RT, R_OK, R_APR, R_ADU, R_DPHI, R_F, R_NUM };
 
 inline PkLay make_layout(const ParkProblem& P, int nfac) {
   PkLay L;
@@ -67,18 +124,24 @@ inline PkLay make_layout(const ParkProblem& P, int nfac) {
   L.dLAM = take(P.V); L.dMU = take(4 * P.nOb); L.dSL = take(P.nOb);
   L.PIn = take(4); L.YNn = take(P.nOb); L.YRn = take(2 * P.nOb);
   L.dSD = take(P.nOb); L.dSN = take(P.nOb); L.dRS = take(1);
-  L.QS = take(NQ); L.qs = take(NYV); L.DYN = take(20); L.R4 = take(4);
-  L.RK = take(16); L.RP = take(NSV * (NSV + 1) / 2 + NSV);
   L.nfac = nfac;
   L.LF = take(P.nOb * nfac);
-  L.RED = take(R_NUM);
   L.total = c;
   return L;
 }
 
+// ---- per-stage slot of the KKT solve (shared memory on the device): RSTRIDE doubles per stage ----
+//   after stage_eval(k):   [RQ..] Q (45, packed 9x9) | [Rq..] q (9) | [RDYN..] dynamics Jacobian (20) | [RR4..] residual (4)
+//   after the backward sweep passed stage k:  [RK..] gain K (2x7) + feed-forward (2)  and, in slot k+1,
+//                                             [RPP..] P_{k+1} (28) + p_{k+1} (7)   (the consumed Q/q space is reused)
+constexpr int RSTRIDE = 79;   // odd -> conflict-free column accesses
+constexpr int RQ = 0, Rq = 45, RDYN = 54, RR4 = 74;
+constexpr int RK = 0, RPP = 16, Rpp = 44;
+
 // per-problem scalar state (shared memory on the device)
 struct ProbState {
   double t, zTL, zTU, dt;           // time scale, its bound multipliers, its step
+  double eN[4];                     // predicted end-point error of the step (stage N is pinned to xF)
   double mu, tau;
   double dw, dw_last;
   double theta_max, theta_min;
@@ -93,6 +156,8 @@ struct ProbState {
   int flag;       // generic broadcast flag
   int ok;
   int n_fact;     // factorisations
+  long long prof[8];   // device cycle counters per phase: eval, kkt, recover, merit, update, serial, n_merit, n_eval
+  long long tmark;
 };
 
 struct PkInputs {
@@ -125,12 +190,16 @@ struct PkCtx {
   const IpmOpts* O;
   PkLay L;
   double* W;
+  double* ric;     // (N+1) x RSTRIDE slots
+  void* red_scratch;   // device: shared-memory scratch of block_reduce
+  double* tile;        // device: 7*9+7 doubles of shared memory for the warp-cooperative KKT sweep
   ProbState* S;
   PkInputs in;
 };
 
 #define WA(name, k) (C.W[(size_t)(C.L.name) * C.L.NSP + (k)])
 #define WV(name, i, k) (C.W[(size_t)(C.L.name + (i)) * C.L.NSP + (k)])
+#define RIC(off, k) (C.ric[(k) * RSTRIDE + (off)])
 
 OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
   const double pl = dmin_(k1 * dmax(1.0, dabs(lo)), k2 * (hi - lo));
@@ -139,6 +208,20 @@ OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
   x = dmin_(x, hi - pu);
   return x;
 }
+
+#if defined(__CUDA_ARCH__)
+// reciprocal for the latency-critical Riccati pivot: single-precision seed + 2 Newton steps in FP64 (relative error
+// ~1e-16, not correctly rounded); falls back to the IEEE division outside the float range.
+__device__ __forceinline__ double fast_rcp(double x) {
+  const double ax = fabs(x);
+  if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+  double r = (double)__frcp_rn((float)x);
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  r = r * (2.0 - x * r);
+  return r;
+}
+#endif
 
 template <int VM, bool SDV>
 struct ParkSolver {
@@ -256,7 +339,7 @@ struct ParkSolver {
   // P1 (K1): fused evaluation at the current iterate.
   //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm) {
+  OBCA_HD static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -269,11 +352,9 @@ struct ParkSolver {
     double sn_, cs_;
     sincos(ps, &sn_, &cs_);
 
-    double Q[NQ], q[NYV];
+    // the stage model (packed 9x9 Q, q) is accumulated directly in the stage slot (shared memory on the device)
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) Q[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NYV; ++i) q[i] = 0.0;
+    for (int i = 0; i < NQ + NYV; ++i) RIC(RQ + i, k) = 0.0;
     double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0;
     double rz_t = 0.0;
     int ok = 1;
@@ -289,14 +370,14 @@ struct ParkSolver {
         const double aXl = X - P.xyb[0], aXu = P.xyb[1] - X, aYl = Y - P.xyb[2], aYu = P.xyb[3] - Y;
         const double aVl = v + 1.0, aVu = 2.0 - v;
         const double zXl = WA(ZXL, k), zXu = WA(ZXU, k), zYl = WA(ZYL, k), zYu = WA(ZYU, k), zVl = WA(ZVL, k), zVu = WA(ZVU, k);
-        Q[sym_idx<NYV>(IX, IX)] += 2e-3 + zXl / aXl + zXu / aXu + dw;
-        Q[sym_idx<NYV>(IY, IY)] += 2e-3 + zYl / aYl + zYu / aYu + dw;
-        Q[sym_idx<NYV>(IP, IP)] += 2.0 * P.w_yaw + dw;
-        Q[sym_idx<NYV>(IV, IV)] += 2e-4 + zVl / aVl + zVu / aVu + dw;
-        q[IX] += gX - mu_b / aXl + mu_b / aXu;
-        q[IY] += gY - mu_b / aYl + mu_b / aYu;
-        q[IP] += gP;
-        q[IV] += gV - mu_b / aVl + mu_b / aVu;
+        RIC(RQ + sym_idx<NYV>(IX, IX), k) += 2e-3 + zXl / aXl + zXu / aXu + dw;
+        RIC(RQ + sym_idx<NYV>(IY, IY), k) += 2e-3 + zYl / aYl + zYu / aYu + dw;
+        RIC(RQ + sym_idx<NYV>(IP, IP), k) += 2.0 * P.w_yaw + dw;
+        RIC(RQ + sym_idx<NYV>(IV, IV), k) += 2e-4 + zVl / aVl + zVu / aVu + dw;
+        RIC(Rq + IX, k) += gX - mu_b / aXl + mu_b / aXu;
+        RIC(Rq + IY, k) += gY - mu_b / aYl + mu_b / aYu;
+        RIC(Rq + IP, k) += gP;
+        RIC(Rq + IV, k) += gV - mu_b / aVl + mu_b / aVu;
         rzX += gX - zXl + zXu; rzY += gY - zYl + zYu; rzP += gP; rzV += gV - zVl + zVu;
         // multiplier of the dynamics row that produced x_k
         rzX += WV(PI, 0, k - 1); rzY += WV(PI, 1, k - 1); rzP += WV(PI, 2, k - 1); rzV += WV(PI, 3, k - 1);
@@ -324,18 +405,18 @@ struct ParkSolver {
       const double gT = fix ? 0.0 : -2.0 * T * it;
       const double aDl = de + 0.6, aDu = 0.6 - de, aAl = ac + 0.4, aAu = 0.4 - ac;
       const double zDl = WA(ZDL, k), zDu = WA(ZDU, k), zAl = WA(ZAL, k), zAu = WA(ZAU, k);
-      Q[sym_idx<NYV>(IDE, IDE)] += 0.02 + 0.2 * ih2 + zDl / aDl + zDu / aDu + dw;
-      Q[sym_idx<NYV>(IAC, IAC)] += 2.0 * P.w_a + 0.2 * ih2 + zAl / aAl + zAu / aAu + dw;
-      Q[sym_idx<NYV>(IWD, IWD)] += 0.2 * ih2;
-      Q[sym_idx<NYV>(IWA, IWA)] += 0.2 * ih2;
-      Q[sym_idx<NYV>(IWD, IDE)] += -0.2 * ih2;
-      Q[sym_idx<NYV>(IWA, IAC)] += -0.2 * ih2;
+      RIC(RQ + sym_idx<NYV>(IDE, IDE), k) += 0.02 + 0.2 * ih2 + zDl / aDl + zDu / aDu + dw;
+      RIC(RQ + sym_idx<NYV>(IAC, IAC), k) += 2.0 * P.w_a + 0.2 * ih2 + zAl / aAl + zAu / aAu + dw;
+      RIC(RQ + sym_idx<NYV>(IWD, IWD), k) += 0.2 * ih2;
+      RIC(RQ + sym_idx<NYV>(IWA, IWA), k) += 0.2 * ih2;
+      RIC(RQ + sym_idx<NYV>(IWD, IDE), k) += -0.2 * ih2;
+      RIC(RQ + sym_idx<NYV>(IWA, IAC), k) += -0.2 * ih2;
       if (!fix) {
-        Q[sym_idx<NYV>(IT, IDE)] += -0.4 * ed * ih2 * it;
-        Q[sym_idx<NYV>(IT, IAC)] += -0.4 * ea * ih2 * it;
-        Q[sym_idx<NYV>(IWD, IT)] += 0.4 * ed * ih2 * it;
-        Q[sym_idx<NYV>(IWA, IT)] += 0.4 * ea * ih2 * it;
-        Q[sym_idx<NYV>(IT, IT)] += 6.0 * T * it * it;
+        RIC(RQ + sym_idx<NYV>(IT, IDE), k) += -0.4 * ed * ih2 * it;
+        RIC(RQ + sym_idx<NYV>(IT, IAC), k) += -0.4 * ea * ih2 * it;
+        RIC(RQ + sym_idx<NYV>(IWD, IT), k) += 0.4 * ed * ih2 * it;
+        RIC(RQ + sym_idx<NYV>(IWA, IT), k) += 0.4 * ea * ih2 * it;
+        RIC(RQ + sym_idx<NYV>(IT, IT), k) += 6.0 * T * it * it;
       }
       // steering-rate row (ParkingSignedDist.jl:167-173):  -0.6 <= (wd - de)/(t Ts) <= 0.6
       const double gr = (wd - de) * ih;
@@ -346,19 +427,19 @@ struct ParkSolver {
       const double cIr = gr - rs;
       const double yr0 = -mu_b / gl + mu_b / gu + Sr * cIr;
       const double jw = ih, jd = -ih, jt = fix ? 0.0 : -gr * it;
-      Q[sym_idx<NYV>(IWD, IWD)] += Sr * jw * jw;
-      Q[sym_idx<NYV>(IWD, IDE)] += Sr * jw * jd;
-      Q[sym_idx<NYV>(IDE, IDE)] += Sr * jd * jd;
+      RIC(RQ + sym_idx<NYV>(IWD, IWD), k) += Sr * jw * jw;
+      RIC(RQ + sym_idx<NYV>(IWD, IDE), k) += Sr * jw * jd;
+      RIC(RQ + sym_idx<NYV>(IDE, IDE), k) += Sr * jd * jd;
       if (!fix) {
-        Q[sym_idx<NYV>(IWD, IT)] += Sr * jw * jt - yIr * ih * it;
-        Q[sym_idx<NYV>(IT, IDE)] += Sr * jt * jd + yIr * ih * it;
-        Q[sym_idx<NYV>(IT, IT)] += Sr * jt * jt + yIr * 2.0 * gr * it * it;
+        RIC(RQ + sym_idx<NYV>(IWD, IT), k) += Sr * jw * jt - yIr * ih * it;
+        RIC(RQ + sym_idx<NYV>(IT, IDE), k) += Sr * jt * jd + yIr * ih * it;
+        RIC(RQ + sym_idx<NYV>(IT, IT), k) += Sr * jt * jt + yIr * 2.0 * gr * it * it;
       }
-      q[IWD] += gWd + jw * yr0;
-      q[IWA] += gWa;
-      q[IDE] += gD + jd * yr0 - mu_b / aDl + mu_b / aDu;
-      q[IAC] += gA - mu_b / aAl + mu_b / aAu;
-      q[IT] += gT + jt * yr0;
+      RIC(Rq + IWD, k) += gWd + jw * yr0;
+      RIC(Rq + IWA, k) += gWa;
+      RIC(Rq + IDE, k) += gD + jd * yr0 - mu_b / aDl + mu_b / aDu;
+      RIC(Rq + IAC, k) += gA - mu_b / aAl + mu_b / aAu;
+      RIC(Rq + IT, k) += gT + jt * yr0;
       // dynamics
       double pi[4], H5[15];
 #pragma unroll
@@ -369,7 +450,7 @@ struct ParkSolver {
 #pragma unroll
         for (int i = 0; i < 5; ++i)
 #pragma unroll
-          for (int j = i; j < 5; ++j) Q[sym_idx_any<NYV>(q5_to_y(i), q5_to_y(j))] += H5[e++];
+          for (int j = i; j < 5; ++j) RIC(RQ + sym_idx_any<NYV>(q5_to_y(i), q5_to_y(j)), k) += H5[e++];
       }
       double xn[4];
       if (k + 1 == N) { xn[0] = C.in.xF[0]; xn[1] = C.in.xF[1]; xn[2] = C.in.xF[2]; xn[3] = C.in.xF[3]; }
@@ -460,15 +541,13 @@ struct ParkSolver {
           swap_rows(R, Qv, piv);
           obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
         }
-        double Sxx[6], rx3[3], fac[LD::NFAC];
-        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, C.O->dc, Sxx, rx3, fac);
+        double Sxx[6], rx3[3];
+        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, C.O->dc, Sxx, rx3, &WV(LF, j * C.L.nfac, k), C.L.NSP);
         if (pose_free) {
-          Q[sym_idx<NYV>(IX, IX)] += Sxx[0]; Q[sym_idx<NYV>(IX, IY)] += Sxx[1]; Q[sym_idx<NYV>(IX, IP)] += Sxx[2];
-          Q[sym_idx<NYV>(IY, IY)] += Sxx[3]; Q[sym_idx<NYV>(IY, IP)] += Sxx[4]; Q[sym_idx<NYV>(IP, IP)] += Sxx[5];
-          q[IX] += rx3[0]; q[IY] += rx3[1]; q[IP] += rx3[2];
+          RIC(RQ + sym_idx<NYV>(IX, IX), k) += Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += Sxx[2];
+          RIC(RQ + sym_idx<NYV>(IY, IY), k) += Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += Sxx[5];
+          RIC(Rq + IX, k) += rx3[0]; RIC(Rq + IY, k) += rx3[1]; RIC(Rq + IP, k) += rx3[2];
         }
-#pragma unroll
-        for (int e = 0; e < LD::NFAC; ++e) WV(LF, j * C.L.nfac + e, k) = fac[e];
       }
     }
     // ---- (D) time-scale variable: objective (N+1)(0.5 t + t^2) (:89) and its (N+1) bound pairs ----
@@ -476,8 +555,8 @@ struct ParkSolver {
       const double m = (double)(N + 1);
       const double gl = t - 0.8, gu = 1.2 - t;
       fobj += m * (0.5 * t + t * t);
-      Q[sym_idx<NYV>(IT, IT)] += 2.0 * m + m * (S.zTL / gl + S.zTU / gu) + dw;
-      q[IT] += m * (0.5 + 2.0 * t) + m * (-mu_b / gl + mu_b / gu);
+      RIC(RQ + sym_idx<NYV>(IT, IT), k) += 2.0 * m + m * (S.zTL / gl + S.zTU / gu) + dw;
+      RIC(Rq + IT, k) += m * (0.5 + 2.0 * t) + m * (-mu_b / gl + mu_b / gu);
       if (do_err) {
         rz_t += m * (0.5 + 2.0 * t) - m * (S.zTL - S.zTU);
         cmax = dmax(cmax, dmax(gl * S.zTL, gu * S.zTU));
@@ -486,24 +565,16 @@ struct ParkSolver {
         phi -= m * mu_b * (log(gl) + log(gu));
       }
     }
-    if (do_err) {
-      if (pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
-      WV(RED, R_DUAL, k) = e_dual; WV(RED, R_PR, k) = e_pr; WV(RED, R_CMAX, k) = cmax; WV(RED, R_CMIN, k) = cmin;
-      WV(RED, R_SY, k) = sum_y; WV(RED, R_SZ, k) = sum_z; WV(RED, R_TH, k) = th; WV(RED, R_PHI, k) = phi + fobj;
-      WV(RED, R_RT, k) = rz_t; WV(RED, R_F, k) = fobj;
-    }
+    if (do_err && pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
+    out.e_dual = e_dual; out.e_pr = e_pr; out.cmax = cmax; out.cmin = cmin; out.sy = sum_y; out.sz = sum_z;
+    out.th = th; out.phi = phi + fobj; out.rt = rz_t; out.f = fobj; out.ok = ok;
     if (do_asm) {
-      WV(RED, R_OK, k) = (double)ok;
       if (has_u) {
 #pragma unroll
-        for (int e = 0; e < NQ; ++e) WV(QS, e, k) = Q[e];
-#pragma unroll
-        for (int e = 0; e < NYV; ++e) WV(qs, e, k) = q[e];
-#pragma unroll
         for (int i = 0; i < 4; ++i) {
-          WV(DYN, 5 * i + 0, k) = dyn.fx[i][0]; WV(DYN, 5 * i + 1, k) = dyn.fx[i][1]; WV(DYN, 5 * i + 2, k) = dyn.ft[i];
-          WV(DYN, 5 * i + 3, k) = dyn.fu[i][0]; WV(DYN, 5 * i + 4, k) = dyn.fu[i][1];
-          WV(R4, i, k) = r4[i];
+          RIC(RDYN + 5 * i + 0, k) = dyn.fx[i][0]; RIC(RDYN + 5 * i + 1, k) = dyn.fx[i][1]; RIC(RDYN + 5 * i + 2, k) = dyn.ft[i];
+          RIC(RDYN + 5 * i + 3, k) = dyn.fu[i][0]; RIC(RDYN + 5 * i + 4, k) = dyn.fu[i][1];
+          RIC(RR4 + i, k) = r4[i];
         }
       }
     }
@@ -532,72 +603,198 @@ struct ParkSolver {
     for (int k = N - 1; k >= 0; --k) {
       // P_{k+1}, p_{k+1} are needed by the forward sweep (multipliers)
 #pragma unroll
-      for (int e = 0; e < NP; ++e) WV(RP, e, k + 1) = Pn[e];
+      for (int e = 0; e < NP; ++e) RIC(RPP + e, k + 1) = Pn[e];
 #pragma unroll
-      for (int e = 0; e < NSV; ++e) WV(RP, NP + e, k + 1) = pn[e];
+      for (int e = 0; e < NSV; ++e) RIC(Rpp + e, k + 1) = pn[e];
       DynOut d;
       double r4[4], Q[NQ], q[NYV];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        d.fx[i][0] = WV(DYN, 5 * i + 0, k); d.fx[i][1] = WV(DYN, 5 * i + 1, k); d.ft[i] = WV(DYN, 5 * i + 2, k);
-        d.fu[i][0] = WV(DYN, 5 * i + 3, k); d.fu[i][1] = WV(DYN, 5 * i + 4, k);
-        r4[i] = WV(R4, i, k);
+        d.fx[i][0] = RIC(RDYN + 5 * i + 0, k); d.fx[i][1] = RIC(RDYN + 5 * i + 1, k); d.ft[i] = RIC(RDYN + 5 * i + 2, k);
+        d.fu[i][0] = RIC(RDYN + 5 * i + 3, k); d.fu[i][1] = RIC(RDYN + 5 * i + 4, k);
+        r4[i] = RIC(RR4 + i, k);
       }
 #pragma unroll
-      for (int e = 0; e < NQ; ++e) Q[e] = WV(QS, e, k);
+      for (int e = 0; e < NQ; ++e) Q[e] = RIC(RQ + e, k);
 #pragma unroll
-      for (int e = 0; e < NYV; ++e) q[e] = WV(qs, e, k);
+      for (int e = 0; e < NYV; ++e) q[e] = RIC(Rq + e, k);
       double Pk[NP], pk[NSV];
       RicStage G;
       ok &= riccati_step(d, r4, Q, q, Pn, pn, Pk, pk, G);
 #pragma unroll
-      for (int j = 0; j < NSV; ++j) { WV(RK, j, k) = G.K[0][j]; WV(RK, NSV + j, k) = G.K[1][j]; }
-      WV(RK, 14, k) = G.kf[0]; WV(RK, 15, k) = G.kf[1];
+      for (int j = 0; j < NSV; ++j) { RIC(RK + j, k) = G.K[0][j]; RIC(RK + NSV + j, k) = G.K[1][j]; }
+      RIC(RK + 14, k) = G.kf[0]; RIC(RK + 15, k) = G.kf[1];
 #pragma unroll
       for (int e = 0; e < NP; ++e) Pn[e] = Pk[e];
 #pragma unroll
       for (int e = 0; e < NSV; ++e) pn[e] = pk[e];
     }
-    // root: x_0, w_0 fixed; dt free (variable time)
+    return ok & kkt_root_forward(C, Pn[sym_idx<NSV>(IT, IT)], pn[IT]);
+  }
+
+  // root of the recursion (x_0, w_0 fixed; dt free if variable time) + forward roll-out of the primal step.
+  // Light and strictly sequential: run by one thread.  The new multipliers of the dynamics rows are computed
+  // afterwards, stage-parallel, in recover_stage().
+  OBCA_HD static int kkt_root_forward(const PkCtx& C, double ptt, double pt) {
+    const ParkProblem& P = *C.P;
+    ProbState& S = *C.S;
+    const int N = P.N;
+    int ok = 1;
     double dt = 0.0;
-    if (!fix) {
-      double ptt = Pn[sym_idx<NSV>(IT, IT)];
+    if (!P.fix_time) {
       if (!(ptt > 0.0)) { ok = 0; ptt = 1e300; }
-      dt = -pn[IT] / ptt;
+      dt = -pt / ptt;
     }
     S.dt = dt;
-    // forward
     double s[NSV] = {0, 0, 0, 0, 0, 0, dt};
     for (int k = 0; k < N; ++k) {
-      double u0 = WV(RK, 14, k), u1 = WV(RK, 15, k);
+      double u0 = RIC(RK + 14, k), u1 = RIC(RK + 15, k);
 #pragma unroll
-      for (int j = 0; j < NSV; ++j) { u0 += WV(RK, j, k) * s[j]; u1 += WV(RK, NSV + j, k) * s[j]; }
+      for (int j = 0; j < NSV; ++j) { u0 += RIC(RK + j, k) * s[j]; u1 += RIC(RK + NSV + j, k) * s[j]; }
       WA(dDE, k) = u0; WA(dAC, k) = u1;
-      double sn[NSV];
+      double sn[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        sn[i] = WV(R4, i, k) + WV(DYN, 5 * i + 0, k) * s[IP] + WV(DYN, 5 * i + 1, k) * s[IV] + WV(DYN, 5 * i + 2, k) * s[IT] +
-                WV(DYN, 5 * i + 3, k) * u0 + WV(DYN, 5 * i + 4, k) * u1;
+        sn[i] = RIC(RR4 + i, k) + RIC(RDYN + 5 * i + 0, k) * s[IP] + RIC(RDYN + 5 * i + 1, k) * s[IV] +
+                RIC(RDYN + 5 * i + 2, k) * s[IT] + RIC(RDYN + 5 * i + 3, k) * u0 + RIC(RDYN + 5 * i + 4, k) * u1;
       }
       sn[0] += s[IX]; sn[1] += s[IY];
-      sn[IWD] = u0; sn[IWA] = u1; sn[IT] = s[IT];
-      // new multiplier of the dynamics row k:  pi+ = -(P_{k+1} s_{k+1} + p_{k+1})_x
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double acc = WV(RP, NP + i, k + 1);
-#pragma unroll
-        for (int l = 0; l < NSV; ++l) acc += WV(RP, sym_idx_any<NSV>(i, l), k + 1) * sn[l];
-        WV(PIn, i, k) = -acc;
-      }
       if (k + 1 < N) { WA(dX, k + 1) = sn[0]; WA(dY, k + 1) = sn[1]; WA(dPS, k + 1) = sn[2]; WA(dVL, k + 1) = sn[3]; }
-#pragma unroll
-      for (int i = 0; i < NSV; ++i) s[i] = sn[i];
+      else { S.eN[0] = sn[0]; S.eN[1] = sn[1]; S.eN[2] = sn[2]; S.eN[3] = sn[3]; }
+      s[0] = sn[0]; s[1] = sn[1]; s[2] = sn[2]; s[3] = sn[3]; s[IWD] = u0; s[IWA] = u1;
     }
     WA(dX, 0) = 0.0; WA(dY, 0) = 0.0; WA(dPS, 0) = 0.0; WA(dVL, 0) = 0.0;
     WA(dX, N) = 0.0; WA(dY, N) = 0.0; WA(dPS, N) = 0.0; WA(dVL, N) = 0.0;
     WA(dDE, N) = 0.0; WA(dAC, N) = 0.0;
     return ok;
   }
+
+#if defined(__CUDA_ARCH__)
+  // -------------------------------------------------------------------------------------------------
+  // Device version of the backward sweep: warp 0 cooperates, nothing is replicated.
+  //   lane l (< 7) owns ROW l of the value function P (7 doubles) and p_l;
+  //   step 1: lane l forms row l of T = P Phi (9 values, Phi sparse) and g_l = p_l + P(l,:) r~ -> shared tile
+  //   step 2: lane j (< 9) reads COLUMN j of T, forms column j of H = Q + Phi' T and hv_j
+  //   step 3: 2x2 pivot on (de, a) via shuffles; lane j (< 7) ends with column j of the new P, which by symmetry
+  //           is the row it must own for the next stage.
+  // Same arithmetic as riccati_step(); the stage slot lives in shared memory.
+  // -------------------------------------------------------------------------------------------------
+  __device__ static int kkt_solve_warp(const PkCtx& C, double* tile /* >= 7*9+7 doubles of shared memory */) {
+    const ParkProblem& Pp = *C.P;
+    const int N = Pp.N;
+    const int lane = threadIdx.x & 31;
+    const int l7 = lane < NSV ? lane : NSV - 1;     // row owned in step 1
+    const int j = lane < NYV ? lane : NYV - 1;      // column owned in step 2
+    const unsigned FULL = 0xffffffffu;
+    double Prow[NSV], pl;
+#pragma unroll
+    for (int b = 0; b < NSV; ++b) Prow[b] = 0.0;
+    pl = 0.0;
+    const double rho = 1.0 / C.O->dc;
+    if (l7 < 4) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Prow[b] = (b == l7) ? rho : 0.0;
+      pl = -WV(PI, l7, N - 1);
+    }
+    int ok = 1;
+    for (int k = N - 1; k >= 0; --k) {
+      double* slot = C.ric + k * RSTRIDE;
+      double* nslot = C.ric + (k + 1) * RSTRIDE;
+      // P_{k+1}, p_{k+1} -> slot k+1 (consumed Q/q space) for the multiplier recovery
+      if (lane < NSV) {
+#pragma unroll
+        for (int b = 0; b < NSV; ++b)
+          if (b >= lane) nslot[RPP + sym_idx<NSV>(lane, b)] = Prow[b];
+        nslot[Rpp + lane] = pl;
+      }
+      // ---- step 1: row l of T = P Phi, g_l ----
+      {
+        double Tr[NYV];
+        double gl = pl;
+        Tr[IX] = Prow[0]; Tr[IY] = Prow[1]; Tr[IWD] = 0.0; Tr[IWA] = 0.0;
+        double tp = 0.0, tv = 0.0, tt = Prow[6], td = Prow[4], ta = Prow[5];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const double pm = Prow[m];
+          tp += pm * slot[RDYN + 5 * m + 0]; tv += pm * slot[RDYN + 5 * m + 1]; tt += pm * slot[RDYN + 5 * m + 2];
+          td += pm * slot[RDYN + 5 * m + 3]; ta += pm * slot[RDYN + 5 * m + 4];
+          gl += pm * slot[RR4 + m];
+        }
+        Tr[IP] = tp; Tr[IV] = tv; Tr[IT] = tt; Tr[IDE] = td; Tr[IAC] = ta;
+        if (lane < NSV) {
+#pragma unroll
+          for (int c = 0; c < NYV; ++c) tile[lane * NYV + c] = Tr[c];
+          tile[NSV * NYV + lane] = gl;
+        }
+      }
+      __syncwarp();
+      // ---- step 2: column j of H = Q + Phi' T, hv_j = q_j + phi_j . g ----
+      double H[NYV], hv;
+      {
+        double T[NSV], g[NSV];
+#pragma unroll
+        for (int a = 0; a < NSV; ++a) { T[a] = tile[a * NYV + j]; g[a] = tile[NSV * NYV + a]; }
+        double fx0[4], fx1[4], ft[4], fu0[4], fu1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          fx0[i] = slot[RDYN + 5 * i + 0]; fx1[i] = slot[RDYN + 5 * i + 1]; ft[i] = slot[RDYN + 5 * i + 2];
+          fu0[i] = slot[RDYN + 5 * i + 3]; fu1[i] = slot[RDYN + 5 * i + 4];
+        }
+        double Qc[NYV];
+#pragma unroll
+        for (int i = 0; i < NYV; ++i) Qc[i] = slot[RQ + (i <= j ? sym_idx<NYV>(i, j) : sym_idx<NYV>(j, i))];
+        H[IX] = Qc[IX] + T[0];
+        H[IY] = Qc[IY] + T[1];
+        H[IP] = Qc[IP] + fx0[0] * T[0] + fx0[1] * T[1] + fx0[2] * T[2] + fx0[3] * T[3];
+        H[IV] = Qc[IV] + fx1[0] * T[0] + fx1[1] * T[1] + fx1[2] * T[2] + fx1[3] * T[3];
+        H[IWD] = Qc[IWD];
+        H[IWA] = Qc[IWA];
+        H[IT] = Qc[IT] + ft[0] * T[0] + ft[1] * T[1] + ft[2] * T[2] + ft[3] * T[3] + T[6];
+        H[IDE] = Qc[IDE] + fu0[0] * T[0] + fu0[1] * T[1] + fu0[2] * T[2] + fu0[3] * T[3] + T[4];
+        H[IAC] = Qc[IAC] + fu1[0] * T[0] + fu1[1] * T[1] + fu1[2] * T[2] + fu1[3] * T[3] + T[5];
+        // phi_j . g with the sparsity of column j of Phi
+        double pg = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double c = 0.0;
+          c = (j == IP) ? fx0[i] : c; c = (j == IV) ? fx1[i] : c; c = (j == IT) ? ft[i] : c;
+          c = (j == IDE) ? fu0[i] : c; c = (j == IAC) ? fu1[i] : c;
+          c = (j == i && i < 2) ? 1.0 : c;
+          pg += c * g[i];
+        }
+        pg += (j == IDE) ? g[4] : 0.0; pg += (j == IAC) ? g[5] : 0.0; pg += (j == IT) ? g[6] : 0.0;
+        hv = slot[Rq + j] + pg;
+      }
+      __syncwarp();
+      // ---- step 3: eliminate u = (de, a) ----
+      double h77 = __shfl_sync(FULL, H[IDE], IDE), h78 = __shfl_sync(FULL, H[IAC], IDE), h88 = __shfl_sync(FULL, H[IAC], IAC);
+      const double hv7 = __shfl_sync(FULL, hv, IDE), hv8 = __shfl_sync(FULL, hv, IAC);
+      // 2x2 SPD pivot with ONE reciprocal (the divisions are the longest dependent chain of the sweep):
+      // positive definite  <=>  h77 > 0 and det > 0
+      double det = h77 * h88 - h78 * h78;
+      if (!(h77 > 0.0) || !(det > 0.0)) { ok = 0; det = 1e300; }
+      const double idet = fast_rcp(det);
+      const double n00 = h88 * idet, n01 = -h78 * idet, n11 = h77 * idet;
+      const double K0 = -(n00 * H[IDE] + n01 * H[IAC]), K1 = -(n01 * H[IDE] + n11 * H[IAC]);   // column j of the gain
+      const double kf0 = -(n00 * hv7 + n01 * hv8), kf1 = -(n01 * hv7 + n11 * hv8);
+#pragma unroll
+      for (int i = 0; i < NSV; ++i) {
+        const double c7 = __shfl_sync(FULL, H[i], IDE), c8 = __shfl_sync(FULL, H[i], IAC);   // H(i, de), H(i, a)
+        Prow[i] = H[i] + c7 * K0 + c8 * K1;      // column j of the new P == row j (lanes >= 7 hold garbage, unused)
+      }
+      pl = hv + H[IDE] * kf0 + H[IAC] * kf1;
+      // ---- gains into the slot (Q/q of this stage are consumed) ----
+      if (lane < NSV) { slot[RK + lane] = K0; slot[RK + NSV + lane] = K1; }
+      if (lane == 0) { slot[RK + 14] = kf0; slot[RK + 15] = kf1; }
+      __syncwarp();
+    }
+    const double ptt = __shfl_sync(FULL, Prow[IT], IT), pt = __shfl_sync(FULL, pl, IT);
+    int okr = 1;
+    if (lane == 0) okr = kkt_root_forward(C, ptt, pt);
+    okr = __shfl_sync(FULL, okr, 0);
+    return ok & okr;
+  }
+#endif
 
   // fraction-to-the-boundary helpers
   OBCA_HD static void ftb(double gap, double dgap, double tau, double& amax) {
@@ -609,7 +806,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // K4a: recover local steps, slack steps; step-length partials; directional derivative of the barrier objective
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void recover_stage(const PkCtx& C, int k) {
+  OBCA_HD static void recover_stage(const PkCtx& C, int k, StepPart& out) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -622,6 +819,20 @@ struct ParkSolver {
     double sn_, cs_;
     sincos(ps, &sn_, &cs_);
     double apr = 1.0, adu = 1.0, dphi = 0.0;
+    if (k < N) {
+      // new multiplier of the dynamics row k:  pi+ = -(P_{k+1} s_{k+1} + p_{k+1})_x   (costate of the Riccati sweep)
+      double sn[NSV];
+      if (k + 1 < N) { sn[0] = WA(dX, k + 1); sn[1] = WA(dY, k + 1); sn[2] = WA(dPS, k + 1); sn[3] = WA(dVL, k + 1); }
+      else { sn[0] = S.eN[0]; sn[1] = S.eN[1]; sn[2] = S.eN[2]; sn[3] = S.eN[3]; }
+      sn[IWD] = WA(dDE, k); sn[IWA] = WA(dAC, k); sn[IT] = S.dt;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double acc = RIC(Rpp + i, k + 1);
+#pragma unroll
+        for (int l = 0; l < NSV; ++l) acc += RIC(RPP + sym_idx_any<NSV>(i, l), k + 1) * sn[l];
+        WV(PIn, i, k) = -acc;
+      }
+    }
     if (pose_free) {
       const double ex = X - C.in.rx[k], ey = Y - C.in.ry[k], ep = ps - C.in.ryaw[k];
       const double aXl = X - P.xyb[0], aXu = P.xyb[1] - X, aYl = Y - P.xyb[2], aYu = P.xyb[3] - Y, aVl = v + 1.0, aVu = 2.0 - v;
@@ -674,11 +885,8 @@ struct ParkSolver {
         swap_rows(R, Qv, piv);
         obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
       }
-      double fac[LD::NFAC];
-#pragma unroll
-      for (int e = 0; e < LD::NFAC; ++e) fac[e] = WV(LF, j * C.L.nfac + e, k);
       ObsStep<VM> St;
-      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, fac, dX, dY, dP, St);
+      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, &WV(LF, j * C.L.nfac, k), C.L.NSP, dX, dY, dP, St);
       // un-permute lambda
       if (piv != 0) {
 #pragma unroll
@@ -733,13 +941,13 @@ struct ParkSolver {
       ftb(S.zTU, dzb(S.zTU, gu, -S.dt, mu_b), tau, adu);
       dphi += m * (0.5 + 2.0 * t - mu_b / gl + mu_b / gu) * S.dt;
     }
-    WV(RED, R_APR, k) = apr; WV(RED, R_ADU, k) = adu; WV(RED, R_DPHI, k) = dphi;
+    out.apr = apr; out.adu = adu; out.dphi = dphi;
   }
 
   // ---------------------------------------------------------------------------------------------------
   // K4b: merit-function partials at the trial point z + alpha dz  (theta = ||c||_1, phi = barrier objective)
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void merit_stage(const PkCtx& C, int k, double alpha) {
+  OBCA_HD static void merit_stage(const PkCtx& C, int k, double alpha, MeritPart& out) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -817,8 +1025,8 @@ struct ParkSolver {
       bad |= !(gl > 0.0) || !(gu > 0.0);
       phi += m * (0.5 * t + t * t) - m * mu_b * (log(gl) + log(gu));
     }
-    WV(RED, R_TH, k) = th;
-    WV(RED, R_PHI, k) = bad ? 1e300 : phi;
+    out.th = th;
+    out.phi = bad ? 1e300 : phi;
   }
 
   // ---------------------------------------------------------------------------------------------------
@@ -931,19 +1139,11 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // serial helpers (thread 0)
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void reduce_errors(const PkCtx& C) {
+  OBCA_HD static void apply_errors(const PkCtx& C, const EvalPart& e) {
     ProbState& S = *C.S;
-    const int NS = C.P->N + 1;
-    double e_dual = 0, e_pr = 0, cmax = 0, cmin = 1e300, sy = 0, sz = 0, th = 0, ph = 0, rt = 0, f = 0;
-    for (int k = 0; k < NS; ++k) {
-      e_dual = dmax(e_dual, WV(RED, R_DUAL, k)); e_pr = dmax(e_pr, WV(RED, R_PR, k));
-      cmax = dmax(cmax, WV(RED, R_CMAX, k)); cmin = dmin_(cmin, WV(RED, R_CMIN, k));
-      sy += WV(RED, R_SY, k); sz += WV(RED, R_SZ, k); th += WV(RED, R_TH, k); ph += WV(RED, R_PHI, k);
-      rt += WV(RED, R_RT, k); f += WV(RED, R_F, k);
-    }
-    if (!C.P->fix_time) e_dual = dmax(e_dual, dabs(rt));
-    S.e_dual = e_dual; S.e_pr = e_pr; S.e_cmax = cmax; S.e_cmin = cmin; S.sum_y = sy; S.sum_z = sz;
-    S.th_k = th; S.ph_k = ph; S.rz_t = rt; S.f_k = f;
+    S.e_dual = C.P->fix_time ? e.e_dual : dmax(e.e_dual, dabs(e.rt));
+    S.e_pr = e.e_pr; S.e_cmax = e.cmax; S.e_cmin = e.cmin; S.sum_y = e.sy; S.sum_z = e.sz;
+    S.th_k = e.th; S.ph_k = e.phi; S.rz_t = e.rt; S.f_k = e.f;
   }
   // number of multipliers (for Ipopt's s_d, s_c scaling)
   OBCA_HD static void mult_counts(const ParkProblem& P, double& n_mult, double& n_bmult) {
@@ -980,6 +1180,10 @@ struct ParkSolver {
       S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
       S.mu = O.mu_init; S.tau = dmax(O.tau_min, 1.0 - O.mu_init);
       S.dw = 0.0; S.dw_last = 0.0; S.nfilt = 0; S.status = 0; S.iters = 0; S.n_fact = 0;
+#if defined(__CUDA_ARCH__)
+      if (!restart) for (int i = 0; i < 8; ++i) S.prof[i] = 0;
+      S.tmark = clock64();
+#endif
     }
     OBCA_SYNC();
     OBCA_FOR_STAGES(k, NS) init_stage(C, k, restart);
@@ -992,10 +1196,14 @@ struct ParkSolver {
       // ---- K1: evaluate (errors + assembly with the current mu and dw = 0) ----
       OBCA_SERIAL { S.dw = 0.0; }
       OBCA_SYNC();
-      OBCA_FOR_STAGES(k, NS) stage_eval(C, k, true, true);
-      OBCA_SYNC();
+      EvalPart ep;
+      part_init(ep);
+      OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
+      OBCA_REDUCE(ep);
+      OBCA_PROF(0); OBCA_PROF_COUNT(7);
       OBCA_SERIAL {
-        reduce_errors(C);
+        apply_errors(C, ep);
+        S.ok = ep.ok;
         if (first) {
           S.theta_max = 1e4 * dmax(1.0, S.th_k);
           S.theta_min = 1e-4 * dmax(1.0, S.th_k);
@@ -1020,23 +1228,33 @@ struct ParkSolver {
       }
       first = false;
       OBCA_SYNC();
+      OBCA_PROF(5);
       if (S.flag == 1) break;
       if (S.flag == 2) {   // mu changed: the barrier terms of the stage models (and phi) are stale
-        OBCA_FOR_STAGES(k, NS) stage_eval(C, k, true, true);
+        part_init(ep);
+        OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
+        OBCA_REDUCE(ep);
+        OBCA_PROF(0); OBCA_PROF_COUNT(7);
+        OBCA_SERIAL { apply_errors(C, ep); S.ok = ep.ok; }
         OBCA_SYNC();
-        OBCA_SERIAL { reduce_errors(C); }
-        OBCA_SYNC();
+        OBCA_PROF(5);
       }
       // ---- K3 with inertia correction (Ipopt Algorithm IC) ----
       bool tried0 = false;
       for (;;) {
+#if defined(__CUDA_ARCH__)
+        if (S.ok && threadIdx.x < 32) {
+          const int ok = kkt_solve_warp(C, C.tile);
+          __syncwarp();
+          if (threadIdx.x == 0) S.ok = ok;
+        }
+#else
+        if (S.ok) S.ok = kkt_solve(C);
+#endif
+        OBCA_SYNC();
         OBCA_SERIAL {
-          int ok = 1;
-          for (int k = 0; k < NS; ++k) ok &= (WV(RED, R_OK, k) != 0.0);
-          if (ok) ok = kkt_solve(C);
           S.n_fact++;
-          S.ok = ok;
-          if (!ok) {
+          if (!S.ok) {
             if (S.dw == 0.0) S.dw = (S.dw_last == 0.0) ? O.dw_first : dmax(O.dw_min, O.kw_minus * S.dw_last);
             else S.dw *= (S.dw_last == 0.0) ? O.kw_plus_first : O.kw_plus;
             if (S.dw > O.dw_max) { S.status = -2; S.ok = -1; }
@@ -1045,20 +1263,25 @@ struct ParkSolver {
           }
         }
         OBCA_SYNC();
+        OBCA_PROF(1);
         if (S.ok != 0) break;
-        OBCA_FOR_STAGES(k, NS) stage_eval(C, k, false, true);
+        part_init(ep);
+        OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, false, true, e1); part_merge(ep, e1); }
+        OBCA_REDUCE(ep);
+        OBCA_SERIAL { S.ok = ep.ok; }
         OBCA_SYNC();
+        OBCA_PROF(0); OBCA_PROF_COUNT(7);
         (void)tried0;
       }
       if (S.ok < 0) break;
       // ---- K4: recover, step lengths, filter line search ----
-      OBCA_FOR_STAGES(k, NS) recover_stage(C, k);
-      OBCA_SYNC();
+      StepPart sp;
+      part_init(sp);
+      OBCA_FOR_STAGES(k, NS) { StepPart s1; recover_stage(C, k, s1); part_merge(sp, s1); }
+      OBCA_REDUCE(sp);
+      OBCA_PROF(2);
       OBCA_SERIAL {
-        double apr = 1.0, adu = 1.0, dphi = 0.0;
-        for (int k = 0; k < NS; ++k) {
-          apr = dmin_(apr, WV(RED, R_APR, k)); adu = dmin_(adu, WV(RED, R_ADU, k)); dphi += WV(RED, R_DPHI, k);
-        }
+        const double apr = sp.apr, adu = sp.adu, dphi = sp.dphi;
         S.a_pr = apr; S.a_du = adu; S.dphi = dphi;
         const double th = S.th_k;
         if (dphi < 0.0 && th <= S.theta_min)
@@ -1073,11 +1296,13 @@ struct ParkSolver {
       OBCA_SYNC();
       for (int nbt = 0;; ++nbt) {
         const double alpha = S.alpha;
-        OBCA_FOR_STAGES(k, NS) merit_stage(C, k, alpha);
-        OBCA_SYNC();
+        MeritPart mp;
+        part_init(mp);
+        OBCA_FOR_STAGES(k, NS) { MeritPart m1; merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
+        OBCA_REDUCE(mp);
+        OBCA_PROF(3); OBCA_PROF_COUNT(6);
         OBCA_SERIAL {
-          double th = 0.0, ph = 0.0;
-          for (int k = 0; k < NS; ++k) { th += WV(RED, R_TH, k); ph += WV(RED, R_PHI, k); }
+          const double th = mp.th, ph = mp.phi;
           S.th_t = th; S.ph_t = ph;
           bool in_filter = th >= S.theta_max || !(ph < 1e299);
           for (int i = 0; i < S.nfilt && !in_filter; ++i) in_filter = (th >= S.filt_th[i] && ph >= S.filt_ph[i]);
@@ -1103,6 +1328,7 @@ struct ParkSolver {
           }
         }
         OBCA_SYNC();
+        OBCA_PROF(5);
         if (S.flag != 0) break;
       }
       if (S.flag < 0) break;
@@ -1116,6 +1342,7 @@ struct ParkSolver {
         }
       }
       OBCA_SYNC();
+      OBCA_PROF(4);
     }
   }
 };

@@ -17,7 +17,8 @@ template <int VM, bool SDV>
 static void run_one(const ParkProblem& P, const IpmOpts& O, const PkLay& L, double* W, const PkInputs& in,
                     const PkOutputs& out, ProbState& S) {
   PkCtx C;
-  C.P = &P; C.O = &O; C.L = L; C.W = W; C.S = &S; C.in = in;
+  std::vector<double> ric((size_t)(P.N + 1) * RSTRIDE, 0.0);
+  C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = ric.data(); C.red_scratch = nullptr; C.tile = nullptr; C.S = &S; C.in = in;
   ParkSolver<VM, SDV>::solve(C);
   for (int k = 0; k <= P.N; ++k) ParkSolver<VM, SDV>::store_stage(C, k, out);
 }
