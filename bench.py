@@ -259,6 +259,31 @@ def gpu_arm(args):
                          "frac": achieved / hbm, "traffic": None,
                          "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x (iterations+1) per problem (SURVEY 8d, fused K1); "
                                  f"peak {how}; the persistent solver is FP64/latency bound, see DESIGN.md"}}
+    # ---- K1 stand-alone (fused constraint / Lagrangian-gradient evaluation) at the solution points: HBM roofline ----
+    nn = C.c_longlong(); mm = C.c_longlong()
+    lib.obca_parking_eval_sizes(C.c_int(N), C.c_int(nOb), NP(vOb), C.c_int(1), C.byref(nn), C.byref(mm))
+    n_z, m_c = nn.value, mm.value
+    yk1 = torch.randn((B, m_c), dtype=torch.float64, device="cuda")
+    ck1 = torch.empty((B, m_c), dtype=torch.float64, device="cuda"); gk1 = torch.empty((B, n_z), dtype=torch.float64, device="cuda")
+    fk1 = torch.empty((B, NS), dtype=torch.float64, device="cuda")
+    k1ms = np.zeros(1)
+
+    def k1(reps):
+        rc = lib.obca_parking_eval_batch_dev(C.c_int(B), C.c_int(N), C.c_int(nOb), NP(vOb), NP(A), NP(b), P(din["x0"]), P(din["xF"]),
+                                             C.c_double(sc["Ts"]), C.c_double(sc["L"]), NP(ego), NP(xyb), P(din["rx"]), P(din["ry"]),
+                                             P(din["ryaw"]), P(dout["xp"]), P(dout["up"]), P(dout["ts"]), P(dout["lp"]), P(dout["np"]),
+                                             P(dout["sl"]), P(yk1), C.c_int(0), C.c_int(1), C.byref(opts), P(ck1), P(gk1), P(fk1),
+                                             C.c_int(reps), NP(k1ms))
+        assert rc == 0, lib.obca_last_error()
+        return float(k1ms[0])
+    k1(3)
+    k1_ms = k1(20)
+    k1_bytes = 8.0 * (2 * n_z + 2 * m_c + 3 * NS) * B
+    k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+    line["roofline_k1"] = {"bound": "hbm", "kernel": "k_parking_eval<2,true>", "achieved": k1_gbs, "peak": hbm, "unit": "GB/s",
+                           "frac": k1_gbs / hbm, "traffic": None, "ms_per_launch": k1_ms,
+                           "note": f"stand-alone fused K1: 8*(2n+2m+3(N+1)) = {int(k1_bytes / B)} B/problem/evaluation, B={B}; working set "
+                                   f"{k1_bytes / 1e6:.0f} MB > L2; mean of 20 back-to-back launches"}
     prof = (C.c_ulonglong * 8)()
     if lib.obca_last_profile(C.c_int(local), prof) == 0:
         names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]

@@ -108,17 +108,23 @@ int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, c
  * #merit evaluations, #K1 evaluations}.  Diagnostic only. */
 int obca_last_profile(int device, unsigned long long* out8);
 
-/* K1 stand-alone: fused evaluation of the OBCA NLP at B given points (no solve).  Reads the stacked
- * (x, u, ts, l, n, sl) batch and the multipliers `duals` (layout below), writes per problem
- *   out[0] = objective f, out[1] = ||c||_inf, out[2] = ||c||_1, out[3] = ||grad L||_inf, out[4] = max compl. product
- * duals per problem: pi 4xN | y_rot 2nOb x(N+1) | y_norm nOb x(N+1) | v_dist nOb x(N+1)   (as written by the solver
- * when opts asks for them; pass NULL for all-zero multipliers).  Device pointers. */
+/* K1 stand-alone: fused evaluation of the parking NLP in the REFERENCE's formulation at B given points (no solve);
+ * what JuMP's eval_g / eval_grad_f / eval_jac_g' * y do for Ipopt (ParkingSignedDist.jl:240), one thread per
+ * (problem, stage).  Per problem it reads z = (xp, ts, up, lp, np[, sl]) (n values), the row multipliers y (m values,
+ * may be NULL = zeros) and rx, ry, ryaw, and writes c (m rows; inequality rows = their bodies),
+ * gradL = grad_z [f + y'c] (n values) and fk (objective per stage, N+1 values).
+ *   rows of c / y:  start 4 | end 4 | dyn 4xN | chain N | rate N | norm nOb x(N+1) | rot 2nOb x(N+1) | dist nOb x(N+1)
+ *   entries of gradL: x 4x(N+1) | timeScale (N+1) | u 2xN | l Vx(N+1) | n 4nOb x(N+1) | sl nOb x(N+1) (SD only)
+ * Algorithmic HBM bytes per problem per call: 8 * (2n + 2m + 3(N+1))  (fused variant).
+ * All batch arrays are DEVICE pointers.  `reps` launches are timed together; kernel_ms = mean per launch. */
+int obca_parking_eval_sizes(int N, int nOb, const int* vOb, int signed_dist, long long* n_out, long long* m_out);
 int obca_parking_eval_batch_dev(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
                                 const double* x0, const double* xF, double Ts, double L, const double* ego,
                                 const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
                                 const double* xp, const double* up, const double* ts, const double* lp,
-                                const double* np, const double* sl, const double* duals, int fixTime,
-                                int signed_dist, const obca_opts* opts, double* out, double* kernel_ms);
+                                const double* np, const double* sl, const double* y, int fixTime, int signed_dist,
+                                const obca_opts* opts, double* c_out, double* gradL_out, double* fk_out, int reps,
+                                double* kernel_ms);
 
 #ifdef __cplusplus
 }

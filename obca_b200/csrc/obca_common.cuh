@@ -12,9 +12,12 @@
 #ifdef __CUDACC__
 #define OBCA_HD __host__ __device__ __forceinline__
 #define OBCA_D __device__ __forceinline__
+// big per-stage phase functions: ONE copy in the kernel (the solver kernel is instruction-cache bound otherwise)
+#define OBCA_HD_NI __host__ __device__ __noinline__
 #else
 #define OBCA_HD inline
 #define OBCA_D inline
+#define OBCA_HD_NI inline
 #endif
 
 #define OBCA_MAX_OB 5      // obstacles per problem

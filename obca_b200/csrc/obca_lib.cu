@@ -18,6 +18,7 @@
 #include "../../include/obca.h"
 #include "obca_check.cuh"
 #include "obca_dualws.cuh"
+#include "obca_eval.cuh"
 #include "obca_host.h"
 
 using namespace obca;
@@ -36,7 +37,7 @@ struct BatchPtrs {
 };
 
 #ifndef OBCA_MIN_BLOCKS
-#define OBCA_MIN_BLOCKS 4
+#define OBCA_MIN_BLOCKS 3
 #endif
 template <int VM, bool SDV>
 __global__ void __launch_bounds__(128, OBCA_MIN_BLOCKS)
@@ -44,7 +45,7 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
                 const BatchPtrs bp, double* __restrict__ Wall, int* __restrict__ counter) {
   extern __shared__ double s_ric[];     // (N+1) x RSTRIDE stage slots of the KKT solve
   __shared__ ProbState S;
-  __shared__ double s_tile[72];          // T = P Phi tile of the KKT sweep
+  __shared__ double s_tile[144];         // exchange tile of the warp-cooperative KKT sweep (obca_solver.cuh)
   __shared__ double s_red[4 * 12];      // block_reduce scratch (4 warps x sizeof(EvalPart))
   __shared__ int s_b;
   __shared__ ChkPart s_chk[4];
@@ -69,17 +70,16 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
     out.sl = bp.sl ? bp.sl + (size_t)nOb * NS * b : nullptr;
     out.duals = bp.duals ? bp.duals + ((size_t)4 * N + (size_t)4 * nOb * NS) * b : nullptr;
 
-    ParkSolver<VM, SDV>::solve(C, 0);
-    __syncthreads();
-    int iters = S.iters;
-    int status = S.status;
-    // ParkingSignedDist.jl:256-263 / ParkingDist.jl:245-263: one more solve from the last iterate
-    if (status != 1 && bp.retry) {
-      __syncthreads();
-      ParkSolver<VM, SDV>::solve(C, 1);
+    // first attempt from the warm start; on failure one more solve from the last iterate
+    // (ParkingSignedDist.jl:256-263 / ParkingDist.jl:245-263).  One call site: the solver body exists once.
+    int iters = 0, status = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      ParkSolver<VM, SDV>::solve(C, attempt);
       __syncthreads();
       iters += S.iters;
       status = S.status;
+      if (status == 1 || !bp.retry) break;
+      __syncthreads();
     }
     for (int k = threadIdx.x; k < NS; k += blockDim.x) ParkSolver<VM, SDV>::store_stage(C, k, out);
     __syncthreads();
@@ -152,6 +152,29 @@ __global__ void k_dualws(const __grid_constant__ ParkProblem P, int B, const dou
 #pragma unroll
     for (int m = 0; m < 4; ++m) np[(size_t)4 * nOb * NS * b + (size_t)(4 * j + m) * NS + k] = mu[m];
     if (dd) dd[(size_t)nOb * NS * b + (size_t)j * NS + k] = d;
+  }
+}
+
+// K1 stand-alone (obca_eval.cuh): one thread per (problem, stage); consecutive threads = consecutive stages, so every
+// warp streams contiguous slices of the stacked (x, u, l, n, sl, y) arrays.
+template <int VM, bool SDV>
+__global__ void __launch_bounds__(128)
+k_parking_eval(const __grid_constant__ ParkProblem P, int B, EvalIn in, EvalOut out) {
+  const int N = P.N, NS = N + 1, nOb = P.nOb, V = P.V;
+  const size_t m = eval_m(P), n = eval_n(P);
+  const size_t total = (size_t)B * NS;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = idx / NS;
+    const int k = (int)(idx - b * NS);
+    EvalIn ib;
+    ib.x0 = in.x0 + 4 * b; ib.xF = in.xF + 4 * b; ib.rx = in.rx + NS * b; ib.ry = in.ry + NS * b; ib.ryaw = in.ryaw + NS * b;
+    ib.xp = in.xp + (size_t)4 * NS * b; ib.up = in.up + (size_t)2 * N * b; ib.ts = in.ts ? in.ts + NS * b : nullptr;
+    ib.lp = in.lp + (size_t)V * NS * b; ib.np = in.np + (size_t)4 * nOb * NS * b;
+    ib.sl = in.sl ? in.sl + (size_t)nOb * NS * b : nullptr;
+    ib.y = in.y ? in.y + m * b : nullptr;
+    EvalOut ob;
+    ob.c = out.c + m * b; ob.gradL = out.gradL + n * b; ob.fk = out.fk + NS * b;
+    eval_stage<VM, SDV>(P, k, ib, ob);
   }
 }
 
@@ -331,6 +354,16 @@ static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, Bat
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
   if (seconds) *seconds = ms * 1e-3;
+  return 0;
+}
+
+template <int VM, bool SDV>
+static int launch_eval(DevCtx& c, const ParkProblem& P, int B, const EvalIn& in, const EvalOut& out, int reps) {
+  const size_t total = (size_t)B * (P.N + 1);
+  const int threads = 128;
+  int blocks = (int)((total + threads - 1) / threads);
+  for (int r = 0; r < reps; ++r) k_parking_eval<VM, SDV><<<blocks, threads, 0, c.st>>>(P, B, in, out);
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -524,12 +557,44 @@ int obca_last_profile(int device, unsigned long long* out8) {
   return 0;
 }
 
-int obca_parking_eval_batch_dev(int, int, int, const int*, const double*, const double*, const double*, const double*,
-                                double, double, const double*, const double*, const double*, const double*,
-                                const double*, const double*, const double*, const double*, const double*,
-                                const double*, const double*, const double*, int, int, const obca_opts*, double*,
-                                double*) {
-  set_err("obca_parking_eval_batch_dev: not built yet");
-  return OBCA_ERR_UNSUPPORTED;
+int obca_parking_eval_sizes(int N, int nOb, const int* vOb, int signed_dist, long long* n_out, long long* m_out) {
+  ParkProblem P;
+  double A[2 * OBCA_MAX_ROWS] = {0}, b[OBCA_MAX_ROWS] = {0}, ego[4] = {1, 1, 1, 1}, xy[4] = {0, 1, 0, 1};
+  if (fill_problem(P, N, nOb, vOb, A, b, 1.0, 1.0, ego, xy, 0, signed_dist)) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  if (n_out) *n_out = (long long)eval_n(P);
+  if (m_out) *m_out = (long long)eval_m(P);
+  return 0;
+}
+
+int obca_parking_eval_batch_dev(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
+                                const double* x0, const double* xF, double Ts, double L, const double* ego,
+                                const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
+                                const double* xp, const double* up, const double* ts, const double* lp,
+                                const double* np, const double* sl, const double* y, int fixTime, int signed_dist,
+                                const obca_opts* opts, double* c_out, double* gradL_out, double* fk_out, int reps,
+                                double* kernel_ms) {
+  if (B <= 0 || !vOb || !A || !b || !x0 || !xF || !ego || !XYbounds || !rx || !ry || !ryaw || !xp || !up || !lp || !np ||
+      !c_out || !gradL_out || !fk_out || (signed_dist && !sl) || (!fixTime && !ts)) { set_err("null argument"); return OBCA_ERR_ARG; }
+  ParkProblem P;
+  if (fill_problem(P, N, nOb, vOb, A, b, Ts, L, ego, XYbounds, fixTime, signed_dist)) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  EvalIn in; in.x0 = x0; in.xF = xF; in.rx = rx; in.ry = ry; in.ryaw = ryaw; in.xp = xp; in.up = up; in.ts = ts; in.lp = lp;
+  in.np = np; in.sl = sl; in.y = y;
+  EvalOut out; out.c = c_out; out.gradL = gradL_out; out.fk = fk_out;
+  if (reps < 1) reps = 1;
+  const int vm = max_vob(P) <= 2 ? 2 : 4;
+  CK(cudaEventRecord(c->ev0, c->st));
+  if (P.signed_dist) rc = vm == 2 ? launch_eval<2, true>(*c, P, B, in, out, reps) : launch_eval<4, true>(*c, P, B, in, out, reps);
+  else rc = vm == 2 ? launch_eval<2, false>(*c, P, B, in, out, reps) : launch_eval<4, false>(*c, P, B, in, out, reps);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev1, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (kernel_ms) *kernel_ms = ms / reps;
+  return 0;
 }
 }

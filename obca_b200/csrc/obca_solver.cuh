@@ -133,10 +133,10 @@ inline PkLay make_layout(const ParkProblem& P, int nfac) {
 // ---- per-stage slot of the KKT solve (shared memory on the device): RSTRIDE doubles per stage ----
 //   after stage_eval(k):   [RQ..] Q (45, packed 9x9) | [Rq..] q (9) | [RDYN..] dynamics Jacobian (20) | [RR4..] residual (4)
 //   after the backward sweep passed stage k:  [RK..] gain K (2x7) + feed-forward (2)  and, in slot k+1,
-//                                             [RPP..] P_{k+1} (28) + p_{k+1} (7)   (the consumed Q/q space is reused)
+//                                             [RPP..] rows 0..3 of P_{k+1} (4x7) + p_{k+1}[0..3]  (consumed Q/q space)
 constexpr int RSTRIDE = 79;   // odd -> conflict-free column accesses
 constexpr int RQ = 0, Rq = 45, RDYN = 54, RR4 = 74;
-constexpr int RK = 0, RPP = 16, Rpp = 44;
+constexpr int RK = 0, RPP = 16, Rpp = 44;   // RPP: rows 0..3 of P_{k+1}, row-major 4x7;  Rpp: p_{k+1}[0..3]
 
 // per-problem scalar state (shared memory on the device)
 struct ProbState {
@@ -265,7 +265,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // restart != 0: re-initialise from the current iterate (the reference's second solve(m) restarts Ipopt from
   // JuMP's stored primal values, ParkingSignedDist.jl:256-263) instead of from the warm-start inputs.
-  OBCA_HD static void init_stage(const PkCtx& C, int k, int restart) {
+  OBCA_HD_NI static void init_stage(const PkCtx& C, int k, int restart) {
     const ParkProblem& P = *C.P;
     const IpmOpts& O = *C.O;
     const int N = P.N;
@@ -309,7 +309,7 @@ struct ParkSolver {
     }
   }
   // slacks need the pushed primal point of the neighbours -> separate phase
-  OBCA_HD static void init_slacks(const PkCtx& C, int k) {
+  OBCA_HD_NI static void init_slacks(const PkCtx& C, int k) {
     const ParkProblem& P = *C.P;
     const IpmOpts& O = *C.O;
     const int N = P.N;
@@ -339,7 +339,7 @@ struct ParkSolver {
   // P1 (K1): fused evaluation at the current iterate.
   //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
+  OBCA_HD_NI static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -603,9 +603,11 @@ struct ParkSolver {
     for (int k = N - 1; k >= 0; --k) {
       // P_{k+1}, p_{k+1} are needed by the forward sweep (multipliers)
 #pragma unroll
-      for (int e = 0; e < NP; ++e) RIC(RPP + e, k + 1) = Pn[e];
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
-      for (int e = 0; e < NSV; ++e) RIC(Rpp + e, k + 1) = pn[e];
+        for (int l = 0; l < NSV; ++l) RIC(RPP + i * NSV + l, k + 1) = Pn[sym_idx_any<NSV>(i, l)];
+        RIC(Rpp + i, k + 1) = pn[i];
+      }
       DynOut d;
       double r4[4], Q[NQ], q[NYV];
 #pragma unroll
@@ -669,130 +671,185 @@ struct ParkSolver {
     return ok;
   }
 
+  // -------------------------------------------------------------------------------------------------
+  // Warp-cooperative KKT sweep (the device path; the host emulation runs the same lane code for 32 lanes in turn).
+  // Nothing is replicated, no branches / selects / index arithmetic inside the stage loop (the loop is
+  // issue-latency bound: every instruction counts).
+  //   lane l (< 7) owns ROW l of the value function P (7 doubles) and p_l
+  //   step 1: lane l: row l of T = P Phi (9 values, Phi sparse), g_l = p_l + P(l,:) r~        -> shared tile
+  //   step 2: lane j (< 9): column j of H = Q + Phi' T and hv_j; the (de, a) columns          -> shared tile
+  //   step 3: 2x2 pivot on (de, a) with ONE reciprocal; lane j (< 7) ends with column j of the new P, which by
+  //           symmetry is the row it owns at the next stage.
+  // Lanes outside the active range park their (meaningless) results in the dump area of the tile.
+  // Tile (doubles): T 7x9 [0,63) | g [63,70) | 0 [70] | zero column [71,91) | H(:,de) [91,100) | H(:,a) [100,109) |
+  //                 hv_de, hv_a [109,111) | dump [112,144)
+  // -------------------------------------------------------------------------------------------------
+  static constexpr int TILE_DOUBLES = 144;
+  struct KktLane {
+    double Prow[NSV], pl;   // row of P / entry of p owned by the lane
+    double H[NYV], hv;      // column of H owned by the lane
+    int qoff[NYV];          // slot offsets of Q(i, j), i = 0..8
+    int dcol;               // offset of the lane's dynamics-Jacobian column in the slot, or -1
+    int gext;               // tile index of the identity entry of Phi' g for this column
+    int tr, gs, hcol, hvst; // tile offsets where the lane writes
+    int ok;
+  };
+  OBCA_HD static void kl_init(KktLane& L, int lane, double* tile, const PkCtx& C) {
+    const int N = C.P->N;
+    const int j = lane < NYV ? lane : NYV - 1;
+#pragma unroll
+    for (int i = 0; i < NYV; ++i) L.qoff[i] = RQ + (i <= j ? sym_idx<NYV>(i, j) : sym_idx<NYV>(j, i));
+    L.dcol = (j == IP) ? RDYN + 0 : (j == IV) ? RDYN + 1 : (j == IT) ? RDYN + 2 : (j == IDE) ? RDYN + 3 : (j == IAC) ? RDYN + 4 : -1;
+    L.gext = (j == IX) ? 63 + 0 : (j == IY) ? 63 + 1 : (j == IT) ? 63 + 6 : (j == IDE) ? 63 + 4 : (j == IAC) ? 63 + 5 : 70;
+    L.tr = (lane < NSV) ? lane * NYV : 112;
+    L.gs = (lane < NSV) ? 63 + lane : 124;
+    L.hcol = (lane == IDE) ? 91 : (lane == IAC) ? 100 : 112;
+    L.hvst = (lane == IDE) ? 109 : (lane == IAC) ? 110 : 124;
+    if (lane < 21) tile[70 + lane] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NSV; ++b) L.Prow[b] = 0.0;
+    L.pl = 0.0;
+    if (lane < 4) {                      // terminal value: rho |x_N - xF|^2 with multiplier estimate pi_{N-1}
+      L.Prow[lane] = 1.0 / C.O->dc;
+      L.pl = -WV(PI, lane, N - 1);
+    }
+    L.ok = 1;
+  }
+  OBCA_HD static void kl_step1(KktLane& L, int lane, double* slot, double* tile) {
+    {  // rows 0..3 of P_{k+1} / p_{k+1} -> slot k+1 (consumed Q/q space) for the multiplier recovery
+      double* const prs = (lane < 4) ? (slot + RSTRIDE + RPP + lane * NSV) : (tile + 125);
+      double* const pps = (lane < 4) ? (slot + RSTRIDE + Rpp + lane) : (tile + 132);
+#pragma unroll
+      for (int b = 0; b < NSV; ++b) prs[b] = L.Prow[b];
+      *pps = L.pl;
+    }
+    double tp = 0.0, tv = 0.0, tt = L.Prow[6], td = L.Prow[4], ta = L.Prow[5], gl = L.pl;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double pm = L.Prow[m];
+      tp += pm * slot[RDYN + 5 * m + 0]; tv += pm * slot[RDYN + 5 * m + 1]; tt += pm * slot[RDYN + 5 * m + 2];
+      td += pm * slot[RDYN + 5 * m + 3]; ta += pm * slot[RDYN + 5 * m + 4];
+      gl += pm * slot[RR4 + m];
+    }
+    double* const tr = tile + L.tr;
+    tr[IX] = L.Prow[0]; tr[IY] = L.Prow[1]; tr[IP] = tp; tr[IV] = tv; tr[IWD] = 0.0; tr[IWA] = 0.0;
+    tr[IT] = tt; tr[IDE] = td; tr[IAC] = ta;
+    tile[L.gs] = gl;
+  }
+  OBCA_HD static void kl_step2(KktLane& L, int lane, double* slot, double* tile) {
+    const int j = lane < NYV ? lane : NYV - 1;
+    double T[NSV];
+#pragma unroll
+    for (int a = 0; a < NSV; ++a) T[a] = tile[a * NYV + j];
+    double hp = slot[L.qoff[IP]], hvv = slot[L.qoff[IV]], ht = slot[L.qoff[IT]] + T[6], hd = slot[L.qoff[IDE]] + T[4],
+           ha = slot[L.qoff[IAC]] + T[5];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double tm = T[m];
+      hp += slot[RDYN + 5 * m + 0] * tm; hvv += slot[RDYN + 5 * m + 1] * tm; ht += slot[RDYN + 5 * m + 2] * tm;
+      hd += slot[RDYN + 5 * m + 3] * tm; ha += slot[RDYN + 5 * m + 4] * tm;
+    }
+    L.H[IX] = slot[L.qoff[IX]] + T[0]; L.H[IY] = slot[L.qoff[IY]] + T[1]; L.H[IP] = hp; L.H[IV] = hvv;
+    L.H[IWD] = slot[L.qoff[IWD]]; L.H[IWA] = slot[L.qoff[IWA]]; L.H[IT] = ht; L.H[IDE] = hd; L.H[IAC] = ha;
+    const double* const dc_ = (L.dcol >= 0) ? (slot + L.dcol) : (tile + 71);
+    L.hv = slot[Rq + j] + tile[L.gext] + dc_[0] * tile[63] + dc_[5] * tile[64] + dc_[10] * tile[65] + dc_[15] * tile[66];
+    double* const hc = tile + L.hcol;
+#pragma unroll
+    for (int i = 0; i < NYV; ++i) hc[i] = L.H[i];
+    tile[L.hvst] = L.hv;
+  }
+  OBCA_HD static void kl_step3(KktLane& L, int lane, double* slot, double* tile) {
+    const double h77 = tile[91 + IDE], h78 = tile[91 + IAC], h88 = tile[100 + IAC];
+    double det = h77 * h88 - h78 * h78;
+    if (!(h77 > 0.0) || !(det > 0.0)) { L.ok = 0; det = 1e300; }
 #if defined(__CUDA_ARCH__)
-  // -------------------------------------------------------------------------------------------------
-  // Device version of the backward sweep: warp 0 cooperates, nothing is replicated.
-  //   lane l (< 7) owns ROW l of the value function P (7 doubles) and p_l;
-  //   step 1: lane l forms row l of T = P Phi (9 values, Phi sparse) and g_l = p_l + P(l,:) r~ -> shared tile
-  //   step 2: lane j (< 9) reads COLUMN j of T, forms column j of H = Q + Phi' T and hv_j
-  //   step 3: 2x2 pivot on (de, a) via shuffles; lane j (< 7) ends with column j of the new P, which by symmetry
-  //           is the row it must own for the next stage.
-  // Same arithmetic as riccati_step(); the stage slot lives in shared memory.
-  // -------------------------------------------------------------------------------------------------
-  __device__ static int kkt_solve_warp(const PkCtx& C, double* tile /* >= 7*9+7 doubles of shared memory */) {
+    const double idet = fast_rcp(det);
+#else
+    const double idet = 1.0 / det;
+#endif
+    const double n00 = h88 * idet, n01 = -h78 * idet, n11 = h77 * idet;
+    const double K0 = -(n00 * L.H[IDE] + n01 * L.H[IAC]), K1 = -(n01 * L.H[IDE] + n11 * L.H[IAC]);   // column j of the gain
+    const double hv7 = tile[109], hv8 = tile[110];
+    const double kf0 = -(n00 * hv7 + n01 * hv8), kf1 = -(n01 * hv7 + n11 * hv8);
+#pragma unroll
+    for (int i = 0; i < NSV; ++i) L.Prow[i] = L.H[i] + tile[91 + i] * K0 + tile[100 + i] * K1;   // new P(:, j) == row j
+    L.pl = L.hv + L.H[IDE] * kf0 + L.H[IAC] * kf1;
+    double* const ks = (lane < NSV) ? (slot + RK + lane) : (tile + 133);
+    ks[0] = K0; ks[NSV] = K1;
+    if (lane == 0) { slot[RK + 14] = kf0; slot[RK + 15] = kf1; }
+  }
+
+#if defined(__CUDA_ARCH__)
+  __device__ static int kkt_solve_warp(const PkCtx& C, double* tile) {
     const ParkProblem& Pp = *C.P;
     const int N = Pp.N;
     const int lane = threadIdx.x & 31;
-    const int l7 = lane < NSV ? lane : NSV - 1;     // row owned in step 1
-    const int j = lane < NYV ? lane : NYV - 1;      // column owned in step 2
+    KktLane L;
+    kl_init(L, lane, tile, C);
+    __syncwarp();
+    for (int k = N - 1; k >= 0; --k) {
+      double* const slot = C.ric + k * RSTRIDE;
+      kl_step1(L, lane, slot, tile);
+      __syncwarp();
+      kl_step2(L, lane, slot, tile);
+      __syncwarp();
+      kl_step3(L, lane, slot, tile);
+      __syncwarp();
+    }
+    int ok = L.ok;
+    // ---- root (x_0, w_0 fixed; dt free) ----
+    if (lane == IT) { tile[63] = L.Prow[IT]; tile[64] = L.pl; }           // P(t, t), p_t
+    __syncwarp();
+    ProbState& S = *C.S;
+    double dt = 0.0;
+    if (!Pp.fix_time) {
+      double ptt = tile[63];
+      if (!(ptt > 0.0)) { ok = 0; ptt = 1e300; }
+      dt = -tile[64] / ptt;
+    }
+    if (lane == 0) S.dt = dt;
+    // ---- forward roll-out, lane-parallel: lanes 0,1 -> controls, lanes 0..3 -> next state rows ----
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
+    const int ur = lane & 1, xr = lane & 3;
     const unsigned FULL = 0xffffffffu;
-    double Prow[NSV], pl;
-#pragma unroll
-    for (int b = 0; b < NSV; ++b) Prow[b] = 0.0;
-    pl = 0.0;
-    const double rho = 1.0 / C.O->dc;
-    if (l7 < 4) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) Prow[b] = (b == l7) ? rho : 0.0;
-      pl = -WV(PI, l7, N - 1);
+    const double selx = (xr == 0) ? 1.0 : 0.0, sely = (xr == 1) ? 1.0 : 0.0;
+    double* const dxw = C.W + (size_t)(C.L.dX + xr) * C.L.NSP;      // dX, dY, dPS, dVL are consecutive arrays
+    double* const duw = C.W + (size_t)(C.L.dDE + ur) * C.L.NSP;     // dDE, dAC are consecutive arrays
+    for (int k = 0; k < N; ++k) {
+      const double* const slot = C.ric + k * RSTRIDE;
+      const double* const kr = slot + RK + ur * NSV;
+      double u = slot[RK + 14 + ur] + kr[0] * s0 + kr[1] * s1 + kr[2] * s2 + kr[3] * s3 + kr[4] * s4 + kr[5] * s5 + kr[6] * dt;
+      const double u0 = __shfl_sync(FULL, u, 0), u1 = __shfl_sync(FULL, u, 1);
+      const double* const dr = slot + RDYN + 5 * xr;
+      double sn = slot[RR4 + xr] + selx * s0 + sely * s1 + dr[0] * s2 + dr[1] * s3 + dr[2] * dt + dr[3] * u0 + dr[4] * u1;
+      if (lane < 2) duw[k] = u;
+      s0 = __shfl_sync(FULL, sn, 0); s1 = __shfl_sync(FULL, sn, 1); s2 = __shfl_sync(FULL, sn, 2); s3 = __shfl_sync(FULL, sn, 3);
+      s4 = u0; s5 = u1;
+      if (lane < 4) {
+        if (k + 1 < N) dxw[k + 1] = sn;
+        else S.eN[xr] = sn;
+      }
+    }
+    if (lane < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
+    if (lane < 2) duw[N] = 0.0;
+    return ok;
+  }
+#else
+  // host emulation of the warp: the 32 lanes run each step one after the other (a step only reads what earlier
+  // steps wrote, exactly what __syncwarp() guarantees on the device)
+  static int kkt_solve_warp_emul(const PkCtx& C, double* tile) {
+    const int N = C.P->N;
+    KktLane L[32];
+    for (int l = 0; l < 32; ++l) kl_init(L[l], l, tile, C);
+    for (int k = N - 1; k >= 0; --k) {
+      double* const slot = C.ric + k * RSTRIDE;
+      for (int l = 0; l < 32; ++l) kl_step1(L[l], l, slot, tile);
+      for (int l = 0; l < 32; ++l) kl_step2(L[l], l, slot, tile);
+      for (int l = 0; l < 32; ++l) kl_step3(L[l], l, slot, tile);
     }
     int ok = 1;
-    for (int k = N - 1; k >= 0; --k) {
-      double* slot = C.ric + k * RSTRIDE;
-      double* nslot = C.ric + (k + 1) * RSTRIDE;
-      // P_{k+1}, p_{k+1} -> slot k+1 (consumed Q/q space) for the multiplier recovery
-      if (lane < NSV) {
-#pragma unroll
-        for (int b = 0; b < NSV; ++b)
-          if (b >= lane) nslot[RPP + sym_idx<NSV>(lane, b)] = Prow[b];
-        nslot[Rpp + lane] = pl;
-      }
-      // ---- step 1: row l of T = P Phi, g_l ----
-      {
-        double Tr[NYV];
-        double gl = pl;
-        Tr[IX] = Prow[0]; Tr[IY] = Prow[1]; Tr[IWD] = 0.0; Tr[IWA] = 0.0;
-        double tp = 0.0, tv = 0.0, tt = Prow[6], td = Prow[4], ta = Prow[5];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const double pm = Prow[m];
-          tp += pm * slot[RDYN + 5 * m + 0]; tv += pm * slot[RDYN + 5 * m + 1]; tt += pm * slot[RDYN + 5 * m + 2];
-          td += pm * slot[RDYN + 5 * m + 3]; ta += pm * slot[RDYN + 5 * m + 4];
-          gl += pm * slot[RR4 + m];
-        }
-        Tr[IP] = tp; Tr[IV] = tv; Tr[IT] = tt; Tr[IDE] = td; Tr[IAC] = ta;
-        if (lane < NSV) {
-#pragma unroll
-          for (int c = 0; c < NYV; ++c) tile[lane * NYV + c] = Tr[c];
-          tile[NSV * NYV + lane] = gl;
-        }
-      }
-      __syncwarp();
-      // ---- step 2: column j of H = Q + Phi' T, hv_j = q_j + phi_j . g ----
-      double H[NYV], hv;
-      {
-        double T[NSV], g[NSV];
-#pragma unroll
-        for (int a = 0; a < NSV; ++a) { T[a] = tile[a * NYV + j]; g[a] = tile[NSV * NYV + a]; }
-        double fx0[4], fx1[4], ft[4], fu0[4], fu1[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          fx0[i] = slot[RDYN + 5 * i + 0]; fx1[i] = slot[RDYN + 5 * i + 1]; ft[i] = slot[RDYN + 5 * i + 2];
-          fu0[i] = slot[RDYN + 5 * i + 3]; fu1[i] = slot[RDYN + 5 * i + 4];
-        }
-        double Qc[NYV];
-#pragma unroll
-        for (int i = 0; i < NYV; ++i) Qc[i] = slot[RQ + (i <= j ? sym_idx<NYV>(i, j) : sym_idx<NYV>(j, i))];
-        H[IX] = Qc[IX] + T[0];
-        H[IY] = Qc[IY] + T[1];
-        H[IP] = Qc[IP] + fx0[0] * T[0] + fx0[1] * T[1] + fx0[2] * T[2] + fx0[3] * T[3];
-        H[IV] = Qc[IV] + fx1[0] * T[0] + fx1[1] * T[1] + fx1[2] * T[2] + fx1[3] * T[3];
-        H[IWD] = Qc[IWD];
-        H[IWA] = Qc[IWA];
-        H[IT] = Qc[IT] + ft[0] * T[0] + ft[1] * T[1] + ft[2] * T[2] + ft[3] * T[3] + T[6];
-        H[IDE] = Qc[IDE] + fu0[0] * T[0] + fu0[1] * T[1] + fu0[2] * T[2] + fu0[3] * T[3] + T[4];
-        H[IAC] = Qc[IAC] + fu1[0] * T[0] + fu1[1] * T[1] + fu1[2] * T[2] + fu1[3] * T[3] + T[5];
-        // phi_j . g with the sparsity of column j of Phi
-        double pg = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double c = 0.0;
-          c = (j == IP) ? fx0[i] : c; c = (j == IV) ? fx1[i] : c; c = (j == IT) ? ft[i] : c;
-          c = (j == IDE) ? fu0[i] : c; c = (j == IAC) ? fu1[i] : c;
-          c = (j == i && i < 2) ? 1.0 : c;
-          pg += c * g[i];
-        }
-        pg += (j == IDE) ? g[4] : 0.0; pg += (j == IAC) ? g[5] : 0.0; pg += (j == IT) ? g[6] : 0.0;
-        hv = slot[Rq + j] + pg;
-      }
-      __syncwarp();
-      // ---- step 3: eliminate u = (de, a) ----
-      double h77 = __shfl_sync(FULL, H[IDE], IDE), h78 = __shfl_sync(FULL, H[IAC], IDE), h88 = __shfl_sync(FULL, H[IAC], IAC);
-      const double hv7 = __shfl_sync(FULL, hv, IDE), hv8 = __shfl_sync(FULL, hv, IAC);
-      // 2x2 SPD pivot with ONE reciprocal (the divisions are the longest dependent chain of the sweep):
-      // positive definite  <=>  h77 > 0 and det > 0
-      double det = h77 * h88 - h78 * h78;
-      if (!(h77 > 0.0) || !(det > 0.0)) { ok = 0; det = 1e300; }
-      const double idet = fast_rcp(det);
-      const double n00 = h88 * idet, n01 = -h78 * idet, n11 = h77 * idet;
-      const double K0 = -(n00 * H[IDE] + n01 * H[IAC]), K1 = -(n01 * H[IDE] + n11 * H[IAC]);   // column j of the gain
-      const double kf0 = -(n00 * hv7 + n01 * hv8), kf1 = -(n01 * hv7 + n11 * hv8);
-#pragma unroll
-      for (int i = 0; i < NSV; ++i) {
-        const double c7 = __shfl_sync(FULL, H[i], IDE), c8 = __shfl_sync(FULL, H[i], IAC);   // H(i, de), H(i, a)
-        Prow[i] = H[i] + c7 * K0 + c8 * K1;      // column j of the new P == row j (lanes >= 7 hold garbage, unused)
-      }
-      pl = hv + H[IDE] * kf0 + H[IAC] * kf1;
-      // ---- gains into the slot (Q/q of this stage are consumed) ----
-      if (lane < NSV) { slot[RK + lane] = K0; slot[RK + NSV + lane] = K1; }
-      if (lane == 0) { slot[RK + 14] = kf0; slot[RK + 15] = kf1; }
-      __syncwarp();
-    }
-    const double ptt = __shfl_sync(FULL, Prow[IT], IT), pt = __shfl_sync(FULL, pl, IT);
-    int okr = 1;
-    if (lane == 0) okr = kkt_root_forward(C, ptt, pt);
-    okr = __shfl_sync(FULL, okr, 0);
-    return ok & okr;
+    for (int l = 0; l < 32; ++l) ok &= L[l].ok;
+    return ok & kkt_root_forward(C, L[IT].Prow[IT], L[IT].pl);
   }
 #endif
 
@@ -806,7 +863,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // K4a: recover local steps, slack steps; step-length partials; directional derivative of the barrier objective
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void recover_stage(const PkCtx& C, int k, StepPart& out) {
+  OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -829,7 +886,7 @@ struct ParkSolver {
       for (int i = 0; i < 4; ++i) {
         double acc = RIC(Rpp + i, k + 1);
 #pragma unroll
-        for (int l = 0; l < NSV; ++l) acc += RIC(RPP + sym_idx_any<NSV>(i, l), k + 1) * sn[l];
+        for (int l = 0; l < NSV; ++l) acc += RIC(RPP + i * NSV + l, k + 1) * sn[l];
         WV(PIn, i, k) = -acc;
       }
     }
@@ -947,7 +1004,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // K4b: merit-function partials at the trial point z + alpha dz  (theta = ||c||_1, phi = barrier objective)
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void merit_stage(const PkCtx& C, int k, double alpha, MeritPart& out) {
+  OBCA_HD_NI static void merit_stage(const PkCtx& C, int k, double alpha, MeritPart& out) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1042,7 +1099,7 @@ struct ParkSolver {
     q += alpha * dq; zl += adu * dzl; zu += adu * dzu;
     zl = clipz(zl, q - lo, mu_b, ks); zu = clipz(zu, hi - q, mu_b, ks);
   }
-  OBCA_HD static void update_stage(const PkCtx& C, int k) {
+  OBCA_HD_NI static void update_stage(const PkCtx& C, int k) {
     const ParkProblem& P = *C.P;
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1249,7 +1306,7 @@ struct ParkSolver {
           if (threadIdx.x == 0) S.ok = ok;
         }
 #else
-        if (S.ok) S.ok = kkt_solve(C);
+        if (S.ok) S.ok = C.tile ? kkt_solve_warp_emul(C, C.tile) : kkt_solve(C);
 #endif
         OBCA_SYNC();
         OBCA_SERIAL {

@@ -126,3 +126,37 @@ def ParkingConstraints(x0, xF, N, Ts, L, ego, XYbounds, nOb, vOb, A, b, x, u, l,
                                      np.asarray(u, float)[None], np.asarray(l, float)[None],
                                      np.asarray(n, float)[None], np.asarray(timeScale, float).reshape(1, -1), fixTime, sd)
     return int(feas[0])
+
+
+def eval_batch(x0, xF, N, Ts, L, ego_, XYbounds, nOb, vOb, A, b, rx, ry, ryaw, fixTime, signed_dist, xp, up, ts, lp, np_, sl=None,
+               y=None, reps=1, opts=None):
+    """K1 stand-alone (obca_parking_eval_batch_dev): fused evaluation of the reference NLP at B points.
+    xp (B,4,N+1), up (B,2,N), ts (B,N+1), lp (B,V,N+1), np_ (B,4nOb,N+1), sl (B,nOb,N+1) -- Julia shapes, stacked;
+    y (B,m) row multipliers in the K1 row order (include/obca.h) or None.  Device buffers are torch tensors
+    (plumbing only).  Returns c (B,m), gradL (B,n), f (B,), kernel_ms."""
+    import torch
+    xp = np.asarray(xp, float); B = xp.shape[0]; NS = N + 1
+    vOb, V, A, b = _shared(nOb, vOb, A, b)
+    nn = C.c_longlong(); mm = C.c_longlong()
+    check(lib().obca_parking_eval_sizes(C.c_int(N), C.c_int(nOb), ptr(vOb), C.c_int(int(signed_dist)), C.byref(nn), C.byref(mm)))
+    n, m = nn.value, mm.value
+    o = opts if opts is not None else _lib.default_opts()
+    dev = torch.device("cuda", o.device)
+    T = lambda a: np.ascontiguousarray(np.transpose(np.asarray(a, float), (0, 2, 1)))
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    bx0 = d(np.broadcast_to(np.asarray(x0, float).reshape(-1, 4), (B, 4))); bxF = d(np.broadcast_to(np.asarray(xF, float).reshape(-1, 4), (B, 4)))
+    brx, bry, bryaw = d(np.asarray(rx).reshape(B, NS)), d(np.asarray(ry).reshape(B, NS)), d(np.asarray(ryaw).reshape(B, NS))
+    dxp, dup, dlp, dnp = d(T(xp)), d(T(up)), d(T(lp)), d(T(np_))
+    dts = d(np.asarray(ts, float).reshape(B, NS)) if ts is not None else None
+    dsl = d(T(sl)) if sl is not None else None
+    dy = d(np.asarray(y, float).reshape(B, m)) if y is not None else None
+    c = torch.zeros((B, m), dtype=torch.float64, device=dev); g = torch.zeros((B, n), dtype=torch.float64, device=dev)
+    fk = torch.zeros((B, NS), dtype=torch.float64, device=dev)
+    ms = np.zeros(1)
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    check(lib().obca_parking_eval_batch_dev(
+        C.c_int(B), C.c_int(N), C.c_int(nOb), ptr(vOb), ptr(A), ptr(b), P(bx0), P(bxF), C.c_double(Ts), C.c_double(L),
+        ptr(f64(np.asarray(ego_).ravel())), ptr(f64(np.asarray(XYbounds).ravel())), P(brx), P(bry), P(bryaw), P(dxp), P(dup), P(dts),
+        P(dlp), P(dnp), P(dsl), P(dy), C.c_int(int(fixTime)), C.c_int(int(signed_dist)), C.byref(o), P(c), P(g), P(fk),
+        C.c_int(int(reps)), ptr(ms)))
+    return c.cpu().numpy(), g.cpu().numpy(), fk.sum(1).cpu().numpy(), float(ms[0])

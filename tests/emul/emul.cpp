@@ -10,6 +10,7 @@
 
 #include "../../obca_b200/csrc/obca_host.h"
 #include "../../obca_b200/csrc/obca_dualws.cuh"
+#include "../../obca_b200/csrc/obca_eval.cuh"
 
 using namespace obca;
 
@@ -17,8 +18,10 @@ template <int VM, bool SDV>
 static void run_one(const ParkProblem& P, const IpmOpts& O, const PkLay& L, double* W, const PkInputs& in,
                     const PkOutputs& out, ProbState& S) {
   PkCtx C;
-  std::vector<double> ric((size_t)(P.N + 1) * RSTRIDE, 0.0);
-  C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = ric.data(); C.red_scratch = nullptr; C.tile = nullptr; C.S = &S; C.in = in;
+  std::vector<double> ric((size_t)(P.N + 2) * RSTRIDE, 0.0);
+  std::vector<double> tile(256, 0.0);
+  static const bool use_warp = getenv("OBCA_EMUL_SERIAL_KKT") == nullptr;
+  C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = ric.data(); C.red_scratch = nullptr; C.tile = use_warp ? tile.data() : nullptr; C.S = &S; C.in = in;
   ParkSolver<VM, SDV>::solve(C);
   for (int k = 0; k <= P.N; ++k) ParkSolver<VM, SDV>::store_stage(C, k, out);
 }
@@ -116,6 +119,33 @@ int emul_dualmultws_batch(int B, int N, int nOb, const int* vOb, const double* A
         if (dd) dd[(size_t)nOb * NS * i + (size_t)j * NS + k] = d;
         if (its_out) its_out[(size_t)nOb * NS * i + (size_t)j * NS + k] = its;
       }
+  }
+  return 0;
+}
+
+// K1 stand-alone evaluator (obca_eval.cuh) on the host: same arguments as obca_parking_eval_batch_dev
+int emul_parking_eval_batch(int B, int N, int nOb, const int* vOb, const double* A, const double* b, const double* x0,
+                            const double* xF, double Ts, double L, const double* ego, const double* XYbounds,
+                            const double* rx, const double* ry, const double* ryaw, const double* xp, const double* up,
+                            const double* ts, const double* lp, const double* np, const double* sl, const double* y,
+                            int fixTime, int signed_dist, double* c_out, double* gradL_out, double* fk_out) {
+  ParkProblem P;
+  int rc = fill_problem(P, N, nOb, vOb, A, b, Ts, L, ego, XYbounds, fixTime, signed_dist);
+  if (rc) return rc;
+  const size_t NS = N + 1, V = P.V, m = eval_m(P), n = eval_n(P);
+  const int vm = max_vob(P) <= 2 ? 2 : 4;
+  for (int bb = 0; bb < B; ++bb) {
+    EvalIn ib;
+    ib.x0 = x0 + 4 * bb; ib.xF = xF + 4 * bb; ib.rx = rx + NS * bb; ib.ry = ry + NS * bb; ib.ryaw = ryaw + NS * bb;
+    ib.xp = xp + 4 * NS * bb; ib.up = up + (size_t)2 * N * bb; ib.ts = ts ? ts + NS * bb : nullptr;
+    ib.lp = lp + V * NS * bb; ib.np = np + (size_t)4 * nOb * NS * bb; ib.sl = sl ? sl + (size_t)nOb * NS * bb : nullptr;
+    ib.y = y ? y + m * bb : nullptr;
+    EvalOut ob;
+    ob.c = c_out + m * bb; ob.gradL = gradL_out + n * bb; ob.fk = fk_out + NS * bb;
+    for (int k = 0; k <= N; ++k) {
+      if (signed_dist) { if (vm == 2) eval_stage<2, true>(P, k, ib, ob); else eval_stage<4, true>(P, k, ib, ob); }
+      else { if (vm == 2) eval_stage<2, false>(P, k, ib, ob); else eval_stage<4, false>(P, k, ib, ob); }
+    }
   }
   return 0;
 }

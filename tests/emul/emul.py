@@ -106,3 +106,26 @@ def dualmultws_batch(sc):
     assert rc == 0
     # return in (B, NS, V) "row = stage" orientation like DualMultWS.jl:81-84
     return np.transpose(lp, (0, 2, 1)).copy(), np.transpose(npp, (0, 2, 1)).copy(), np.transpose(d, (0, 2, 1)).copy(), its
+
+
+def eval_batch(sc_one, arrays, fixTime, variant):
+    """K1 stand-alone on the host for ONE problem.  sc_one: dict with N, nOb, vOb, A, b, x0 (4,), xF (4,), Ts, L, ego,
+    XYbounds, rx, ry, ryaw (N+1,).  arrays: dict from tests/k1_maps.k1_inputs."""
+    N, nOb = sc_one["N"], sc_one["nOb"]
+    vOb = np.ascontiguousarray(sc_one["vOb"], dtype=np.int32); V = int(vOb.sum())
+    sd = 1 if variant == "sd" else 0
+    NS = N + 1
+    n = 4 * NS + NS + 2 * N + V * NS + 4 * nOb * NS + (nOb * NS if sd else 0)
+    m = 8 + 6 * N + 4 * nOb * NS
+    c = np.zeros(m); gl = np.zeros(n); fk = np.zeros(NS)
+    f = lib().emul_parking_eval_batch
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_double, C.c_double] + [C.c_void_p] * 12 + [C.c_int, C.c_int] + [C.c_void_p] * 3
+    A = np.asfortranarray(sc_one["A"], dtype=float); b = np.ascontiguousarray(sc_one["b"], dtype=float).ravel()
+    g = lambda a: np.ascontiguousarray(a, dtype=float) if a is not None else None
+    keep = [g(sc_one["x0"]), g(sc_one["xF"]), g(sc_one["ego"]), g(sc_one["XYbounds"]), g(sc_one["rx"]), g(sc_one["ry"]), g(sc_one["ryaw"])]
+    rc = f(1, N, nOb, _p(vOb), _p(A), _p(b), _p(keep[0]), _p(keep[1]), float(sc_one["Ts"]), float(sc_one["L"]), _p(keep[2]), _p(keep[3]),
+           _p(keep[4]), _p(keep[5]), _p(keep[6]), _p(arrays["xp"]), _p(arrays["up"]), _p(arrays["ts"]), _p(arrays["lp"]), _p(arrays["np"]),
+           _p(arrays["sl"]), _p(arrays["y"]), int(fixTime), sd, _p(c), _p(gl), _p(fk))
+    assert rc == 0
+    return c, gl, fk

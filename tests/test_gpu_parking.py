@@ -189,3 +189,32 @@ def test_usage_errors_do_not_throw(P, cfg2):
     o = obca_b200.default_opts(device=63)
     with pytest.raises(obca_b200.ObcaError):
         solve(P, cfg2, opts=o)
+
+
+@pytest.mark.parametrize("variant,fix", [("sd", 0), ("d", 0), ("sd", 1), ("d", 1)])
+def test_k1_standalone_matches_oracle(P, variant, fix):
+    """K1 (fused constraint / Lagrangian-gradient evaluation) against the oracle's sympy-derived NLP."""
+    import k1_maps
+    from obca_b200 import scenarios
+    from oracle.parking_nlp import build_parking_nlp
+    sc = scenarios.reverse_parking_scenario()
+    N = 80
+    rng = np.random.default_rng(11)
+    rx, ry, ryaw = rng.normal(size=(3, N + 1))
+    x0 = np.array([-6, 9.5, 0.1, 0.2]); xF = sc["xF"]
+    nlp = build_parking_nlp(x0, xF, N, 0.6, sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"], sc["b"], rx, ry, ryaw, fix, variant)
+    B = 3
+    pts = [k1_maps.random_point(nlp, rng) for _ in range(B)]
+    arrs = [k1_maps.k1_inputs(nlp, *p) for p in pts]
+    rowmap = arrs[0][1]
+    stack = lambda key: np.stack([np.asarray(a[0][key]).T if np.ndim(a[0][key]) == 2 else a[0][key] for a in arrs])
+    sd = variant == "sd"
+    c, gl, f, ms = P.eval_batch(x0, xF, N, 0.6, sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"], sc["b"],
+                                np.tile(rx, (B, 1)), np.tile(ry, (B, 1)), np.tile(ryaw, (B, 1)), fix, 1 if sd else 0,
+                                stack("xp"), stack("up"), stack("ts"), stack("lp"), stack("np"), stack("sl") if sd else None,
+                                stack("y"))
+    for i in range(B):
+        c_ref, gl_ref, f_ref = k1_maps.oracle_reference(nlp, *pts[i], rowmap)
+        assert np.abs(c[i] - c_ref).max() < 1e-11 * (1 + np.abs(c_ref).max())
+        assert np.abs(gl[i] - gl_ref).max() < 1e-10 * (1 + np.abs(gl_ref).max())
+        assert abs(f[i] - f_ref) < 1e-10 * (1 + abs(f_ref))
