@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # CPU arm: one thread per worker process
+    os.environ.setdefault(_v, "1")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -65,10 +68,30 @@ def _cpu_solve_one(args):
     return int(res.status == 1), res.iters, time.time() - t0
 
 
+_WARM = False
+
+
+def _warm_templates():
+    """Build the oracle's sympy expression templates once in the parent (inherited by the forked workers): symbolic
+    differentiation is an artefact of the oracle, not part of the reference's per-call work."""
+    global _WARM
+    if _WARM:
+        return
+    from obca_b200.scenarios import reverse_parking_batch
+    from oracle.dualmultws_ref import dualmultws_ipm
+    from oracle.parking_nlp import build_parking_nlp
+    sc = reverse_parking_batch(1, N_HORIZON, 0)
+    build_parking_nlp(sc["x0"][0], sc["xF"], N_HORIZON, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"],
+                      sc["A"], sc["b"], sc["rx"][0], sc["ry"][0], sc["ryaw"][0], 0, "sd")
+    dualmultws_ipm(2, sc["nOb"], sc["vOb"], sc["A"], sc["b"], sc["rx"][0][:3], sc["ry"][0][:3], sc["ryaw"][0][:3], sc["ego"])
+    _WARM = True
+
+
 def cpu_arm(n_problems, cores):
     """Oracle port (IPOPT stand-in: same NLP, same warm starts, tol 1e-5, max_iter 200; includes DualMultWS and the
     model build, like one call of ParkingSignedDist) on `cores` worker processes."""
     import multiprocessing as mp
+    _warm_templates()
     ctx = mp.get_context("fork")
     t0 = time.time()
     with ctx.Pool(cores) as pool:
@@ -76,6 +99,17 @@ def cpu_arm(n_problems, cores):
     wall = time.time() - t0
     conv = sum(r[0] for r in res)
     return conv / wall, wall, conv, float(np.mean([r[1] for r in res])), float(np.mean([r[2] for r in res]))
+
+
+def cpu_arm_best(cores):
+    """The host may expose more logical CPUs than it can run the sparse solves on at full speed (SMT, memory
+    bandwidth): try cores, cores/2 and cores/4 workers and keep the best throughput."""
+    best = None
+    for w in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+        r = cpu_arm(w, w)
+        if best is None or r[0] > best[1][0]:
+            best = (w, r)
+    return best
 
 
 def host_cores():
@@ -89,10 +123,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = host_cores()
+    cores, _ = cpu_arm_best(host_cores())      # doubles as the warm-up (template build, page-in)
     per_step = cores
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_arm(cores, cores)
     t0 = time.time(); conv = 0; its = []
     for _ in range(args.steps):
         v, wall, c, it, _ = cpu_arm(per_step, cores)
@@ -291,8 +323,7 @@ def gpu_arm(args):
         line["phase_share"] = {n: round(prof[i] / tot, 4) for i, n in enumerate(names)}
         line["phase_counts"] = {"merit_evals": int(prof[6]), "k1_evals": int(prof[7])}
     if world == 1 and not args.no_cpu:
-        cores = host_cores()
-        v, wall, c, it, per = cpu_arm(cores, cores)
+        cores, (v, wall, c, it, per) = cpu_arm_best(host_cores())
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": "port",
                                 "sample": f"{cores} problems of the same batch (seed 0), {wall:.1f} s wall, mean {per:.1f} s/solve, "
                                           f"mean {it:.0f} iterations; oracle/ipm_ref.py sparse path = IPOPT stand-in, not IPOPT"}

@@ -76,6 +76,12 @@ OBCA_HD IpmOpts default_opts() {
   return o;
 }
 
+// Reciprocal used on the Newton-step path: computed once per gap / pivot and reused for every quotient with that
+// denominator.  (A single-precision-seeded Newton reciprocal was measured on B200 and was SLOWER than the IEEE
+// division here: the solver kernel is instruction-fetch / issue bound and the inline range checks cost more than
+// nvcc's own division fast path.)
+OBCA_HD double rcp(double x) { return 1.0 / x; }
+
 OBCA_HD double dmax(double a, double b) { return a > b ? a : b; }
 OBCA_HD double dmin_(double a, double b) { return a < b ? a : b; }
 OBCA_HD double dabs(double a) { return a < 0 ? -a : a; }

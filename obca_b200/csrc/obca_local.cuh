@@ -141,12 +141,13 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
 
   const double yId = -Q.vd;
   const double g1 = P.g[0], g2 = P.g[1], g3 = P.g[2], g4 = P.g[3];
-  const double s3 = Q.zmu[2] / Q.mu[2] + dw, s4 = Q.zmu[3] / Q.mu[3] + dw;
-  const double gapd = Q.sd - P.dmin;
-  const double Sd = Q.vd / gapd;
-  const double yd0 = -mu_b / gapd + Sd * (G.cd - g3 * G.cr1 - g4 * G.cr2);
-  const double c3 = s3 * G.cr1 - mu_b / Q.mu[2];
-  const double c4 = s4 * G.cr2 - mu_b / Q.mu[3];
+  const double im3 = rcp(Q.mu[2]), im4 = rcp(Q.mu[3]);
+  const double s3 = Q.zmu[2] * im3 + dw, s4 = Q.zmu[3] * im4 + dw;
+  const double igd = rcp(Q.sd - P.dmin);
+  const double Sd = Q.vd * igd;
+  const double yd0 = -mu_b * igd + Sd * (G.cd - g3 * G.cr1 - g4 * G.cr2);
+  const double c3 = s3 * G.cr1 - mu_b * im3;
+  const double c4 = s4 * G.cr2 - mu_b * im4;
 
   // vectors over the ND unknowns: t3, t4 (rot rows after eliminating mu3, mu4) and Gt (dist row)
   double t3[ND], t4[ND], Gt[ND];
@@ -181,9 +182,9 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
   const double ynorm = SDV ? Q.yn : Q.vn;   // multiplier of the norm row (row multiplier yI = vU for the Dist variant)
   double Sn = 0.0, yn0 = 0.0;
   if (!SDV) {
-    const double gapn = 1.0 - Q.sn;
-    Sn = Q.vn / gapn;
-    yn0 = mu_b / gapn + Sn * G.cn;
+    const double ign = rcp(1.0 - Q.sn);
+    Sn = Q.vn * ign;
+    yn0 = mu_b * ign + Sn * G.cn;
   }
 #pragma unroll
   for (int i = 0; i < VM; ++i) {
@@ -197,11 +198,12 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
           M[sym_idx_any<ND>(li, D::il(l))] += w;
         }
       }
-      M[sym_idx<ND>(li, li)] += Q.zlam[i] / Q.lam[i] + dw;
+      const double il_ = rcp(Q.lam[i]);
+      M[sym_idx<ND>(li, li)] += Q.zlam[i] * il_ + dw;
       M[sym_idx_any<ND>(li, D::I_X)] += yId * R.a1[i];
       M[sym_idx_any<ND>(li, D::I_Y)] += yId * R.a2[i];
       M[sym_idx_any<ND>(li, D::I_P)] += Q.yr1 * G.ah2[i] - Q.yr2 * G.ah1[i] + yId * P.off * G.ah2[i];
-      r[li] += -mu_b / Q.lam[i] + (SDV ? 0.0 : G.gn[i] * yn0);
+      r[li] += -mu_b * il_ + (SDV ? 0.0 : G.gn[i] * yn0);
       if (SDV) M[sym_idx_any<ND>(li, 1)] = G.gn[i];
     } else {
       // padded half-space: decoupled unit pivot
@@ -212,10 +214,11 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
     }
   }
   M[sym_idx<ND>(D::I_P, D::I_P)] += -Q.yr1 * G.e1 - Q.yr2 * G.e2 - yId * P.off * G.e1;
-  M[sym_idx<ND>(D::I_MU1, D::I_MU1)] += Q.zmu[0] / Q.mu[0] + dw;
-  M[sym_idx<ND>(D::I_MU2, D::I_MU2)] += Q.zmu[1] / Q.mu[1] + dw;
-  r[D::I_MU1] += -mu_b / Q.mu[0];
-  r[D::I_MU2] += -mu_b / Q.mu[1];
+  const double im1 = rcp(Q.mu[0]), im2 = rcp(Q.mu[1]);
+  M[sym_idx<ND>(D::I_MU1, D::I_MU1)] += Q.zmu[0] * im1 + dw;
+  M[sym_idx<ND>(D::I_MU2, D::I_MU2)] += Q.zmu[1] * im2 + dw;
+  r[D::I_MU1] += -mu_b * im1;
+  r[D::I_MU2] += -mu_b * im2;
   if (SDV) {
     M[sym_idx<ND>(D::I_SL, D::I_SL)] += 2.0e4 + dw;
     r[D::I_SL] += 1.0e2 + 2.0e4 * Q.sl;
@@ -231,7 +234,7 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
     const double m00 = M[sym_idx<ND>(0, 0)], m01 = M[sym_idx<ND>(0, 1)], m11 = M[sym_idx<ND>(1, 1)];
     double det = m00 * m11 - m01 * m01;
     if (!(det < 0.0)) { ok = 0; det = -1e-300; }
-    const double id = 1.0 / det;
+    const double id = rcp(det);
     const double i00 = m11 * id, i01 = -m01 * id, i11 = m00 * id;
     double u0[ND], u1[ND];
 #pragma unroll
@@ -255,7 +258,7 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
   for (int i = first; i < D::NLT; ++i) {
     double piv = M[sym_idx<ND>(i, i)];
     if (!(piv > 0.0)) { ok = 0; piv = 1e300; }
-    const double ip = 1.0 / piv;
+    const double ip = rcp(piv);
     M[sym_idx<ND>(i, i)] = ip;   // store inverse pivot
 #pragma unroll
     for (int rr = i + 1; rr < ND; ++rr) {
@@ -339,14 +342,15 @@ OBCA_HD void obs_recover(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
   S.dmu[2] = t3d + G.cr1;
   S.dmu[3] = t4d + G.cr2;
   S.dsl = SDV ? x[D::I_SL] : 0.0;
-  const double gapd = Q.sd - P.dmin;
-  const double Sd = Q.vd / gapd;
+  const double igd = rcp(Q.sd - P.dmin);
+  const double Sd = Q.vd * igd;
   const double ds = Gd + G.cd - g3 * G.cr1 - g4 * G.cr2;    // = grad(dist).d + (g - s)
-  const double yd_new = -mu_b / gapd + Sd * ds;              // new row multiplier of the dist row (= -vd_new)
+  const double yd_new = -mu_b * igd + Sd * ds;               // new row multiplier of the dist row (= -vd_new)
   S.dsd = ds;
-  const double s3 = Q.zmu[2] / Q.mu[2] + dw, s4 = Q.zmu[3] / Q.mu[3] + dw;
-  S.yr1_new = s3 * S.dmu[2] - g3 * yd_new - mu_b / Q.mu[2];
-  S.yr2_new = s4 * S.dmu[3] - g4 * yd_new - mu_b / Q.mu[3];
+  const double im3 = rcp(Q.mu[2]), im4 = rcp(Q.mu[3]);
+  const double s3 = Q.zmu[2] * im3 + dw, s4 = Q.zmu[3] * im4 + dw;
+  S.yr1_new = s3 * S.dmu[2] - g3 * yd_new - mu_b * im3;
+  S.yr2_new = s4 * S.dmu[3] - g4 * yd_new - mu_b * im4;
   S.yn_new = SDV ? x[1] : 0.0;
   S.dsn = SDV ? 0.0 : (gnd + G.cn);
 }

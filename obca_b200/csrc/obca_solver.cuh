@@ -209,19 +209,6 @@ OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
   return x;
 }
 
-#if defined(__CUDA_ARCH__)
-// reciprocal for the latency-critical Riccati pivot: single-precision seed + 2 Newton steps in FP64 (relative error
-// ~1e-16, not correctly rounded); falls back to the IEEE division outside the float range.
-__device__ __forceinline__ double fast_rcp(double x) {
-  const double ax = fabs(x);
-  if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
-  double r = (double)__frcp_rn((float)x);
-  r = r * (2.0 - x * r);
-  r = r * (2.0 - x * r);
-  r = r * (2.0 - x * r);
-  return r;
-}
-#endif
 
 template <int VM, bool SDV>
 struct ParkSolver {
@@ -370,14 +357,14 @@ struct ParkSolver {
         const double aXl = X - P.xyb[0], aXu = P.xyb[1] - X, aYl = Y - P.xyb[2], aYu = P.xyb[3] - Y;
         const double aVl = v + 1.0, aVu = 2.0 - v;
         const double zXl = WA(ZXL, k), zXu = WA(ZXU, k), zYl = WA(ZYL, k), zYu = WA(ZYU, k), zVl = WA(ZVL, k), zVu = WA(ZVU, k);
-        RIC(RQ + sym_idx<NYV>(IX, IX), k) += 2e-3 + zXl / aXl + zXu / aXu + dw;
-        RIC(RQ + sym_idx<NYV>(IY, IY), k) += 2e-3 + zYl / aYl + zYu / aYu + dw;
+        RIC(RQ + sym_idx<NYV>(IX, IX), k) += 2e-3 + zXl * rcp(aXl) + zXu * rcp(aXu) + dw;
+        RIC(RQ + sym_idx<NYV>(IY, IY), k) += 2e-3 + zYl * rcp(aYl) + zYu * rcp(aYu) + dw;
         RIC(RQ + sym_idx<NYV>(IP, IP), k) += 2.0 * P.w_yaw + dw;
-        RIC(RQ + sym_idx<NYV>(IV, IV), k) += 2e-4 + zVl / aVl + zVu / aVu + dw;
-        RIC(Rq + IX, k) += gX - mu_b / aXl + mu_b / aXu;
-        RIC(Rq + IY, k) += gY - mu_b / aYl + mu_b / aYu;
+        RIC(RQ + sym_idx<NYV>(IV, IV), k) += 2e-4 + zVl * rcp(aVl) + zVu * rcp(aVu) + dw;
+        RIC(Rq + IX, k) += gX - mu_b * rcp(aXl) + mu_b * rcp(aXu);
+        RIC(Rq + IY, k) += gY - mu_b * rcp(aYl) + mu_b * rcp(aYu);
         RIC(Rq + IP, k) += gP;
-        RIC(Rq + IV, k) += gV - mu_b / aVl + mu_b / aVu;
+        RIC(Rq + IV, k) += gV - mu_b * rcp(aVl) + mu_b * rcp(aVu);
         rzX += gX - zXl + zXu; rzY += gY - zYl + zYu; rzP += gP; rzV += gV - zVl + zVu;
         // multiplier of the dynamics row that produced x_k
         rzX += WV(PI, 0, k - 1); rzY += WV(PI, 1, k - 1); rzP += WV(PI, 2, k - 1); rzV += WV(PI, 3, k - 1);
@@ -396,7 +383,7 @@ struct ParkSolver {
     if (has_u) {
       const double de = WA(DE, k), ac = WA(AC, k);
       const double wd = k > 0 ? WA(DE, k - 1) : 0.0, wa = k > 0 ? WA(AC, k - 1) : 0.0;
-      const double h = t * P.Ts, ih = 1.0 / h, ih2 = ih * ih, it = 1.0 / t;
+      const double h = t * P.Ts, ih = rcp(h), ih2 = ih * ih, it = rcp(t);
       const double ed = de - wd, ea = ac - wa;
       const double T = 0.1 * (ed * ed + ea * ea) * ih2;
       fobj += 0.01 * de * de + P.w_a * ac * ac + T;
@@ -405,8 +392,8 @@ struct ParkSolver {
       const double gT = fix ? 0.0 : -2.0 * T * it;
       const double aDl = de + 0.6, aDu = 0.6 - de, aAl = ac + 0.4, aAu = 0.4 - ac;
       const double zDl = WA(ZDL, k), zDu = WA(ZDU, k), zAl = WA(ZAL, k), zAu = WA(ZAU, k);
-      RIC(RQ + sym_idx<NYV>(IDE, IDE), k) += 0.02 + 0.2 * ih2 + zDl / aDl + zDu / aDu + dw;
-      RIC(RQ + sym_idx<NYV>(IAC, IAC), k) += 2.0 * P.w_a + 0.2 * ih2 + zAl / aAl + zAu / aAu + dw;
+      RIC(RQ + sym_idx<NYV>(IDE, IDE), k) += 0.02 + 0.2 * ih2 + zDl * rcp(aDl) + zDu * rcp(aDu) + dw;
+      RIC(RQ + sym_idx<NYV>(IAC, IAC), k) += 2.0 * P.w_a + 0.2 * ih2 + zAl * rcp(aAl) + zAu * rcp(aAu) + dw;
       RIC(RQ + sym_idx<NYV>(IWD, IWD), k) += 0.2 * ih2;
       RIC(RQ + sym_idx<NYV>(IWA, IWA), k) += 0.2 * ih2;
       RIC(RQ + sym_idx<NYV>(IWD, IDE), k) += -0.2 * ih2;
@@ -423,9 +410,9 @@ struct ParkSolver {
       const double rs = WA(RS, k), rvl = WA(RVL, k), rvu = WA(RVU, k);
       const double yIr = rvu - rvl;
       const double gl = rs + 0.6, gu = 0.6 - rs;
-      const double Sr = rvl / gl + rvu / gu;
+      const double Sr = rvl * rcp(gl) + rvu * rcp(gu);
       const double cIr = gr - rs;
-      const double yr0 = -mu_b / gl + mu_b / gu + Sr * cIr;
+      const double yr0 = -mu_b * rcp(gl) + mu_b * rcp(gu) + Sr * cIr;
       const double jw = ih, jd = -ih, jt = fix ? 0.0 : -gr * it;
       RIC(RQ + sym_idx<NYV>(IWD, IWD), k) += Sr * jw * jw;
       RIC(RQ + sym_idx<NYV>(IWD, IDE), k) += Sr * jw * jd;
@@ -437,8 +424,8 @@ struct ParkSolver {
       }
       RIC(Rq + IWD, k) += gWd + jw * yr0;
       RIC(Rq + IWA, k) += gWa;
-      RIC(Rq + IDE, k) += gD + jd * yr0 - mu_b / aDl + mu_b / aDu;
-      RIC(Rq + IAC, k) += gA - mu_b / aAl + mu_b / aAu;
+      RIC(Rq + IDE, k) += gD + jd * yr0 - mu_b * rcp(aDl) + mu_b * rcp(aDu);
+      RIC(Rq + IAC, k) += gA - mu_b * rcp(aAl) + mu_b * rcp(aAu);
       RIC(Rq + IT, k) += gT + jt * yr0;
       // dynamics
       double pi[4], H5[15];
@@ -555,8 +542,8 @@ struct ParkSolver {
       const double m = (double)(N + 1);
       const double gl = t - 0.8, gu = 1.2 - t;
       fobj += m * (0.5 * t + t * t);
-      RIC(RQ + sym_idx<NYV>(IT, IT), k) += 2.0 * m + m * (S.zTL / gl + S.zTU / gu) + dw;
-      RIC(Rq + IT, k) += m * (0.5 + 2.0 * t) + m * (-mu_b / gl + mu_b / gu);
+      RIC(RQ + sym_idx<NYV>(IT, IT), k) += 2.0 * m + m * (S.zTL * rcp(gl) + S.zTU * rcp(gu)) + dw;
+      RIC(Rq + IT, k) += m * (0.5 + 2.0 * t) + m * (-mu_b * rcp(gl) + mu_b * rcp(gu));
       if (do_err) {
         rz_t += m * (0.5 + 2.0 * t) - m * (S.zTL - S.zTU);
         cmax = dmax(cmax, dmax(gl * S.zTL, gu * S.zTU));
@@ -762,11 +749,7 @@ struct ParkSolver {
     const double h77 = tile[91 + IDE], h78 = tile[91 + IAC], h88 = tile[100 + IAC];
     double det = h77 * h88 - h78 * h78;
     if (!(h77 > 0.0) || !(det > 0.0)) { L.ok = 0; det = 1e300; }
-#if defined(__CUDA_ARCH__)
-    const double idet = fast_rcp(det);
-#else
-    const double idet = 1.0 / det;
-#endif
+    const double idet = rcp(det);
     const double n00 = h88 * idet, n01 = -h78 * idet, n11 = h77 * idet;
     const double K0 = -(n00 * L.H[IDE] + n01 * L.H[IAC]), K1 = -(n01 * L.H[IDE] + n11 * L.H[IAC]);   // column j of the gain
     const double hv7 = tile[109], hv8 = tile[110];
@@ -795,8 +778,10 @@ struct ParkSolver {
       __syncwarp();
       kl_step3(L, lane, slot, tile);
       __syncwarp();
+      if (!L.ok) break;      // wrong inertia: the sweep result is discarded anyway (all lanes see the same pivot)
     }
     int ok = L.ok;
+    if (!ok) return 0;
     // ---- root (x_0, w_0 fixed; dt free) ----
     if (lane == IT) { tile[63] = L.Prow[IT]; tile[64] = L.pl; }           // P(t, t), p_t
     __syncwarp();
@@ -846,6 +831,7 @@ struct ParkSolver {
       for (int l = 0; l < 32; ++l) kl_step1(L[l], l, slot, tile);
       for (int l = 0; l < 32; ++l) kl_step2(L[l], l, slot, tile);
       for (int l = 0; l < 32; ++l) kl_step3(L[l], l, slot, tile);
+      if (!L[0].ok) return 0;
     }
     int ok = 1;
     for (int l = 0; l < 32; ++l) ok &= L[l].ok;
@@ -855,10 +841,10 @@ struct ParkSolver {
 
   // fraction-to-the-boundary helpers
   OBCA_HD static void ftb(double gap, double dgap, double tau, double& amax) {
-    if (dgap < 0.0) amax = dmin_(amax, -tau * gap / dgap);
+    if (dgap < 0.0) amax = dmin_(amax, -tau * gap * rcp(dgap));
   }
   // dual step of a bound multiplier z with primal gap `gap` whose gap moves by dgap
-  OBCA_HD static double dzb(double z, double gap, double dgap, double mu_b) { return mu_b / gap - z - z / gap * dgap; }
+  OBCA_HD static double dzb(double z, double gap, double dgap, double mu_b) { return (mu_b - z * dgap) * rcp(gap) - z; }
 
   // ---------------------------------------------------------------------------------------------------
   // K4a: recover local steps, slack steps; step-length partials; directional derivative of the barrier objective
@@ -902,14 +888,14 @@ struct ParkSolver {
       z = WA(ZYU, k); ftb(z, dzb(z, aYu, -dY, mu_b), tau, adu);
       z = WA(ZVL, k); ftb(z, dzb(z, aVl, dV, mu_b), tau, adu);
       z = WA(ZVU, k); ftb(z, dzb(z, aVu, -dV, mu_b), tau, adu);
-      dphi += (2e-3 * ex - mu_b / aXl + mu_b / aXu) * dX + (2e-3 * ey - mu_b / aYl + mu_b / aYu) * dY +
-              2.0 * P.w_yaw * ep * dP + (2e-4 * v - mu_b / aVl + mu_b / aVu) * dV;
+      dphi += (2e-3 * ex - mu_b * rcp(aXl) + mu_b * rcp(aXu)) * dX + (2e-3 * ey - mu_b * rcp(aYl) + mu_b * rcp(aYu)) * dY +
+              2.0 * P.w_yaw * ep * dP + (2e-4 * v - mu_b * rcp(aVl) + mu_b * rcp(aVu)) * dV;
     }
     if (k < N) {
       const double de = WA(DE, k), ac = WA(AC, k), dD = WA(dDE, k), dA = WA(dAC, k);
       const double wd = k > 0 ? WA(DE, k - 1) : 0.0, wa = k > 0 ? WA(AC, k - 1) : 0.0;
       const double dwd = k > 0 ? WA(dDE, k - 1) : 0.0, dwa = k > 0 ? WA(dAC, k - 1) : 0.0;
-      const double h = t * P.Ts, ih = 1.0 / h, ih2 = ih * ih, it = 1.0 / t;
+      const double h = t * P.Ts, ih = rcp(h), ih2 = ih * ih, it = rcp(t);
       const double ed = de - wd, ea = ac - wa;
       const double T = 0.1 * (ed * ed + ea * ea) * ih2;
       const double aDl = de + 0.6, aDu = 0.6 - de, aAl = ac + 0.4, aAu = 0.4 - ac;
@@ -928,9 +914,9 @@ struct ParkSolver {
       ftb(gl, drs, tau, apr); ftb(gu, -drs, tau, apr);
       z = WA(RVL, k); ftb(z, dzb(z, gl, drs, mu_b), tau, adu);
       z = WA(RVU, k); ftb(z, dzb(z, gu, -drs, mu_b), tau, adu);
-      dphi += (0.02 * de + 0.2 * ed * ih2 - mu_b / aDl + mu_b / aDu) * dD + (2.0 * P.w_a * ac + 0.2 * ea * ih2 - mu_b / aAl + mu_b / aAu) * dA +
+      dphi += (0.02 * de + 0.2 * ed * ih2 - mu_b * rcp(aDl) + mu_b * rcp(aDu)) * dD + (2.0 * P.w_a * ac + 0.2 * ea * ih2 - mu_b * rcp(aAl) + mu_b * rcp(aAu)) * dA +
               (-0.2 * ed * ih2) * dwd + (-0.2 * ea * ih2) * dwa + (fix ? 0.0 : -2.0 * T * it * S.dt) +
-              (-mu_b / gl + mu_b / gu) * drs;
+              (-mu_b * rcp(gl) + mu_b * rcp(gu)) * drs;
     }
     for (int j = 0; j < P.nOb; ++j) {
       ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
@@ -960,7 +946,7 @@ struct ParkSolver {
           WV(dLAM, P.voff[j] + i, k) = St.dlam[i];
           ftb(Qv.lam[i], St.dlam[i], tau, apr);
           ftb(Qv.zlam[i], dzb(Qv.zlam[i], Qv.lam[i], St.dlam[i], mu_b), tau, adu);
-          dphi += -mu_b / Qv.lam[i] * St.dlam[i];
+          dphi += -mu_b * rcp(Qv.lam[i]) * St.dlam[i];
         }
       }
 #pragma unroll
@@ -968,7 +954,7 @@ struct ParkSolver {
         WV(dMU, 4 * j + m, k) = St.dmu[m];
         ftb(Qv.mu[m], St.dmu[m], tau, apr);
         ftb(Qv.zmu[m], dzb(Qv.zmu[m], Qv.mu[m], St.dmu[m], mu_b), tau, adu);
-        dphi += -mu_b / Qv.mu[m] * St.dmu[m];
+        dphi += -mu_b * rcp(Qv.mu[m]) * St.dmu[m];
       }
       if (SDV) {
         WV(dSL, j, k) = St.dsl; WV(YNn, j, k) = St.yn_new;
@@ -980,14 +966,14 @@ struct ParkSolver {
         const double gap = Qv.sd - P.dmin;
         ftb(gap, St.dsd, tau, apr);
         ftb(Qv.vd, dzb(Qv.vd, gap, St.dsd, mu_b), tau, adu);
-        dphi += -mu_b / gap * St.dsd;
+        dphi += -mu_b * rcp(gap) * St.dsd;
       }
       if (!SDV) {
         WV(dSN, j, k) = St.dsn;
         const double gap = 1.0 - Qv.sn;
         ftb(gap, -St.dsn, tau, apr);
         ftb(Qv.vn, dzb(Qv.vn, gap, -St.dsn, mu_b), tau, adu);
-        dphi += mu_b / gap * St.dsn;
+        dphi += mu_b * rcp(gap) * St.dsn;
       }
     }
     if (k == 0 && !fix) {
@@ -996,7 +982,7 @@ struct ParkSolver {
       ftb(gl, S.dt, tau, apr); ftb(gu, -S.dt, tau, apr);
       ftb(S.zTL, dzb(S.zTL, gl, S.dt, mu_b), tau, adu);
       ftb(S.zTU, dzb(S.zTU, gu, -S.dt, mu_b), tau, adu);
-      dphi += m * (0.5 + 2.0 * t - mu_b / gl + mu_b / gu) * S.dt;
+      dphi += m * (0.5 + 2.0 * t - mu_b * rcp(gl) + mu_b * rcp(gu)) * S.dt;
     }
     out.apr = apr; out.adu = adu; out.dphi = dphi;
   }
@@ -1090,7 +1076,8 @@ struct ParkSolver {
   // K4c: accept the step (primal alpha, dual a_du, equality multipliers a_y) + Ipopt's multiplier safeguard
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD static double clipz(double z, double gap, double mu_b, double ks) {
-    return dmax(dmin_(z, ks * mu_b / gap), mu_b / (ks * gap));
+    const double mg = mu_b * rcp(gap);
+    return dmax(dmin_(z, ks * mg), mg * rcp(ks));
   }
   OBCA_HD static void upd_pair(double& q, double dq, double& zl, double& zu, double lo, double hi, double alpha,
                                double adu, double mu_b, double ks) {

@@ -78,3 +78,29 @@ def test_config2_solutions_are_kkt_points_of_reference_nlp(cfg2):
                                            cfg2["vOb"], cfg2["A"], cfg2["b"], rr["xp"][i], rr["up"][i], rr["lp"][i], rr["np"][i],
                                            rr["ts"][i], 0, 1, rr["sl"][i])
         assert ok2 == 1, worst
+
+
+def test_warp_kkt_lane_code_matches_serial_riccati(tmp_path):
+    """K3: the lane functions of the warp-cooperative sweep (kl_step1/2/3, run for 32 emulated lanes) and the plain
+    serial Riccati recursion (riccati_step) give the same Newton steps."""
+    import os, subprocess, sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {repr(os.path.join(os.path.dirname(__file__), 'emul'))}); sys.path.insert(0, {repr(os.path.dirname(os.path.dirname(__file__)))})\n"
+        "import emul\nfrom obca_b200 import scenarios\n"
+        "sc = scenarios.reverse_parking_batch(4, 80, 0)\n"
+        "lp, npp, _, _ = emul.dualmultws_batch(sc)\n"
+        "o = emul.default_opts(); o.max_iter = 3\n"
+        "r = emul.solve_batch(sc, 0, 'sd', o, lp, npp)\n"
+        "np.savez(sys.argv[1], xp=r['xp'], up=r['up'], lp=r['lp'], np=r['np'], ts=r['ts'])\n")
+    outs = []
+    for mode in ("warp", "serial"):
+        env = dict(os.environ)
+        if mode == "serial":
+            env["OBCA_EMUL_SERIAL_KKT"] = "1"
+        f = str(tmp_path / f"{mode}.npz")
+        subprocess.check_call([sys.executable, str(script), f], env=env)
+        outs.append(np.load(f))
+    for key in ("xp", "up", "lp", "np", "ts"):
+        assert np.abs(outs[0][key] - outs[1][key]).max() < 1e-7, key   # round-off x 1/dc (terminal penalty 1e9)
