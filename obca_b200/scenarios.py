@@ -169,3 +169,81 @@ def reverse_parking_batch(B, N=80, seed=0):
         rx[i], ry[i], ryaw[i], xWS[i], uWS[i] = warmstart_reverse(x0[i], sc["xF"], N, sc["Ts"], sc["L"])
     sc.update(B=B, N=N, x0=x0, rx=rx, ry=ry, ryaw=ryaw, xWS=xWS, uWS=uWS)
     return sc
+
+
+# ----------------------------------------------------------------------------------------------
+# quadcopter (QuadcopterNavigation/mainQuadcopter.jl)
+# ----------------------------------------------------------------------------------------------
+def quadcopter_scenario():
+    """mainQuadcopter.jl:36-55: ball ego R = 0.25, five boxes b = [x_up, y_up, z_up, -x_lo, -y_lo, -z_lo]
+    (A = [I; -I], QuadcopterSignedDist.jl:162-163): a wall with a gap below z = 0.6 and a wall with a window."""
+    obs = np.array([[2.5, 12, 7, -2, 2, -0.6],      # ob12
+                    [7.5, 12, 7, -7, -5, 2],        # ob22
+                    [7.5, 4, 7, -7, 2, 2],          # ob32
+                    [7.5, 5, 2, -7, -4, 2],         # ob42
+                    [7.5, 5, 7, -7, -4, -3]])       # ob52
+    return dict(R=0.25, obs=obs, Ts80=0.25, x0=np.array([1, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]),
+                xF=np.array([9, 3, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]))
+
+
+def warmstart_quadcopter(x0, xF, N):
+    """Position warm start standing in for the 3-D A* of mainQuadcopter.jl:122-135 (out of scope): a polyline
+    start -> under wall 1 -> through the window of wall 2 -> goal, sampled at N+1 equal arc-length points; all other
+    states 0 like xWS_as (:134)."""
+    p0 = np.asarray(x0[:3], float); p5 = np.asarray(xF[:3], float)
+    way = np.array([p0, [1.6, p0[1], 0.17], [2.9, p0[1], 0.17], [6.6, 4.5, 2.5], [7.9, 4.5, 2.5], p5])
+    seg = np.linalg.norm(np.diff(way, axis=0), axis=1)
+    s = np.concatenate([[0], np.cumsum(seg)])
+    q = np.linspace(0, s[-1], N + 1)
+    xWS = np.zeros((12, N + 1))
+    for d in range(3):
+        xWS[d] = np.interp(q, s, way[:, d])
+    return xWS
+
+
+def quadcopter_batch(B, N=100, seed=2):
+    """BASELINE config 4: x0 = [1, Y, Z, 0..], xF = [9, Y', Z', 0..], Y ~ U(0.5, 9.5), Z ~ U(0.5, 4.5)
+    (mainQuadcopter.jl:48-51), Ts * N = 20 (:131)."""
+    sc = quadcopter_scenario()
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, 12)); xF = np.zeros((B, 12))
+    x0[:, 0] = 1; xF[:, 0] = 9
+    x0[:, 1] = rng.uniform(0.5, 9.5, B); x0[:, 2] = rng.uniform(0.5, 4.5, B)
+    xF[:, 1] = rng.uniform(0.5, 9.5, B); xF[:, 2] = rng.uniform(0.5, 4.5, B)
+    Ts = round((sc["Ts80"] * 80 / N) * 100) / 100
+    xWS = np.stack([warmstart_quadcopter(x0[i], xF[i], N) for i in range(B)])
+    sc.update(B=B, N=N, Ts=Ts, x0=x0, xF=xF, xWS=xWS, timeWS=1.0)
+    return sc
+
+
+# ----------------------------------------------------------------------------------------------
+# parallel parking (BASELINE config 3)
+# ----------------------------------------------------------------------------------------------
+def warmstart_parallel(x0, xF, N, Ts, L, R=4.5):
+    """Warm start for the parallel-parking slot of main.jl:154-162 (goal heading 0, slot between x=-3 and x=3 below
+    y=5): straight along the lane to the start of a reverse S-curve (right-steer arc, then left-steer arc), standing in
+    for Hybrid A* (out of scope)."""
+    X0, Y0 = float(x0[0]), float(x0[1])
+    dy = Y0 - float(xF[1])
+    th = math.acos(max(-1.0, min(1.0, 1.0 - dy / (2 * R))))
+    x_s = float(xF[0]) + 2 * R * math.sin(th)
+    segs = [(x_s - X0, 0.0), (-R * th, -1.0 / R), (-R * th, 1.0 / R)]
+    segs = [sg for sg in segs if abs(sg[0]) > 1e-9]
+    xWS, uWS = warmstart_from_segments([X0, Y0, float(x0[2])], segs, N, Ts, L)
+    xWS[0] = x0; xWS[-1] = xF
+    return xWS[:, 0].copy(), xWS[:, 1].copy(), xWS[:, 2].copy(), xWS, uWS
+
+
+def parallel_parking_batch(B, N=80, seed=1, n_obstacles=3):
+    """BASELINE.json config 3: parallel parking, N=80, seed 1; n_obstacles=3 (obstacles 1-3 of main.jl:154-157, the
+    wall at y=11 dropped -- XYbounds y<=10 makes it inactive) or 4 (the reference's own list)."""
+    sc = parallel_parking_scenario(n_obstacles)
+    rng = np.random.default_rng(seed)
+    X0 = rng.uniform(-10, 10, B); Y0 = rng.uniform(6.5, 9.5, B)
+    x0 = np.stack([X0, Y0, np.zeros(B), np.zeros(B)], 1)
+    rx = np.zeros((B, N + 1)); ry = np.zeros((B, N + 1)); ryaw = np.zeros((B, N + 1))
+    xWS = np.zeros((B, N + 1, 4)); uWS = np.zeros((B, N, 2))
+    for i in range(B):
+        rx[i], ry[i], ryaw[i], xWS[i], uWS[i] = warmstart_parallel(x0[i], sc["xF"], N, sc["Ts"], sc["L"])
+    sc.update(B=B, N=N, x0=x0, rx=rx, ry=ry, ryaw=ryaw, xWS=xWS, uWS=uWS)
+    return sc

@@ -68,6 +68,9 @@ class IpmOptions:
     #           poor.  This is the generic sparse-direct path (what Ipopt does with MUMPS) used for CPU timing.
     linsolve: str = "dense"
     order: np.ndarray | None = None     # symmetric ordering of the (n + mE) KKT unknowns for the sparse path
+    freeze_degenerate: float = 0.0      # > 0: an always-regularised row whose Jacobian row is below this threshold
+                                        # keeps its multiplier this iteration (its linearisation carries no information;
+                                        # Newton on |p|^2 = 1 from p = 0, QuadcopterSignedDist.jl:169 with l = 0.05)
 
 
 @dataclass
@@ -260,7 +263,13 @@ def solve(nlp, z0, opt: IpmOptions | None = None, yE0=None) -> IpmResult:
         bz = gf - np.where(hasL, mu / a, 0.0) + np.where(hasU, mu / b_, 0.0)
         gam = -np.where(sHasL, mu / c, 0.0) + np.where(sHasU, mu / d, 0.0)
         H0s = (W + sps.diags(Sz) + JI.T @ sps.diags(Ss) @ JI).tocsc()
-        rhs = np.concatenate([-(bz + JI.T @ (gam + Ss * cI)), -cE - dc * yE])
+        cE_eff = cE
+        if o.freeze_degenerate > 0 and o.dc_rows is not None:
+            rown = np.asarray(abs(JE).max(axis=1).todense()).ravel()
+            frozen = (dc > 0) & (rown < o.freeze_degenerate)
+            if frozen.any():
+                cE_eff = np.where(frozen, 0.0, cE)
+        rhs = np.concatenate([-(bz + JI.T @ (gam + Ss * cI)), -cE_eff - dc * yE])
         use_sparse = o.linsolve == "sparse"
         if not use_sparse:
             H0 = H0s.toarray(); JEd = JE.toarray()

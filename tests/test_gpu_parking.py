@@ -218,3 +218,32 @@ def test_k1_standalone_matches_oracle(P, variant, fix):
         assert np.abs(c[i] - c_ref).max() < 1e-11 * (1 + np.abs(c_ref).max())
         assert np.abs(gl[i] - gl_ref).max() < 1e-10 * (1 + np.abs(gl_ref).max())
         assert abs(f[i] - f_ref) < 1e-10 * (1 + abs(f_ref))
+
+
+@pytest.mark.parametrize("nob", [3, 4])
+def test_parallel_parking_config3(P, nob):
+    """BASELINE config 3 (parallel parking, seed 1): 3 obstacles as in BASELINE.json and the reference's own 4-obstacle
+    list (main.jl:154-157, vOb=[2,2,1,1]); signed-distance variant, retry enabled like the reference."""
+    from obca_b200 import scenarios
+    from oracle import kkt_check
+    sc = scenarios.parallel_parking_batch(512, 80, 1, nob)
+    r = solve(P, sc)
+    conv = r["exitflag"] == 1
+    assert conv.mean() >= 0.97
+    feas, e7, strict = P.check_parking_batch(sc["x0"], sc["xF"], 80, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], nob, sc["vOb"], sc["A"],
+                                             sc["b"], r["xp"], r["up"], r["lp"], r["np"], r["ts"], 0, 1, r["sl"])
+    assert strict[conv].mean() >= 0.99
+    i = int(np.argmax(conv))
+    e = kkt_check.reference_kkt_error(sc, i, r, "sd", 0)
+    assert e["E0"] < 1e-4
+
+
+def test_dist_and_fixed_time_full_batch_rates(P):
+    """Convergence of the other three driver variants at batch scale on the collision-free reverse-parking warm starts."""
+    from obca_b200 import scenarios
+    sc = scenarios.reverse_parking_batch(1024, 80, 0)
+    for sd, fix in ((0, 0), (1, 1), (0, 1)):
+        r = solve(P, sc, fix, sd)
+        assert (r["exitflag"] == 1).mean() >= 0.97, (sd, fix, (r["exitflag"] == 1).mean())
+        if fix:
+            assert np.array_equal(r["ts"], np.ones_like(r["ts"]))
