@@ -49,6 +49,8 @@ typedef struct obca_opts {
   double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, gamma_alpha;
   int max_backtrack;
   double dc;
+  int max_kick;      /* restoration substitute: barrier kicks per attempt after a failed line search (default 3) */
+  int quad_dual_ws;  /* quadcopter: 1 (default) closed-form dual warm start; 0 the reference's l = 0.05 start */
   /* execution */
   int device;        /* CUDA device ordinal used by this call */
   int retry;         /* 1: re-solve once from the last iterate when the first attempt does not converge
@@ -102,6 +104,26 @@ int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, c
                        const double* x, const double* u, const double* l, const double* n, const double* timeScale,
                        const double* sl, int fixTime, int sd, const obca_opts* opts, int* feasible, int* e,
                        int* strict);
+
+/* Batched QuadcopterSignedDist (signed_dist=1, QuadcopterNavigation/QuadcopterSignedDist.jl:25-300, called from
+ * mainQuadcopter.jl:152) / QuadcopterDist (signed_dist=0, QuadcopterDist.jl:25-282, mainQuadcopter.jl:145).
+ * inputs:  x0, xF 12 per problem; ob = ob1..ob5 as a 6 x 5 column-major block shared by the batch; xWS 12x(N+1) per
+ *          problem; timeWS scalar.  (uWS is ignored by the reference, QuadcopterSignedDist.jl:202.)
+ * outputs: xp 12x(N+1), up 4xN, ts (N+1), lp 30x(N+1) (= [l1;l2;l3;l4;l5], :296), slack 5x(N+1) (SD only, may be
+ *          NULL), exitflag 1 / 0 / 2 (2 = converged but sum(slack) > 1e-3, :283-288), iters, kkt_err, solve_seconds.
+ * A single solve attempt, like the reference (flag = 1, :227-235).  opts == NULL: defaults with max_iter = 3000
+ * (the reference leaves Ipopt's default). */
+int obca_quadcopter_solve_batch(int B, int N, const double* x0, const double* xF, double Ts, double R, const double* ob,
+                                const double* xWS, double timeWS, int signed_dist, const obca_opts* opts, double* xp,
+                                double* up, double* ts, double* lp, double* slack, int* exitflag, int* iters,
+                                double* kkt_err, double* solve_seconds);
+
+/* Batched constrSatisfaction (QuadcopterNavigation/constrSatisfaction.jl:25-204, called from mainQuadcopter.jl:147,154),
+ * restated verbatim (tolerance 1e-3, rows for i = 1..N, Dist-variant box on x10, one-sided norm row, quirk Q5).
+ * feasible[B] = the reference's Bool; worst[B] (optional) = largest violation found. */
+int obca_check_quadcopter(int B, int N, const double* x, const double* u, const double* timeScale, const double* x0,
+                          const double* xF, double Ts, const double* lambda, const double* ob, double R,
+                          const obca_opts* opts, int* feasible, double* worst);
 
 /* Per-phase device cycle counters of the last obca_parking_solve_batch[_dev] on `device`, summed over the batch
  * (thread 0 of every CTA, clock64): out8 = {eval (K1), kkt (K3), recover, merit, update, serial sections,

@@ -17,7 +17,7 @@ mutable struct ObcaOpts
     dual_inf_tol::Cdouble; constr_viol_tol::Cdouble; compl_inf_tol::Cdouble
     dw_min::Cdouble; dw_first::Cdouble; dw_max::Cdouble; kw_minus::Cdouble; kw_plus::Cdouble; kw_plus_first::Cdouble
     gamma_theta::Cdouble; gamma_phi::Cdouble; delta::Cdouble; s_theta::Cdouble; s_phi::Cdouble; eta_phi::Cdouble
-    gamma_alpha::Cdouble; max_backtrack::Cint; dc::Cdouble
+    gamma_alpha::Cdouble; max_backtrack::Cint; dc::Cdouble; max_kick::Cint; quad_dual_ws::Cint
     device::Cint; retry::Cint
     ObcaOpts() = new()
 end

@@ -62,6 +62,8 @@ struct IpmOpts {
   double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, gamma_alpha;
   int max_backtrack;
   double dc;             // always-on dual regularisation on norm rows and the terminal dynamics rows (1e-9)
+  int max_kick;          // barrier kicks (restoration substitute) per attempt; 0 = fail at the first line-search failure
+  int quad_dual_ws;      // quadcopter: 1 = closed-form dual warm start, 0 = the reference's l = 0.05
 };
 
 OBCA_HD IpmOpts default_opts() {
@@ -72,7 +74,7 @@ OBCA_HD IpmOpts default_opts() {
   o.dual_inf_tol = 1.0; o.constr_viol_tol = 1e-4; o.compl_inf_tol = 1e-4;
   o.dw_min = 1e-12; o.dw_first = 1e-4; o.dw_max = 1e20; o.kw_minus = 1.0 / 3.0; o.kw_plus = 8.0; o.kw_plus_first = 100.0;
   o.gamma_theta = 1e-5; o.gamma_phi = 1e-8; o.delta = 1.0; o.s_theta = 1.1; o.s_phi = 2.3; o.eta_phi = 1e-8;
-  o.gamma_alpha = 0.05; o.max_backtrack = 40; o.dc = 1e-9;
+  o.gamma_alpha = 0.05; o.max_backtrack = 40; o.dc = 1e-9; o.max_kick = 3; o.quad_dual_ws = 1;
   return o;
 }
 

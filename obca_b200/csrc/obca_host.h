@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "obca_solver.cuh"
+#include "obca_quad.cuh"
 
 namespace obca {
 
@@ -34,6 +35,19 @@ inline int fill_problem(ParkProblem& P, int N, int nOb, const int* vOb, const do
   P.signed_dist = signed_dist ? 1 : 0;
   P.w_a = (fixTime || !signed_dist) ? 0.5 : 0.1;                          // :79,:86 ; ParkingDist.jl:79,87
   P.w_yaw = fixTime ? 0.01 : 0.0001;                                      // :82,:91
+  return 0;
+}
+
+// Arguments of QuadcopterSignedDist.jl:25: obs = ob1..ob5 as 6 x 5 column-major; bounds of :78-93 (QuadcopterDist.jl:88).
+inline int fill_quad_problem(QuadProblem& P, int N, double Ts, double R, const double* obs, int signed_dist) {
+  memset(&P, 0, sizeof(P));
+  if (N < 2) return -1;
+  P.N = N; P.Ts = Ts; P.R = R; P.signed_dist = signed_dist ? 1 : 0;
+  for (int o = 0; o < QNOB; ++o)
+    for (int r = 0; r < 6; ++r) P.obs[o][r] = obs[6 * o + r];
+  const double lo[12] = {0, 0, 0, -3, -0.2, -0.2, -1, -1, -1, signed_dist ? -1.0 : -1.5, -1, -1};
+  const double hi[12] = {10, 10, 5, 3, 0.2, 0.2, 1, 1, 1, signed_dist ? 1.0 : 3.0, 1, 1};
+  for (int i = 0; i < 12; ++i) { P.xlo[i] = lo[i]; P.xhi[i] = hi[i]; }
   return 0;
 }
 

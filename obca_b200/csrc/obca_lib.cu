@@ -74,7 +74,7 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
     // (ParkingSignedDist.jl:256-263 / ParkingDist.jl:245-263).  One call site: the solver body exists once.
     int iters = 0, status = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-      ParkSolver<VM, SDV>::solve(C, attempt);
+      IpmDriver<ParkSolver<VM, SDV> >::solve(C, attempt);
       __syncthreads();
       iters += S.iters;
       status = S.status;
@@ -229,6 +229,84 @@ __global__ void k_check(const __grid_constant__ ParkProblem P, int B, const doub
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// quadcopter (obca_quad.cuh): persistent solver kernel + constrSatisfaction twin
+// ---------------------------------------------------------------------------------------------------------
+struct QBatchPtrs {
+  const double *x0, *xF, *xWS;
+  double timeWS;
+  double *xp, *up, *ts, *lp, *slack;
+  int *exitflag, *iters;
+  double* kkt_err;
+  int B;
+};
+
+template <bool SDV>
+__global__ void __launch_bounds__(128, 2)
+k_quad_solve(const __grid_constant__ QuadProblem P, const __grid_constant__ IpmOpts O, const QLay L, const QBatchPtrs bp,
+             double* __restrict__ Wall, int* __restrict__ counter) {
+  __shared__ ProbState S;
+  __shared__ double s_red[4 * 12];
+  __shared__ int s_b;
+  __shared__ double s_sum[4];
+  const int N = P.N, NS = N + 1;
+  double* W = Wall + (size_t)blockIdx.x * L.total * L.NSP;
+  for (;;) {
+    if (threadIdx.x == 0) s_b = atomicAdd(counter, 1);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= bp.B) break;
+    QCtx C;
+    C.P = &P; C.O = &O; C.L = L; C.W = W; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+    C.in.x0 = bp.x0 + 12 * (size_t)b; C.in.xF = bp.xF + 12 * (size_t)b; C.in.xWS = bp.xWS + (size_t)12 * NS * b;
+    C.in.timeWS = bp.timeWS;
+    QOutputs out;
+    out.xp = bp.xp + (size_t)12 * NS * b; out.up = bp.up + (size_t)4 * N * b; out.ts = bp.ts + (size_t)NS * b;
+    out.lp = bp.lp + (size_t)30 * NS * b; out.slack = bp.slack ? bp.slack + (size_t)5 * NS * b : nullptr;
+    IpmDriver<QuadSolver<SDV> >::solve(C, 0);      // flag = 1 in the reference: a single attempt (QuadcopterSignedDist.jl:227-235)
+    __syncthreads();
+    double ssum = 0.0;
+    for (int k = threadIdx.x; k < NS; k += blockDim.x) {
+      QuadSolver<SDV>::store_stage(C, k, out);
+      if (SDV) for (int j = 0; j < QNOB; ++j) ssum += W[(size_t)(L.SLK + j) * L.NSP + k];
+    }
+    for (int off = 16; off > 0; off >>= 1) ssum += __shfl_down_sync(0xffffffffu, ssum, off);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = ssum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_sum[w];
+      int ef = S.status == 1 ? 1 : 0;
+      if (SDV && ef == 1 && tot > 1e-3) ef = 2;      // sum-slack gate, QuadcopterSignedDist.jl:283-288
+      bp.exitflag[b] = ef; bp.iters[b] = S.iters; bp.kkt_err[b] = S.e0;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_quad_check(const __grid_constant__ QuadProblem P, int B, const double* __restrict__ x0,
+                             const double* __restrict__ xF, const double* __restrict__ x, const double* __restrict__ u,
+                             const double* __restrict__ ts, const double* __restrict__ lam, int* __restrict__ feasible,
+                             double* __restrict__ worst_out) {
+  __shared__ double s_w[4];
+  const int N = P.N, NS = N + 1;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    double w = 0.0;
+    for (int k = threadIdx.x; k < NS; k += blockDim.x)
+      w = fmax(w, quad_check_stage(P, k, x0 + 12 * (size_t)b, xF + 12 * (size_t)b, x + (size_t)12 * NS * b, u + (size_t)4 * N * b,
+                                   ts + (size_t)NS * b, lam + (size_t)30 * NS * b));
+    for (int off = 16; off > 0; off >>= 1) w = fmax(w, __shfl_down_sync(0xffffffffu, w, off));
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) w = fmax(w, s_w[i]);
+      feasible[b] = w <= 1e-3 ? 1 : 0;
+      if (worst_out) worst_out[b] = w;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -295,7 +373,7 @@ static IpmOpts to_ipm(const obca_opts* o) {
   r.kw_plus = o->kw_plus; r.kw_plus_first = o->kw_plus_first;
   r.gamma_theta = o->gamma_theta; r.gamma_phi = o->gamma_phi; r.delta = o->delta; r.s_theta = o->s_theta;
   r.s_phi = o->s_phi; r.eta_phi = o->eta_phi; r.gamma_alpha = o->gamma_alpha; r.max_backtrack = o->max_backtrack;
-  r.dc = o->dc;
+  r.dc = o->dc; r.max_kick = o->max_kick; r.quad_dual_ws = o->quad_dual_ws;
   return r;
 }
 
@@ -367,6 +445,24 @@ static int launch_eval(DevCtx& c, const ParkProblem& P, int B, const EvalIn& in,
   return 0;
 }
 
+template <bool SDV>
+static int launch_quad(DevCtx& c, const QuadProblem& P, const IpmOpts& O, const QBatchPtrs& bp) {
+  QLay L = make_qlayout(P);
+  if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad_solve<SDV>, L.NSP, 0));
+  if (occ < 1) occ = 1;
+  int grid = c.sms * occ;
+  if (grid > bp.B) grid = bp.B;
+  const size_t need = (size_t)grid * L.total * L.NSP * sizeof(double);
+  int rc = ensure((void**)&c.W, &c.Wbytes, need);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
+  k_quad_solve<SDV><<<grid, L.NSP, 0, c.st>>>(P, O, L, bp, c.W, c.counter);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" {
 
 int obca_version(void) { return OBCA_VERSION; }
@@ -386,7 +482,7 @@ void obca_default_opts(obca_opts* o) {
   o->kw_plus = d.kw_plus; o->kw_plus_first = d.kw_plus_first;
   o->gamma_theta = d.gamma_theta; o->gamma_phi = d.gamma_phi; o->delta = d.delta; o->s_theta = d.s_theta;
   o->s_phi = d.s_phi; o->eta_phi = d.eta_phi; o->gamma_alpha = d.gamma_alpha; o->max_backtrack = d.max_backtrack;
-  o->dc = d.dc;
+  o->dc = d.dc; o->max_kick = d.max_kick; o->quad_dual_ws = d.quad_dual_ws;
   o->device = 0; o->retry = 1;
 }
 
@@ -547,6 +643,85 @@ int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, c
   CK(cudaMemcpyAsync(feasible, di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (e) CK(cudaMemcpyAsync(e, di + B, 7 * (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (strict) CK(cudaMemcpyAsync(strict, di + 8 * (size_t)B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int obca_quadcopter_solve_batch(int B, int N, const double* x0, const double* xF, double Ts, double R, const double* ob,
+                                const double* xWS, double timeWS, int signed_dist, const obca_opts* opts, double* xp,
+                                double* up, double* ts, double* lp, double* slack, int* exitflag, int* iters,
+                                double* kkt_err, double* solve_seconds) {
+  if (B <= 0 || !x0 || !xF || !ob || !xWS || !xp || !up || !ts || !lp || !exitflag || !iters || !kkt_err) {
+    set_err("null argument"); return OBCA_ERR_ARG;
+  }
+  QuadProblem P;
+  if (fill_quad_problem(P, N, Ts, R, ob, signed_dist)) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  IpmOpts O = to_ipm(opts);
+  if (!opts) O.max_iter = 3000;                        // the reference sets no max_iter here (Ipopt default)
+  const size_t NS = N + 1;
+  const size_t n0 = 12 * (size_t)B, nx = 12 * NS * B, nu = 4 * (size_t)N * B, nt = NS * B, nl = 30 * NS * B, ns = 5 * NS * B;
+  const size_t dbytes = (2 * n0 + 2 * nx + nu + nt + nl + ns + B) * sizeof(double);
+  rc = ensure((void**)&c->stage, &c->stage_bytes, dbytes + 2 * (size_t)B * sizeof(int));
+  if (rc) return rc;
+  double* d = (double*)c->stage;
+  double *d0 = d, *dF = d0 + n0, *dW = dF + n0, *dxp = dW + nx, *dup = dxp + nx, *dts = dup + nu, *dlp = dts + nt, *dsl = dlp + nl,
+         *derr = dsl + ns;
+  int* di = (int*)(c->stage + dbytes);
+  cudaStream_t st = c->st;
+  CK(cudaMemcpyAsync(d0, x0, n0 * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dF, xF, n0 * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dW, xWS, nx * 8, cudaMemcpyHostToDevice, st));
+  QBatchPtrs bp;
+  bp.x0 = d0; bp.xF = dF; bp.xWS = dW; bp.timeWS = timeWS; bp.xp = dxp; bp.up = dup; bp.ts = dts; bp.lp = dlp; bp.slack = dsl;
+  bp.exitflag = di; bp.iters = di + B; bp.kkt_err = derr; bp.B = B;
+  CK(cudaEventRecord(c->ev0, st));
+  rc = signed_dist ? launch_quad<true>(*c, P, O, bp) : launch_quad<false>(*c, P, O, bp);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev1, st));
+  CK(cudaMemcpyAsync(xp, dxp, nx * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(up, dup, nu * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ts, dts, nt * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(lp, dlp, nl * 8, cudaMemcpyDeviceToHost, st));
+  if (slack && signed_dist) CK(cudaMemcpyAsync(slack, dsl, ns * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(kkt_err, derr, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(exitflag, di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(iters, di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (solve_seconds) *solve_seconds = ms * 1e-3;
+  return 0;
+}
+
+int obca_check_quadcopter(int B, int N, const double* x, const double* u, const double* timeScale, const double* x0,
+                          const double* xF, double Ts, const double* lambda, const double* ob, double R,
+                          const obca_opts* opts, int* feasible, double* worst) {
+  if (B <= 0 || !x || !u || !timeScale || !x0 || !xF || !lambda || !ob || !feasible) { set_err("null argument"); return OBCA_ERR_ARG; }
+  QuadProblem P;
+  if (fill_quad_problem(P, N, Ts, R, ob, 0)) { set_err("unsupported problem shape"); return OBCA_ERR_ARG; }
+  DevCtx* c;
+  int rc = get_ctx(opts ? opts->device : 0, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t NS = N + 1;
+  const size_t n0 = 12 * (size_t)B, nx = 12 * NS * B, nu = 4 * (size_t)N * B, nt = NS * B, nl = 30 * NS * B;
+  const size_t dbytes = (2 * n0 + nx + nu + nt + nl + B) * sizeof(double);
+  rc = ensure((void**)&c->stage, &c->stage_bytes, dbytes + (size_t)B * sizeof(int));
+  if (rc) return rc;
+  double* d = (double*)c->stage;
+  double *d0 = d, *dF = d0 + n0, *dx = dF + n0, *du = dx + nx, *dt = du + nu, *dl = dt + nt, *dw = dl + nl;
+  int* di = (int*)(c->stage + dbytes);
+  cudaStream_t st = c->st;
+  CK(cudaMemcpyAsync(d0, x0, n0 * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dF, xF, n0 * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dx, x, nx * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(du, u, nu * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dt, timeScale, nt * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dl, lambda, nl * 8, cudaMemcpyHostToDevice, st));
+  const int grid = B < 4 * c->sms ? B : 4 * c->sms;
+  k_quad_check<<<grid, 128, 0, st>>>(P, B, d0, dF, dx, du, dt, dl, di, dw);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(feasible, di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (worst) CK(cudaMemcpyAsync(worst, dw, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -142,6 +142,7 @@ constexpr int RK = 0, RPP = 16, Rpp = 44;   // RPP: rows 0..3 of P_{k+1}, row-ma
 struct ProbState {
   double t, zTL, zTU, dt;           // time scale, its bound multipliers, its step
   double eN[4];                     // predicted end-point error of the step (stage N is pinned to xF)
+  double eNq[12];                   // same, quadcopter model
   double mu, tau;
   double dw, dw_last;
   double theta_max, theta_min;
@@ -156,6 +157,7 @@ struct ProbState {
   int flag;       // generic broadcast flag
   int ok;
   int n_fact;     // factorisations
+  int n_kick;     // barrier kicks after line-search failures
   long long prof[8];   // device cycle counters per phase: eval, kkt, recover, merit, update, serial, n_merit, n_eval
   long long tmark;
 };
@@ -542,7 +544,7 @@ struct ParkSolver {
       const double m = (double)(N + 1);
       const double gl = t - 0.8, gu = 1.2 - t;
       fobj += m * (0.5 * t + t * t);
-      RIC(RQ + sym_idx<NYV>(IT, IT), k) += 2.0 * m + m * (S.zTL * rcp(gl) + S.zTU * rcp(gu)) + dw;
+      RIC(RQ + sym_idx<NYV>(IT, IT), k) += 2.0 * m + m * (S.zTL * rcp(gl) + S.zTU * rcp(gu)) + m * dw;   // N+1 copies of timeScale, each regularised
       RIC(Rq + IT, k) += m * (0.5 + 2.0 * t) + m * (-mu_b * rcp(gl) + mu_b * rcp(gu));
       if (do_err) {
         rz_t += m * (0.5 + 2.0 * t) - m * (S.zTL - S.zTU);
@@ -1183,12 +1185,6 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // serial helpers (thread 0)
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void apply_errors(const PkCtx& C, const EvalPart& e) {
-    ProbState& S = *C.S;
-    S.e_dual = C.P->fix_time ? e.e_dual : dmax(e.e_dual, dabs(e.rt));
-    S.e_pr = e.e_pr; S.e_cmax = e.cmax; S.e_cmin = e.cmin; S.sum_y = e.sy; S.sum_z = e.sz;
-    S.th_k = e.th; S.ph_k = e.phi; S.rz_t = e.rt; S.f_k = e.f;
-  }
   // number of multipliers (for Ipopt's s_d, s_c scaling)
   OBCA_HD static void mult_counts(const ParkProblem& P, double& n_mult, double& n_bmult) {
     const int N = P.N, NS = N + 1;
@@ -1198,11 +1194,52 @@ struct ParkSolver {
     const double mI = N + (double)P.nOb * NS + (P.signed_dist ? 0.0 : (double)P.nOb * NS);
     n_bmult = nb; n_mult = nb + mE + mI;
   }
-  OBCA_HD static double err_mu(const PkCtx& C, double mu_t) {
+  // ---- adapters used by the generic interior-point driver (obca_ipm.cuh) ----
+  typedef PkCtx Ctx;
+  OBCA_HD static int n_stages(const PkCtx& C) { return C.P->N + 1; }
+  OBCA_HD static bool fixed_time(const PkCtx& C) { return C.P->fix_time != 0; }
+  OBCA_HD static void mult_counts(const PkCtx& C, double& n_mult, double& n_bmult) { mult_counts(*C.P, n_mult, n_bmult); }
+  OBCA_HD static void init_scalars(const PkCtx& C, int restart) {
+    ProbState& S = *C.S;
+    const IpmOpts& O = *C.O;
+    S.t = C.P->fix_time ? 1.0 : push_lo(restart ? S.t : 1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
+    S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
+  }
+  OBCA_HD static void update_scalars(const PkCtx& C) {
+    ProbState& S = *C.S;
+    if (!C.P->fix_time) {
+      double q = S.t, zl = S.zTL, zu = S.zTU;
+      upd_pair(q, S.dt, zl, zu, 0.8, 1.2, S.alpha, S.a_du, S.mu, C.O->kappa_sigma);
+      S.t = q; S.zTL = zl; S.zTU = zu;
+    }
+  }
+  OBCA_HD static int kkt_host(const PkCtx& C) {
+#if defined(__CUDA_ARCH__)
+    return 0;
+#else
+    return C.tile ? kkt_solve_warp_emul(C, C.tile) : kkt_solve(C);
+#endif
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Generic interior-point driver (Ipopt's algorithm: monotone barrier update, inertia correction, filter line
+// search).  M is the model policy (ParkSolver<VM,SDV>, QuadSolver<SDV>): per-stage phase functions + the KKT sweep.
+// ------------------------------------------------------------------------------------------------------------
+template <class M>
+struct IpmDriver {
+  typedef typename M::Ctx Ctx;
+  OBCA_HD static void apply_errors(const Ctx& C, const EvalPart& e) {
+    ProbState& S = *C.S;
+    S.e_dual = M::fixed_time(C) ? e.e_dual : dmax(e.e_dual, dabs(e.rt));
+    S.e_pr = e.e_pr; S.e_cmax = e.cmax; S.e_cmin = e.cmin; S.sum_y = e.sy; S.sum_z = e.sz;
+    S.th_k = e.th; S.ph_k = e.phi; S.rz_t = e.rt; S.f_k = e.f;
+  }
+  OBCA_HD static double err_mu(const Ctx& C, double mu_t) {
     const ProbState& S = *C.S;
     const IpmOpts& O = *C.O;
     double n_mult, n_bmult;
-    mult_counts(*C.P, n_mult, n_bmult);
+    M::mult_counts(C, n_mult, n_bmult);
     const double sd = dmax(O.s_max, (S.sum_y + S.sum_z) / n_mult) / O.s_max;
     const double sc = dmax(O.s_max, S.sum_z / n_bmult) / O.s_max;
     const double comp = dmax(S.e_cmax - mu_t, mu_t - S.e_cmin);
@@ -1212,27 +1249,24 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // the solve: all threads of the CTA call this with the same context
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD static void solve(const PkCtx& C, int restart = 0) {
-    const ParkProblem& P = *C.P;
+  OBCA_HD static void solve(const Ctx& C, int restart = 0) {
     const IpmOpts& O = *C.O;
     ProbState& S = *C.S;
-    const int N = P.N, NS = N + 1;
-    const bool fix = P.fix_time != 0;
+    const int NS = M::n_stages(C);
 
     OBCA_SERIAL {
-      S.t = fix ? 1.0 : push_lo(restart ? S.t : 1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
-      S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
+      M::init_scalars(C, restart);
       S.mu = O.mu_init; S.tau = dmax(O.tau_min, 1.0 - O.mu_init);
-      S.dw = 0.0; S.dw_last = 0.0; S.nfilt = 0; S.status = 0; S.iters = 0; S.n_fact = 0;
+      S.dw = 0.0; S.dw_last = 0.0; S.nfilt = 0; S.status = 0; S.iters = 0; S.n_fact = 0; S.n_kick = 0;
 #if defined(__CUDA_ARCH__)
       if (!restart) for (int i = 0; i < 8; ++i) S.prof[i] = 0;
       S.tmark = clock64();
 #endif
     }
     OBCA_SYNC();
-    OBCA_FOR_STAGES(k, NS) init_stage(C, k, restart);
+    OBCA_FOR_STAGES(k, NS) M::init_stage(C, k, restart);
     OBCA_SYNC();
-    OBCA_FOR_STAGES(k, NS) init_slacks(C, k);
+    OBCA_FOR_STAGES(k, NS) M::init_slacks(C, k);
     OBCA_SYNC();
 
     bool first = true;
@@ -1242,7 +1276,7 @@ struct ParkSolver {
       OBCA_SYNC();
       EvalPart ep;
       part_init(ep);
-      OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
+      OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
       OBCA_REDUCE(ep);
       OBCA_PROF(0); OBCA_PROF_COUNT(7);
       OBCA_SERIAL {
@@ -1276,7 +1310,7 @@ struct ParkSolver {
       if (S.flag == 1) break;
       if (S.flag == 2) {   // mu changed: the barrier terms of the stage models (and phi) are stale
         part_init(ep);
-        OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
+        OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
         OBCA_REDUCE(ep);
         OBCA_PROF(0); OBCA_PROF_COUNT(7);
         OBCA_SERIAL { apply_errors(C, ep); S.ok = ep.ok; }
@@ -1288,12 +1322,12 @@ struct ParkSolver {
       for (;;) {
 #if defined(__CUDA_ARCH__)
         if (S.ok && threadIdx.x < 32) {
-          const int ok = kkt_solve_warp(C, C.tile);
+          const int ok = M::kkt_solve_warp(C, C.tile);
           __syncwarp();
           if (threadIdx.x == 0) S.ok = ok;
         }
 #else
-        if (S.ok) S.ok = C.tile ? kkt_solve_warp_emul(C, C.tile) : kkt_solve(C);
+        if (S.ok) S.ok = M::kkt_host(C);
 #endif
         OBCA_SYNC();
         OBCA_SERIAL {
@@ -1310,7 +1344,7 @@ struct ParkSolver {
         OBCA_PROF(1);
         if (S.ok != 0) break;
         part_init(ep);
-        OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, false, true, e1); part_merge(ep, e1); }
+        OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, false, true, e1); part_merge(ep, e1); }
         OBCA_REDUCE(ep);
         OBCA_SERIAL { S.ok = ep.ok; }
         OBCA_SYNC();
@@ -1321,7 +1355,7 @@ struct ParkSolver {
       // ---- K4: recover, step lengths, filter line search ----
       StepPart sp;
       part_init(sp);
-      OBCA_FOR_STAGES(k, NS) { StepPart s1; recover_stage(C, k, s1); part_merge(sp, s1); }
+      OBCA_FOR_STAGES(k, NS) { StepPart s1; M::recover_stage(C, k, s1); part_merge(sp, s1); }
       OBCA_REDUCE(sp);
       OBCA_PROF(2);
       OBCA_SERIAL {
@@ -1342,7 +1376,7 @@ struct ParkSolver {
         const double alpha = S.alpha;
         MeritPart mp;
         part_init(mp);
-        OBCA_FOR_STAGES(k, NS) { MeritPart m1; merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
+        OBCA_FOR_STAGES(k, NS) { MeritPart m1; M::merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
         OBCA_REDUCE(mp);
         OBCA_PROF(3); OBCA_PROF_COUNT(6);
         OBCA_SERIAL {
@@ -1368,23 +1402,31 @@ struct ParkSolver {
             }
           } else {
             S.alpha = 0.5 * alpha;
-            if (S.alpha < S.a_min || nbt + 1 >= O.max_backtrack) { S.flag = -1; S.status = -1; }
+            if (S.alpha < S.a_min || nbt + 1 >= O.max_backtrack) {
+              // Ipopt would enter its restoration phase here.  Substitute ("barrier kick"): forget the filter,
+              // raise the barrier parameter one decade and recompute the direction from the same iterate; after
+              // max_kick kicks the attempt ends with a line-search failure (the caller's retry logic takes over).
+              if (S.n_kick < O.max_kick) {
+                S.n_kick++;
+                S.nfilt = 0;
+                S.mu = dmin_(O.mu_init, 10.0 * S.mu);
+                S.tau = dmax(O.tau_min, 1.0 - S.mu);
+                S.flag = -2;
+              } else {
+                S.flag = -1; S.status = -1;
+              }
+            }
           }
         }
         OBCA_SYNC();
         OBCA_PROF(5);
         if (S.flag != 0) break;
       }
+      if (S.flag == -2) continue;     // barrier kick: new direction from the same iterate
       if (S.flag < 0) break;
       // ---- accept ----
-      OBCA_FOR_STAGES(k, NS) update_stage(C, k);
-      OBCA_SERIAL {
-        if (!fix) {
-          double q = S.t, zl = S.zTL, zu = S.zTU;
-          upd_pair(q, S.dt, zl, zu, 0.8, 1.2, S.alpha, S.a_du, S.mu, O.kappa_sigma);
-          S.t = q; S.zTL = zl; S.zTU = zu;
-        }
-      }
+      OBCA_FOR_STAGES(k, NS) M::update_stage(C, k);
+      OBCA_SERIAL { M::update_scalars(C); }
       OBCA_SYNC();
       OBCA_PROF(4);
     }

@@ -101,3 +101,48 @@ def strict_check(x0, xF, N, Ts, L, ego, XYbounds, nOb, vOb, A, b, x, u, l, n, ti
             dist = dist + np.asarray(sl, float)[j]
         worst = max(worst, (0.05 - dist).max())
     return (1 if worst <= tol else 0), worst
+
+
+def constrSatisfaction(x, u, timeScale, x0, xF, Ts, lam, ob1, ob2, ob3, ob4, ob5, R):
+    """Verbatim numpy restatement of QuadcopterNavigation/constrSatisfaction.jl:25-204 (tolerance 1e-3; rows for
+    i = 1..N only; Dist-variant box on x10; one-sided norm row; quirk Q5 in the body-rate rows)."""
+    mass, g = 0.5, 9.81
+    k_F, k_M = 0.0611, 0.0015
+    I = np.array([3.9, 4.4, 4.9]) * 1e-3
+    L = 0.225
+    x = np.asarray(x, float); u = np.asarray(u, float); ts = np.asarray(timeScale, float).ravel(); lam = np.asarray(lam, float)
+    x0 = np.asarray(x0, float).ravel(); xF = np.asarray(xF, float).ravel()
+    ls = [lam[6 * o:6 * o + 6] for o in range(5)]
+    bs = [np.asarray(b, float).ravel() for b in (ob1, ob2, ob3, ob4, ob5)]
+    N = x.shape[1] - 1
+    if np.abs(x[:, 0] - x0).max() > 1e-3: return False              # :56-61
+    if np.abs(x[:, -1] - xF).max() > 1e-3: return False             # :63-68
+    A = np.vstack([np.eye(3), -np.eye(3)])
+    xl = x.ravel(order="F")                                          # linear (column-major) indexing
+    lo = np.array([0, 0, 0, -3, -0.2, -0.2, -1, -1, -1, -1.5, -1, -1.0]); hi = np.array([10, 10, 5, 3, 0.2, 0.2, 1, 1, 1, 3, 1, 1.0])
+    for i in range(N):
+        if (1.2 - u[:, i]).max() > 0 or (u[:, i] - 7.8).max() > 0: return False
+        if (lo - x[:, i]).max() > 0 or (x[:, i] - hi).max() > 0: return False
+        h = ts[i] * Ts
+        F = k_F * (u[:, i] ** 2).sum()
+        xi = x[:, i]
+        s = np.zeros(13)
+        s[0] = x[0, i + 1] - (xi[0] + h * xi[6]); s[1] = x[1, i + 1] - (xi[1] + h * xi[7]); s[2] = x[2, i + 1] - (xi[2] + h * xi[8])
+        s[3] = x[3, i + 1] - (xi[3] + h * (np.cos(xi[4]) * xi[9] + np.sin(xi[4]) * xi[11]))
+        s[4] = x[4, i + 1] - (xi[4] + h * (np.sin(xi[4]) * np.tan(xi[3]) * xi[9] + xi[10] - np.cos(xi[4]) * np.tan(xi[3]) * xi[11]))
+        s[5] = x[5, i + 1] - (xi[5] + h * (-np.sin(xi[4]) / np.cos(xi[3]) * xi[9] + np.cos(xi[4]) / np.cos(xi[3]) * xi[11]))
+        s[6] = x[6, i + 1] - (xi[6] + h / mass * (F * (np.sin(xi[3]) * np.cos(xi[4]) * np.sin(xi[5]) + np.sin(xi[4]) * np.cos(xi[5]))))
+        s[7] = x[7, i + 1] - (xi[7] + h / mass * (F * (-np.sin(xi[3]) * np.cos(xi[4]) * np.cos(xi[5]) + np.sin(xi[4]) * np.sin(xi[5]))))
+        s[8] = x[8, i + 1] - (xi[8] + h / mass * (F * (np.cos(xi[3]) * np.cos(xi[4])) - mass * g))
+        s[9] = x[9, i + 1] - (xi[9] + h / I[0] * (L * k_F * (u[1, i] ** 2 - u[3, i] ** 2) - (I[2] - I[1]) * xl[10] * xl[11]))
+        s[10] = x[10, i + 1] - (xi[10] + h / I[1] * (L * k_F * (u[2, i] ** 2 - u[0, i] ** 2) - (I[0] - I[2]) * xl[9] * xl[11]))
+        s[11] = x[11, i + 1] - (xi[11] + h / I[2] * (k_M * (u[0, i] ** 2 - u[1, i] ** 2 + u[2, i] ** 2 - u[3, i] ** 2) - (I[1] - I[0]) * xl[9] * xl[10]))
+        s[12] = ts[i] - ts[i + 1]
+        if np.abs(s).max() > 1e-3: return False
+        if lam.min() < -1e-3: return False
+        t1 = np.array([(l[0, i] - l[3, i]) ** 2 + (l[1, i] - l[4, i]) ** 2 + (l[2, i] - l[5, i]) ** 2 - 1 for l in ls])
+        if t1.max() > 1e-3: return False
+        t2 = np.array([-(b @ l[:, i]) + xi[0] * (A[:, 0] @ l[:, i]) + xi[1] * (A[:, 1] @ l[:, i]) + xi[2] * (A[:, 2] @ l[:, i]) - R
+                       for l, b in zip(ls, bs)])
+        if t2.min() < -1e-3: return False
+    return True

@@ -68,6 +68,7 @@ class IpmOptions:
     #           poor.  This is the generic sparse-direct path (what Ipopt does with MUMPS) used for CPU timing.
     linsolve: str = "dense"
     order: np.ndarray | None = None     # symmetric ordering of the (n + mE) KKT unknowns for the sparse path
+    max_kick: int = 3                   # restoration substitute: barrier kicks after a failed line search
     freeze_degenerate: float = 0.0      # > 0: an always-regularised row whose Jacobian row is below this threshold
                                         # keeps its multiplier this iteration (its linearisation carries no information;
                                         # Newton on |p|^2 = 1 from p = 0, QuadcopterSignedDist.jl:169 with l = 0.05)
@@ -221,6 +222,7 @@ def solve(nlp, z0, opt: IpmOptions | None = None, yE0=None) -> IpmResult:
         return max(dinf / sd, cinf, pinf / sc), dinf, cinf, pinf
 
     filt = []           # list of (theta, phi)
+    n_kick = 0
     th0 = theta(z, s)
     theta_max = 1e4 * max(1.0, th0); theta_min = 1e-4 * max(1.0, th0)
     dw_last = 0.0
@@ -369,6 +371,12 @@ def solve(nlp, z0, opt: IpmOptions | None = None, yE0=None) -> IpmResult:
             alpha *= 0.5
             nbt += 1
         if not accepted:
+            if n_kick < o.max_kick:             # "barrier kick" (restoration substitute, same rule as the CUDA solver)
+                n_kick += 1
+                filt = []
+                mu = min(o.mu_init, 10.0 * mu)
+                tau = max(o.tau_min, 1 - mu)
+                continue
             status = -1
             break
         if not ftype:

@@ -162,13 +162,38 @@ def build_quadcopter_nlp(x0, xF, N, Ts, R, obs, variant="sd"):
     return nlp
 
 
-def initial_point(lay: QLayout, xWS, timeWS):
-    """:199-210: ts = timeWS, x = xWS, u = w_H ("faster not to warm-start", uWS ignored), l = 0.05, slack = 1."""
+def dual_ws(pos, b6):
+    """Closed-form dual warm start of one (position, box) pair (twin of quad_dual_ws in obca_quad_local.cuh)."""
+    hi = b6[:3]; lo = -b6[3:]
+    cl = np.clip(pos, lo, hi)
+    d = pos - cl
+    lam = np.zeros(6)
+    n2 = d @ d
+    if n2 > 1e-24:
+        p = d / np.sqrt(n2)
+        lam[:3] = np.maximum(p, 0); lam[3:] = np.maximum(-p, 0)
+    else:
+        pen = np.concatenate([hi - pos, pos - lo])
+        # same tie-breaking order as the kernel: (hi_0, lo_0, hi_1, lo_1, hi_2, lo_2), first strict minimum
+        order = [0, 3, 1, 4, 2, 5]
+        best = min(order, key=lambda i: (pen[i], order.index(i)))
+        lam[best] = 1.0
+    return lam
+
+
+def initial_point(lay: QLayout, xWS, timeWS, obs=None):
+    """:199-210: ts = timeWS, x = xWS, u = w_H ("faster not to warm-start", uWS ignored), slack = 1 and
+    l = 0.05 (obs=None, the reference's start) or the closed-form dual warm start (obs given)."""
     z = np.zeros(lay.n)
-    z[:12 * lay.NS] = np.asarray(xWS, float)[:, :lay.NS].T.ravel()
+    xWS = np.asarray(xWS, float)
+    z[:12 * lay.NS] = xWS[:, :lay.NS].T.ravel()
     z[lay.oT:lay.oT + lay.NS] = timeWS
     z[lay.oU:lay.oU + 4 * lay.N] = W_H
     z[lay.oL:lay.oS] = 0.05
+    if obs is not None:
+        for o in range(5):
+            for k in range(lay.NS):
+                z[lay.l(o, np.arange(6), k)] = dual_ws(xWS[:3, k], np.asarray(obs[o], float))
     if lay.variant == "sd":
         z[lay.oS:] = 1.0
     return z

@@ -11,6 +11,7 @@
 #include "../../obca_b200/csrc/obca_host.h"
 #include "../../obca_b200/csrc/obca_dualws.cuh"
 #include "../../obca_b200/csrc/obca_eval.cuh"
+#include "../../obca_b200/csrc/obca_quad.cuh"
 
 using namespace obca;
 
@@ -22,7 +23,7 @@ static void run_one(const ParkProblem& P, const IpmOpts& O, const PkLay& L, doub
   std::vector<double> tile(256, 0.0);
   static const bool use_warp = getenv("OBCA_EMUL_SERIAL_KKT") == nullptr;
   C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = ric.data(); C.red_scratch = nullptr; C.tile = use_warp ? tile.data() : nullptr; C.S = &S; C.in = in;
-  ParkSolver<VM, SDV>::solve(C);
+  IpmDriver<ParkSolver<VM, SDV> >::solve(C);
   for (int k = 0; k <= P.N; ++k) ParkSolver<VM, SDV>::store_stage(C, k, out);
 }
 
@@ -146,6 +147,40 @@ int emul_parking_eval_batch(int B, int N, int nOb, const int* vOb, const double*
       if (signed_dist) { if (vm == 2) eval_stage<2, true>(P, k, ib, ob); else eval_stage<4, true>(P, k, ib, ob); }
       else { if (vm == 2) eval_stage<2, false>(P, k, ib, ob); else eval_stage<4, false>(P, k, ib, ob); }
     }
+  }
+  return 0;
+}
+
+// quadcopter (QuadcopterSignedDist.jl:25 / QuadcopterDist.jl:25), B problems; x0, xF 12 x B; obs 6 x 5 shared;
+// xWS 12 x (N+1) per problem; outputs in the reference's shapes
+int emul_quadcopter_solve_batch(int B, int N, const double* x0, const double* xF, double Ts, double R, const double* obs,
+                                const double* xWS, double timeWS, int signed_dist, const IpmOpts* opts, double* xp,
+                                double* up, double* ts, double* lp, double* slack, int* status, int* iters,
+                                double* kkt_err, int* nfact) {
+  QuadProblem P;
+  if (fill_quad_problem(P, N, Ts, R, obs, signed_dist)) return -1;
+  IpmOpts O = opts ? *opts : default_opts();
+  QLay Lay = make_qlayout(P);
+  const size_t NS = N + 1;
+#pragma omp parallel for schedule(dynamic)
+  for (int i = 0; i < B; ++i) {
+    std::vector<double> W((size_t)Lay.total * Lay.NSP, 0.0);
+    QCtx C;
+    ProbState S;
+    C.P = &P; C.O = &O; C.L = Lay; C.W = W.data(); C.red_scratch = nullptr; C.tile = nullptr; C.S = &S;
+    C.in.x0 = x0 + 12 * (size_t)i; C.in.xF = xF + 12 * (size_t)i; C.in.xWS = xWS + 12 * NS * i; C.in.timeWS = timeWS;
+    QOutputs out;
+    out.xp = xp + 12 * NS * i; out.up = up + (size_t)4 * N * i; out.ts = ts + NS * i; out.lp = lp + 30 * NS * i;
+    out.slack = slack ? slack + 5 * NS * i : nullptr;
+    if (signed_dist) {
+      IpmDriver<QuadSolver<true> >::solve(C);
+      for (int k = 0; k <= N; ++k) QuadSolver<true>::store_stage(C, k, out);
+    } else {
+      IpmDriver<QuadSolver<false> >::solve(C);
+      for (int k = 0; k <= N; ++k) QuadSolver<false>::store_stage(C, k, out);
+    }
+    status[i] = S.status; iters[i] = S.iters; kkt_err[i] = S.e0;
+    if (nfact) nfact[i] = S.n_fact;
   }
   return 0;
 }

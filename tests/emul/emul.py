@@ -20,7 +20,7 @@ class IpmOpts(C.Structure):
                 ("kw_plus", C.c_double), ("kw_plus_first", C.c_double),
                 ("gamma_theta", C.c_double), ("gamma_phi", C.c_double), ("delta", C.c_double), ("s_theta", C.c_double),
                 ("s_phi", C.c_double), ("eta_phi", C.c_double), ("gamma_alpha", C.c_double),
-                ("max_backtrack", C.c_int), ("dc", C.c_double)]
+                ("max_backtrack", C.c_int), ("dc", C.c_double), ("max_kick", C.c_int), ("quad_dual_ws", C.c_int)]
 
 
 def build(force=False):
@@ -129,3 +129,23 @@ def eval_batch(sc_one, arrays, fixTime, variant):
            _p(arrays["sl"]), _p(arrays["y"]), int(fixTime), sd, _p(c), _p(gl), _p(fk))
     assert rc == 0
     return c, gl, fk
+
+
+def quad_solve_batch(sc, variant="sd", opts=None):
+    """sc: dict from obca_b200.scenarios.quadcopter_batch (B, N, Ts, R, obs (5,6), x0 (B,12), xF (B,12), xWS (B,12,N+1))."""
+    B, N = sc["B"], sc["N"]; NS = N + 1
+    x0 = np.ascontiguousarray(sc["x0"], dtype=float); xF = np.ascontiguousarray(sc["xF"], dtype=float)
+    obs = np.ascontiguousarray(sc["obs"], dtype=float)                       # rows = obstacles -> memory 6 x 5 column-major
+    xWS = np.ascontiguousarray(np.transpose(sc["xWS"], (0, 2, 1)), dtype=float)   # per problem [N+1][12] == 12 x (N+1) column-major
+    sd = 1 if variant == "sd" else 0
+    xp = np.zeros((B, NS, 12)); up = np.zeros((B, N, 4)); ts = np.zeros((B, NS)); lp = np.zeros((B, NS, 30)); sl = np.zeros((B, NS, 5))
+    status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32); err = np.zeros(B); nfact = np.zeros(B, np.int32)
+    f = lib().emul_quadcopter_solve_batch
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 10
+    rc = f(B, N, _p(x0), _p(xF), float(sc["Ts"]), float(sc["R"]), _p(obs), _p(xWS), float(sc.get("timeWS", 1.0)), sd,
+           C.cast(C.byref(opts), C.c_void_p) if opts is not None else None, _p(xp), _p(up), _p(ts), _p(lp), _p(sl), _p(status),
+           _p(iters), _p(err), _p(nfact))
+    assert rc == 0, rc
+    T = lambda a: np.transpose(a, (0, 2, 1))
+    return dict(xp=T(xp), up=T(up), ts=ts, lp=T(lp), slack=T(sl), status=status, iters=iters, err=err, nfact=nfact)

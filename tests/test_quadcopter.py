@@ -1,0 +1,84 @@
+"""Quadcopter NLPs (QuadcopterSignedDist.jl / QuadcopterDist.jl / constrSatisfaction.jl, BASELINE config 4).
+CPU part: kernel sources (host emulation) against the oracle.  GPU part (-m gpu): the C-ABI path."""
+import numpy as np
+import pytest
+
+from obca_b200 import scenarios
+from oracle import checkers, ipm_ref, kkt_check
+from oracle.quadcopter_nlp import build_quadcopter_nlp
+from oracle.quadcopter_solve import solve_quadcopter
+
+
+def _cert(sc, i, N, variant, xp, up, ts, lp, sl):
+    nlp = build_quadcopter_nlp(sc["x0"][i], sc["xF"][i], N, sc["Ts"], sc["R"], sc["obs"], variant)
+    z = nlp.lay.pack(xp, up, ts, lp, sl if variant == "sd" else None)
+    return kkt_check.kkt_certificate(nlp, z), nlp
+
+
+def test_oracle_quadcopter_nlp_sizes_and_derivatives():
+    sc = scenarios.quadcopter_batch(1, 10, 2)
+    for variant, n_exp in (("sd", 52 * 10 + 48), ("d", 47 * 10 + 43)):
+        nlp = build_quadcopter_nlp(sc["x0"][0], sc["xF"][0], 10, sc["Ts"], sc["R"], sc["obs"], variant)
+        assert (nlp.n, nlp.mE, nlp.mI) == (n_exp, 18 * 10 + 29, 5 * 10 + 5)
+        rng = np.random.default_rng(0)
+        z = rng.normal(size=nlp.n) * 0.2
+        z[nlp.lay.oT:nlp.lay.oU] = 1.0; z[nlp.lay.oU:nlp.lay.oL] += 4.0
+        yE = rng.normal(size=nlp.mE); yI = rng.normal(size=nlp.mI)
+        H = nlp.hess(z, yE, yI).toarray(); JE = nlp.JE(z).toarray()
+        gl = lambda zz: nlp.grad(zz) + nlp.JE(zz).T @ yE + nlp.JI(zz).T @ yI
+        for j in rng.choice(nlp.n, 40, replace=False):
+            e = np.zeros(nlp.n); e[j] = 1e-6
+            assert np.abs((nlp.cE(z + e) - nlp.cE(z - e)) / 2e-6 - JE[:, j]).max() < 1e-6
+            assert np.abs((gl(z + e) - gl(z - e)) / 2e-6 - H[:, j]).max() < 2e-5
+
+
+@pytest.mark.parametrize("variant", ["sd", "d"])
+def test_kernel_sources_vs_oracle(variant):
+    import emul
+    N = 20
+    sc = scenarios.quadcopter_batch(2, N, 2)
+    i = 0
+    # first Newton step: identical up to round-off x the 1/dc terminal penalty
+    o = emul.default_opts(); o.max_iter = 1; o.dc = 1e-6
+    r = emul.quad_solve_batch(sc, variant, o)
+    out, res, nlp = solve_quadcopter(sc["x0"][i], sc["xF"][i], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"][i], 1.0, variant,
+                                     ipm_ref.IpmOptions(max_iter=1, dc_value=1e-6))
+    assert np.abs(out[0] - r["xp"][i]).max() < 1e-7 and np.abs(out[1] - r["up"][i]).max() < 1e-7
+    assert np.abs(out[2] - r["ts"][i]).max() < 1e-8 and np.abs(out[5] - r["lp"][i]).max() < 1e-7
+    # converged: same objective and time scale, both KKT points of the reference NLP, verbatim checker passes
+    o = emul.default_opts(); o.max_iter = 3000
+    r = emul.quad_solve_batch(sc, variant, o)
+    out, res, nlp = solve_quadcopter(sc["x0"][i], sc["xF"][i], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"][i], 1.0, variant,
+                                     ipm_ref.IpmOptions(max_iter=3000, linsolve="sparse"))
+    assert r["status"][i] == 1 and res.status == 1
+    e, nlp2 = _cert(sc, i, N, variant, r["xp"][i], r["up"][i], r["ts"][i], r["lp"][i], r["slack"][i])
+    assert e["E0"] < 5e-5
+    assert abs(e["f"] - nlp.f(res.z)) < 1e-4 * abs(e["f"]) and np.abs(out[2] - r["ts"][i]).max() < 1e-5
+    assert checkers.constrSatisfaction(r["xp"][i], r["up"][i], r["ts"][i], sc["x0"][i], sc["xF"][i], sc["Ts"], r["lp"][i], *sc["obs"], sc["R"])
+    if variant == "sd":
+        assert r["slack"][i].sum() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["sd", "d"])
+def test_gpu_quadcopter_config4(variant):
+    import obca_b200
+    from obca_b200 import quadcopter
+    N, B = 100, 16
+    sc = scenarios.quadcopter_batch(B, N, 2)
+    r = quadcopter.quadcopter_solve_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"], 1.0, 1 if variant == "sd" else 0)
+    assert (r["exitflag"] == 1).sum() >= B - 1
+    feas, worst = quadcopter.check_quadcopter_batch(r["xp"], r["up"], r["ts"], sc["x0"], sc["xF"], sc["Ts"], r["lp"], sc["obs"], sc["R"])
+    for i in range(B):
+        ref = checkers.constrSatisfaction(r["xp"][i], r["up"][i], r["ts"][i], sc["x0"][i], sc["xF"][i], sc["Ts"], r["lp"][i], *sc["obs"], sc["R"])
+        assert bool(feas[i]) == ref
+        if r["exitflag"][i] == 1:
+            assert ref
+    i = int(np.argmax(r["exitflag"] == 1))
+    e, _ = _cert(sc, i, N, variant, r["xp"][i], r["up"][i], r["ts"][i], r["lp"][i], r["slack"][i])
+    assert e["E0"] < 1e-4 and e["constr_viol"] < 1e-4
+    # reference-named single-problem call surface (QuadcopterSignedDist.jl:25 / :298)
+    f = obca_b200.QuadcopterSignedDist if variant == "sd" else obca_b200.QuadcopterDist
+    xp, up, tsp, ef, t, lp, status = f(sc["x0"][i][None], sc["xF"][i][None], N, sc["Ts"], sc["R"], *sc["obs"], sc["xWS"][i], np.full((4, N), 0.5), 1)
+    assert xp.shape == (12, N + 1) and up.shape == (4, N) and tsp.shape == (N + 1,) and lp.shape == (30, N + 1) and ef == 1 and status == "Optimal"
+    assert obca_b200.constrSatisfaction(xp, up, tsp, sc["x0"][i][None], sc["xF"][i][None], sc["Ts"], lp, *sc["obs"], sc["R"]) is True
