@@ -93,3 +93,37 @@ function ParkingConstraints(x0, xF, N, Ts, L, ego, XYbounds, nOb, vOb, A, b, x, 
                Int(fixTime), Int(sd), o, feas, C_NULL, C_NULL)
     return rc == 0 ? Int(feas[]) : 0
 end
+
+# ---- quadcopter (QuadcopterNavigation/setupQuadcopter.jl:33-34 includes QuadcopterSignedDist.jl / QuadcopterDist.jl /
+#      constrSatisfaction.jl; include this file instead) ----
+function _quadcopter(signed_dist::Int, x0, xF, N, Ts, R, ob1, ob2, ob3, ob4, ob5, xWS, uWS, timeWS)
+    N = Int(N)
+    ob = hcat(vec(_f64(ob1)), vec(_f64(ob2)), vec(_f64(ob3)), vec(_f64(ob4)), vec(_f64(ob5)))     # 6 x 5
+    xw = _f64(xWS)[1:12, 1:N+1]                          # setvalue(x, xWS)   QuadcopterSignedDist.jl:201 (uWS unused, :202)
+    xp = Matrix{Float64}(undef, 12, N + 1); up = Matrix{Float64}(undef, 4, N); ts = Vector{Float64}(undef, N + 1)
+    lp = Matrix{Float64}(undef, 30, N + 1); sl = Matrix{Float64}(undef, 5, N + 1)
+    exitflag = Ref{Cint}(0); iters = Ref{Cint}(0); kkt = Ref{Cdouble}(0.0); secs = Ref{Cdouble}(0.0)
+    rc = ccall((:obca_quadcopter_solve_batch, LIBOBCA), Cint,
+               (Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ptr{Cvoid},
+                Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cint}, Ref{Cint}, Ref{Cdouble}, Ref{Cdouble}),
+               1, N, vec(_f64(x0)), vec(_f64(xF)), Float64(Ts), Float64(R), ob, xw, Float64(timeWS), signed_dist, C_NULL,
+               xp, up, ts, lp, sl, exitflag, iters, kkt, secs)
+    ef = rc == 0 ? Int(exitflag[]) : 0
+    return xp, up, ts, ef, secs[], lp, (ef >= 1 ? "Optimal" : "Error")          # :298
+end
+QuadcopterSignedDist(x0, xF, N, Ts, R, ob1, ob2, ob3, ob4, ob5, xWS, uWS, timeWS) =
+    _quadcopter(1, x0, xF, N, Ts, R, ob1, ob2, ob3, ob4, ob5, xWS, uWS, timeWS)
+QuadcopterDist(x0, xF, N, Ts, R, ob1, ob2, ob3, ob4, ob5, xWS, uWS, timeWS) =
+    _quadcopter(0, x0, xF, N, Ts, R, ob1, ob2, ob3, ob4, ob5, xWS, uWS, timeWS)
+
+function constrSatisfaction(x, u, timeScale, x0, xF, Ts, lambda, ob1, ob2, ob3, ob4, ob5, R)
+    N = size(x, 2) - 1
+    ob = hcat(vec(_f64(ob1)), vec(_f64(ob2)), vec(_f64(ob3)), vec(_f64(ob4)), vec(_f64(ob5)))
+    feas = Ref{Cint}(0)
+    rc = ccall((:obca_check_quadcopter, LIBOBCA), Cint,
+               (Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble},
+                Cdouble, Ptr{Cvoid}, Ref{Cint}, Ptr{Cdouble}),
+               1, N, _f64(x), _f64(u), vec(_f64(timeScale)), vec(_f64(x0)), vec(_f64(xF)), Float64(Ts), _f64(lambda), ob, Float64(R),
+               C_NULL, feas, C_NULL)
+    return rc == 0 && feas[] == 1
+end

@@ -244,6 +244,7 @@ template <bool SDV>
 __global__ void __launch_bounds__(128, 2)
 k_quad_solve(const __grid_constant__ QuadProblem P, const __grid_constant__ IpmOpts O, const QLay L, const QBatchPtrs bp,
              double* __restrict__ Wall, int* __restrict__ counter) {
+  extern __shared__ double s_kkt[];      // QuadSolver::smem_doubles(N): block-cooperative KKT sweep
   __shared__ ProbState S;
   __shared__ double s_red[4 * 12];
   __shared__ int s_b;
@@ -256,7 +257,7 @@ k_quad_solve(const __grid_constant__ QuadProblem P, const __grid_constant__ IpmO
     const int b = s_b;
     if (b >= bp.B) break;
     QCtx C;
-    C.P = &P; C.O = &O; C.L = L; C.W = W; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+    C.P = &P; C.O = &O; C.L = L; C.W = W; C.red_scratch = s_red; C.tile = s_kkt; C.S = &S;
     C.in.x0 = bp.x0 + 12 * (size_t)b; C.in.xF = bp.xF + 12 * (size_t)b; C.in.xWS = bp.xWS + (size_t)12 * NS * b;
     C.in.timeWS = bp.timeWS;
     QOutputs out;
@@ -449,8 +450,11 @@ template <bool SDV>
 static int launch_quad(DevCtx& c, const QuadProblem& P, const IpmOpts& O, const QBatchPtrs& bp) {
   QLay L = make_qlayout(P);
   if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)QuadSolver<SDV>::smem_doubles(P.N) * sizeof(double);
+  if (smem > 200 * 1024) { set_err("horizon too long for the quadcopter kernel's shared memory"); return OBCA_ERR_UNSUPPORTED; }
+  CK(cudaFuncSetAttribute(k_quad_solve<SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad_solve<SDV>, L.NSP, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad_solve<SDV>, L.NSP, smem));
   if (occ < 1) occ = 1;
   int grid = c.sms * occ;
   if (grid > bp.B) grid = bp.B;
@@ -458,7 +462,7 @@ static int launch_quad(DevCtx& c, const QuadProblem& P, const IpmOpts& O, const 
   int rc = ensure((void**)&c.W, &c.Wbytes, need);
   if (rc) return rc;
   CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
-  k_quad_solve<SDV><<<grid, L.NSP, 0, c.st>>>(P, O, L, bp, c.W, c.counter);
+  k_quad_solve<SDV><<<grid, L.NSP, smem, c.st>>>(P, O, L, bp, c.W, c.counter);
   CK(cudaGetLastError());
   return 0;
 }

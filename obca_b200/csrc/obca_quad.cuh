@@ -489,12 +489,170 @@ struct QuadSolver {
     return 1;
   }
   OBCA_HD static int kkt_host(const QCtx& C) { return kkt_dense(C); }
+  static constexpr int SM_P = 0, SM_p = SM_P + QNSV * QNSV, SM_g = SM_p + QNSV, SM_T = SM_g + QNSV, SM_H = SM_T + QNSV * QNYV,
+                       SM_hv = SM_H + QNYV * QNYV, SM_K = SM_hv + QNYV, SM_L = SM_K + QNU * (QNSV + 1), SM_J = SM_L + 16,
+                       SM_r = SM_J + QD_NJ, SM_s = SM_r + QNX, SM_u = SM_s + QNSV, SM_flag = SM_u + QNU, SM_Kall = SM_flag + 1;
+  static constexpr int KROW = QNU * (QNSV + 1);     // 72 gain entries per stage
+  OBCA_HD static int smem_doubles(int N) { return SM_Kall + N * KROW; }
+  static constexpr bool KKT_BLOCK = true;
+
 #if defined(__CUDA_ARCH__)
-  __device__ static int kkt_solve_warp(const QCtx& C, double*) {
-    int ok = 0;
-    if ((threadIdx.x & 31) == 0) ok = kkt_dense(C);
-    return __shfl_sync(0xffffffffu, ok, 0);
+  // -------------------------------------------------------------------------------------------------
+  // Device version: the whole CTA cooperates on every stage of the sweep through shared memory (entry-parallel
+  // T = P Phi, H = Q + Phi' T, gains, value-function update; the 4x4 Cholesky is done by thread 0).  Same
+  // arithmetic as kkt_dense().  Shared layout (doubles), QSM_TOTAL in all:
+  //   P 17x17 | p 17 | g 17 | T 17x21 | H 21x21 | hv 21 | K 4x18 | Lc 16 | Jv 66 | r12 12 | s 17 | u 4 | flag 1 | Kall N x 72
+  // -------------------------------------------------------------------------------------------------
+  __device__ static int kkt_solve_block(const QCtx& C) {
+    const QuadProblem& Pp = *C.P;
+    ProbState& S = *C.S;
+    const int N = Pp.N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* sm = C.tile;
+    double *P = sm + SM_P, *p = sm + SM_p, *g = sm + SM_g, *T = sm + SM_T, *H = sm + SM_H, *hv = sm + SM_hv, *K = sm + SM_K,
+           *Lc = sm + SM_L, *Jv = sm + SM_J, *r12 = sm + SM_r, *sv = sm + SM_s, *uv = sm + SM_u, *Kall = sm + SM_Kall;
+    static constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
+    static constexpr int JC[QD_NJ] = OBCA_QD_J_COL;
+    static constexpr int RPT[QNX + 1] = OBCA_QD_ROW_PTR;
+    static constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
+    static constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
+    const double rho = 1.0 / C.O->dc;
+    for (int e = tid; e < QNSV * QNSV; e += nt) P[e] = (e / QNSV == e % QNSV && e / QNSV < QNX) ? rho : 0.0;
+    for (int a = tid; a < QNSV; a += nt) p[a] = a < QNX ? -QA(PI, a, N - 1) : 0.0;
+    if (tid == 0) sm[SM_flag] = 1.0;
+    __syncthreads();
+    for (int k = N - 1; k >= 0; --k) {
+      // rows 0..11 of P_{k+1}, p_{k+1} for the multiplier recovery; stage data into shared memory
+      for (int e = tid; e < QNX * QNSV; e += nt) QA(RP, e, k + 1) = P[e];
+      for (int i = tid; i < QNX; i += nt) { QA(RP, QNX * QNSV + i, k + 1) = p[i]; r12[i] = QA(R12, i, k); }
+      for (int e = tid; e < QD_NJ; e += nt) Jv[e] = QA(JV, e, k);
+      __syncthreads();
+      // g = p + P r~ ;  T = P Phi
+      for (int a = tid; a < QNSV; a += nt) {
+        double acc = p[a];
+        for (int l = 0; l < QNX; ++l) acc += P[a * QNSV + l] * r12[l];
+        g[a] = acc;
+      }
+      for (int e = tid; e < QNSV * QNYV; e += nt) {
+        const int a = e / QNYV, c = e - a * QNYV;
+        double acc = 0.0;
+        for (int q = CPT[c]; q < CPT[c + 1]; ++q) { const int z = CIX[q]; acc += P[a * QNSV + JR[z]] * Jv[z]; }
+        if (c >= QIU) acc += P[a * QNSV + QIW + (c - QIU)];
+        if (c == QIT) acc += P[a * QNSV + QIT];
+        T[e] = acc;
+      }
+      __syncthreads();
+      // H = Q + Phi' T ; hv = q + Phi' g
+      for (int e = tid; e < QNYV * QNYV; e += nt) {
+        const int c1 = e / QNYV, c2 = e - c1 * QNYV;
+        double acc = QA(QS, sym_idx_any<QNYV>(c1, c2), k);
+        for (int q = CPT[c1]; q < CPT[c1 + 1]; ++q) { const int z = CIX[q]; acc += Jv[z] * T[JR[z] * QNYV + c2]; }
+        if (c1 >= QIU) acc += T[(QIW + c1 - QIU) * QNYV + c2];
+        if (c1 == QIT) acc += T[QIT * QNYV + c2];
+        H[e] = acc;
+      }
+      for (int c = tid; c < QNYV; c += nt) {
+        double acc = QA(qs, c, k);
+        for (int q = CPT[c]; q < CPT[c + 1]; ++q) { const int z = CIX[q]; acc += Jv[z] * g[JR[z]]; }
+        if (c >= QIU) acc += g[QIW + c - QIU];
+        if (c == QIT) acc += g[QIT];
+        hv[c] = acc;
+      }
+      __syncthreads();
+      // Cholesky of Huu (4x4)
+      if (tid == 0) {
+        int ok = 1;
+        for (int a = 0; a < QNU; ++a)
+          for (int b = 0; b <= a; ++b) {
+            double acc = H[(QIU + a) * QNYV + QIU + b];
+            for (int l = 0; l < b; ++l) acc -= Lc[a * 4 + l] * Lc[b * 4 + l];
+            if (a == b) { if (!(acc > 0.0)) { ok = 0; acc = 1e300; } Lc[a * 4 + a] = sqrt(acc); }
+            else Lc[a * 4 + b] = acc / Lc[b * 4 + b];
+          }
+        if (!ok) sm[SM_flag] = 0.0;
+      }
+      __syncthreads();
+      if (sm[SM_flag] == 0.0) return 0;
+      // K = -Huu^{-1} [Hus | hu]   (column c = 0..17, one thread per column)
+      for (int c = tid; c <= QNSV; c += nt) {
+        double y4[QNU], k4[QNU];
+        for (int a = 0; a < QNU; ++a) {
+          double acc = c < QNSV ? H[(QIU + a) * QNYV + c] : hv[QIU + a];
+          for (int l = 0; l < a; ++l) acc -= Lc[a * 4 + l] * y4[l];
+          y4[a] = acc / Lc[a * 4 + a];
+        }
+        for (int a = QNU - 1; a >= 0; --a) {
+          double acc = y4[a];
+          for (int l = a + 1; l < QNU; ++l) acc -= Lc[l * 4 + a] * k4[l];
+          k4[a] = acc / Lc[a * 4 + a];
+        }
+        for (int a = 0; a < QNU; ++a) { K[a * (QNSV + 1) + c] = -k4[a]; Kall[k * KROW + a * (QNSV + 1) + c] = -k4[a]; }
+      }
+      __syncthreads();
+      // value function of stage k
+      for (int e = tid; e < QNSV * QNSV; e += nt) {
+        const int a = e / QNSV, b = e - a * QNSV;
+        double v = H[a * QNYV + b];
+        for (int l = 0; l < QNU; ++l) v += H[a * QNYV + QIU + l] * K[l * (QNSV + 1) + b];
+        P[e] = v;
+      }
+      for (int a = tid; a < QNSV; a += nt) {
+        double acc = hv[a];
+        for (int l = 0; l < QNU; ++l) acc += H[a * QNYV + QIU + l] * K[l * (QNSV + 1) + QNSV];
+        p[a] = acc;
+      }
+      __syncthreads();
+      // symmetrise (the entry-parallel update computes P(a,b) and P(b,a) separately)
+      for (int e = tid; e < QNSV * QNSV; e += nt) {
+        const int a = e / QNSV, b = e - a * QNSV;
+        if (a < b) { const double v = 0.5 * (P[e] + P[b * QNSV + a]); T[e] = v; }
+      }
+      __syncthreads();
+      for (int e = tid; e < QNSV * QNSV; e += nt) {
+        const int a = e / QNSV, b = e - a * QNSV;
+        if (a < b) { P[e] = T[e]; P[b * QNSV + a] = T[e]; }
+      }
+      __syncthreads();
+    }
+    // root
+    if (tid == 0) {
+      const double ptt = P[QIT * QNSV + QIT];
+      if (!(ptt > 0.0)) sm[SM_flag] = 0.0;
+      else S.dt = -p[QIT] / ptt;
+    }
+    __syncthreads();
+    if (sm[SM_flag] == 0.0) return 0;
+    // forward roll-out (2 barriers per stage)
+    for (int a = tid; a < QNSV; a += nt) sv[a] = (a == QIT) ? S.dt : 0.0;
+    __syncthreads();
+    for (int k = 0; k < N; ++k) {
+      if (tid < QNU) {
+        const double* kr = Kall + k * KROW + tid * (QNSV + 1);
+        double acc = kr[QNSV];
+        for (int c = 0; c < QNSV; ++c) acc += kr[c] * sv[c];
+        uv[tid] = acc;
+        QA(dU, tid, k) = acc;
+      }
+      for (int e = tid; e < QD_NJ; e += nt) Jv[e] = QA(JV, e, k);
+      for (int i = tid; i < QNX; i += nt) r12[i] = QA(R12, i, k);
+      __syncthreads();
+      double snv = 0.0;
+      if (tid < QNX) {
+        snv = r12[tid];
+        for (int q = RPT[tid]; q < RPT[tid + 1]; ++q) { const int c = JC[q]; snv += Jv[q] * (c < QNSV ? sv[c] : uv[c - QIU]); }
+        if (k + 1 < N) QA(dX, tid, k + 1) = snv; else S.eNq[tid] = snv;
+      }
+      __syncthreads();
+      if (tid < QNX) sv[tid] = snv;
+      else if (tid < QNX + QNU) sv[tid] = uv[tid - QNX];
+      __syncthreads();
+    }
+    for (int i = tid; i < QNX; i += nt) { QA(dX, i, 0) = 0.0; QA(dX, i, N) = 0.0; }
+    for (int a = tid; a < QNU; a += nt) QA(dU, a, N) = 0.0;
+    __syncthreads();
+    return 1;
   }
+  __device__ static int kkt_solve_warp(const QCtx&, double*) { return 0; }   // unused (KKT_BLOCK)
 #endif
 
   // ---- K4a ----

@@ -1194,8 +1194,12 @@ struct ParkSolver {
     const double mI = N + (double)P.nOb * NS + (P.signed_dist ? 0.0 : (double)P.nOb * NS);
     n_bmult = nb; n_mult = nb + mE + mI;
   }
-  // ---- adapters used by the generic interior-point driver (obca_ipm.cuh) ----
+  // ---- adapters used by the generic interior-point driver (IpmDriver below) ----
   typedef PkCtx Ctx;
+  static constexpr bool KKT_BLOCK = false;   // the KKT sweep is run by warp 0 (kkt_solve_warp)
+#if defined(__CUDA_ARCH__)
+  __device__ static int kkt_solve_block(const PkCtx&) { return 0; }
+#endif
   OBCA_HD static int n_stages(const PkCtx& C) { return C.P->N + 1; }
   OBCA_HD static bool fixed_time(const PkCtx& C) { return C.P->fix_time != 0; }
   OBCA_HD static void mult_counts(const PkCtx& C, double& n_mult, double& n_bmult) { mult_counts(*C.P, n_mult, n_bmult); }
@@ -1321,7 +1325,13 @@ struct IpmDriver {
       bool tried0 = false;
       for (;;) {
 #if defined(__CUDA_ARCH__)
-        if (S.ok && threadIdx.x < 32) {
+        if (M::KKT_BLOCK) {
+          if (S.ok) {                                // uniform: S.ok was published before the last barrier
+            const int ok = M::kkt_solve_block(C);
+            __syncthreads();
+            if (threadIdx.x == 0) S.ok = ok;
+          }
+        } else if (S.ok && threadIdx.x < 32) {
           const int ok = M::kkt_solve_warp(C, C.tile);
           __syncwarp();
           if (threadIdx.x == 0) S.ok = ok;
