@@ -88,6 +88,19 @@ OBCA_HD double dmax(double a, double b) { return a > b ? a : b; }
 OBCA_HD double dmin_(double a, double b) { return a < b ? a : b; }
 OBCA_HD double dabs(double a) { return a < 0 ? -a : a; }
 
+// sum of log(gap) over many gaps with few log() calls: products of up to 6 gaps (gaps lie in ~[1e-12, 1e2], so a product
+// stays far inside the double range); FP64 log is ~50 instructions and the solver kernel is issue bound.
+struct LogAcc {
+  double prod, sum;
+  int n;
+  OBCA_HD LogAcc() : prod(1.0), sum(0.0), n(0) {}
+  OBCA_HD void add(double g) {
+    prod *= g;
+    if (++n == 6) { sum += log(prod); prod = 1.0; n = 0; }
+  }
+  OBCA_HD double total() { if (n) { sum += log(prod); prod = 1.0; n = 0; } return sum; }
+};
+
 // packed upper-triangular index for an n x n symmetric matrix, i <= j
 template <int N>
 OBCA_HD constexpr int sym_idx(int i, int j) { return i * N - (i * (i - 1)) / 2 + (j - i); }

@@ -209,6 +209,7 @@ struct QuadSolver {
     const bool has_u = k < N;
     double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0, rz_t = 0.0;
     int ok = 1;
+    LogAcc lacc;
     double x[QNX], rzx[QNX];
     for (int i = 0; i < QNX; ++i) { x[i] = QA(X, i, k); rzx[i] = 0.0; }
     if (do_asm && has_u) {
@@ -233,7 +234,7 @@ struct QuadSolver {
         if (do_err) {
           cmax = dmax(cmax, dmax(al * zl, au * zu)); cmin = dmin_(cmin, dmin_(al * zl, au * zu));
           sum_z += zl + zu;
-          phi -= mu_b * (log(al) + log(au));
+          lacc.add(al); lacc.add(au);
         }
       }
     }
@@ -261,7 +262,7 @@ struct QuadSolver {
         if (do_err) {
           cmax = dmax(cmax, dmax(al * zl, au * zu)); cmin = dmin_(cmin, dmin_(al * zl, au * zu));
           sum_z += zl + zu;
-          phi -= mu_b * (log(al) + log(au));
+          lacc.add(al); lacc.add(au);
         }
       }
       double f[QNX], Jv[QD_NJ], Hv[QD_NH];
@@ -304,7 +305,7 @@ struct QuadSolver {
           const double cp = Q.lam[i] * Q.zlam[i];
           cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
           sum_z += Q.zlam[i];
-          phi -= mu_b * log(Q.lam[i]);
+          lacc.add(Q.lam[i]);
           fobj += QUAD_REG2 * Q.lam[i] * Q.lam[i];
         }
         if (SDV) {
@@ -312,7 +313,7 @@ struct QuadSolver {
           const double cp = Q.sl * Q.zsl;
           cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
           sum_z += Q.zsl;
-          phi -= mu_b * log(Q.sl);
+          lacc.add(Q.sl);
           fobj += 1e2 * Q.sl + 1e3 * Q.sl * Q.sl;
         }
         e_pr = dmax(e_pr, dmax(dabs(G.cn), dabs(G.cd)));
@@ -320,7 +321,7 @@ struct QuadSolver {
         sum_y += dabs(Q.yn) + Q.vd; sum_z += Q.vd;
         const double cp = (Q.sd - P.R) * Q.vd;
         cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-        phi -= mu_b * log(Q.sd - P.R);
+        lacc.add(Q.sd - P.R);
       }
       if (do_asm) {
         const int piv = qobs_choose_pivot(G);
@@ -349,6 +350,7 @@ struct QuadSolver {
         phi -= m * mu_b * (log(gl) + log(gu));
       }
     }
+    if (do_err) phi -= mu_b * lacc.total();
     if (do_err && free_x)
       for (int i = 0; i < QNX; ++i) e_dual = dmax(e_dual, dabs(rzx[i]));
     out.e_dual = e_dual; out.e_pr = e_pr; out.cmax = cmax; out.cmin = cmin; out.sy = sum_y; out.sz = sum_z;
@@ -752,6 +754,7 @@ struct QuadSolver {
     const double t = S.t + alpha * S.dt;
     double th = 0.0, phi = 0.0;
     bool bad = false;
+    LogAcc lacc;
     double x[QNX];
     for (int i = 0; i < QNX; ++i) x[i] = QA(X, i, k) + alpha * QA(dX, i, k);
     phi += QUAD_REG3 * (x[9] * x[9] + x[10] * x[10] + x[11] * x[11]);
@@ -759,7 +762,7 @@ struct QuadSolver {
       for (int i = 0; i < QNX; ++i) {
         const double al = x[i] - P.xlo[i], au = P.xhi[i] - x[i];
         bad |= !(al > 0.0) || !(au > 0.0);
-        phi -= mu_b * (log(al) + log(au));
+        lacc.add(al); lacc.add(au);
       }
     if (k < N) {
       double u[QNU], c0[3] = {C.in.x0[9], C.in.x0[10], C.in.x0[11]};
@@ -770,7 +773,7 @@ struct QuadSolver {
         phi += 1e-3 * eh * eh + 1e-2 * ed * ed;
         const double al = u[j] - 1.2, au = 7.8 - u[j];
         bad |= !(al > 0.0) || !(au > 0.0);
-        phi -= mu_b * (log(al) + log(au));
+        lacc.add(al); lacc.add(au);
       }
       double f[QNX];
       quad_dyn_f(x, u, t, P.Ts, c0, f);
@@ -787,12 +790,12 @@ struct QuadSolver {
       th += dabs(G.cn) + dabs(G.cd);
       for (int i = 0; i < 6; ++i) {
         bad |= !(Q.lam[i] > 0.0);
-        phi += QUAD_REG2 * Q.lam[i] * Q.lam[i] - mu_b * log(Q.lam[i]);
+        phi += QUAD_REG2 * Q.lam[i] * Q.lam[i]; lacc.add(Q.lam[i]);
       }
-      if (SDV) { bad |= !(Q.sl > 0.0); phi += 1e2 * Q.sl + 1e3 * Q.sl * Q.sl - mu_b * log(Q.sl); }
+      if (SDV) { bad |= !(Q.sl > 0.0); phi += 1e2 * Q.sl + 1e3 * Q.sl * Q.sl; lacc.add(Q.sl); }
       const double gap = Q.sd - P.R;
       bad |= !(gap > 0.0);
-      phi -= mu_b * log(gap);
+      lacc.add(gap);
     }
     if (k == 0) {
       const double m = (double)(N + 1);
@@ -800,6 +803,7 @@ struct QuadSolver {
       bad |= !(gl > 0.0) || !(gu > 0.0);
       phi += m * (0.25 * t + 5.0 * t * t) - m * mu_b * (log(gl) + log(gu));
     }
+    phi -= mu_b * lacc.total();
     out.th = th;
     out.phi = bad ? 1e300 : phi;
   }

@@ -347,6 +347,7 @@ struct ParkSolver {
     double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0;
     double rz_t = 0.0;
     int ok = 1;
+    LogAcc lacc;   // barrier terms: phi -= mu * sum(log gap)
     // Lagrangian gradient rows of the pose
     double rzX = 0.0, rzY = 0.0, rzP = 0.0, rzV = 0.0;
 
@@ -375,7 +376,7 @@ struct ParkSolver {
 #pragma unroll
           for (int i = 0; i < 6; ++i) { cmax = dmax(cmax, c6[i]); cmin = dmin_(cmin, c6[i]); }
           sum_z += zXl + zXu + zYl + zYu + zVl + zVu;
-          phi -= mu_b * (log(aXl) + log(aXu) + log(aYl) + log(aYu) + log(aVl) + log(aVu));
+          lacc.add(aXl); lacc.add(aXu); lacc.add(aYl); lacc.add(aYu); lacc.add(aVl); lacc.add(aVu);
         }
       }
     }
@@ -475,7 +476,7 @@ struct ParkSolver {
         const double c6[6] = {aDl * zDl, aDu * zDu, aAl * zAl, aAu * zAu, gl * rvl, gu * rvu};
 #pragma unroll
         for (int i = 0; i < 6; ++i) { cmax = dmax(cmax, c6[i]); cmin = dmin_(cmin, c6[i]); }
-        phi -= mu_b * (log(aDl) + log(aDu) + log(aAl) + log(aAu) + log(gl) + log(gu));
+        lacc.add(aDl); lacc.add(aDu); lacc.add(aAl); lacc.add(aAu); lacc.add(gl); lacc.add(gu);
       }
     }
     // ---- (C) obstacle blocks ----
@@ -495,7 +496,7 @@ struct ParkSolver {
             const double cp = Qv.lam[i] * Qv.zlam[i];
             cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
             sum_z += Qv.zlam[i];
-            phi -= mu_b * log(Qv.lam[i]);
+            lacc.add(Qv.lam[i]);
           }
         }
 #pragma unroll
@@ -504,7 +505,7 @@ struct ParkSolver {
           const double cp = Qv.mu[m] * Qv.zmu[m];
           cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
           sum_z += Qv.zmu[m];
-          phi -= mu_b * log(Qv.mu[m]);
+          lacc.add(Qv.mu[m]);
         }
         if (SDV) { e_dual = dmax(e_dual, dabs(rs_)); fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl; }
         e_pr = dmax(e_pr, dmax(dmax(dabs(G.cn), dabs(G.cd)), dmax(dabs(G.cr1), dabs(G.cr2))));
@@ -514,12 +515,12 @@ struct ParkSolver {
         {
           const double cp = (Qv.sd - P.dmin) * Qv.vd;
           cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-          phi -= mu_b * log(Qv.sd - P.dmin);
+          lacc.add(Qv.sd - P.dmin);
         }
         if (!SDV) {
           const double cp = (1.0 - Qv.sn) * Qv.vn;
           cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-          phi -= mu_b * log(1.0 - Qv.sn);
+          lacc.add(1.0 - Qv.sn);
         }
       } else if (SDV) {
         fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
@@ -554,6 +555,7 @@ struct ParkSolver {
         phi -= m * mu_b * (log(gl) + log(gu));
       }
     }
+    if (do_err) phi -= mu_b * lacc.total();
     if (do_err && pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
     out.e_dual = e_dual; out.e_pr = e_pr; out.cmax = cmax; out.cmin = cmin; out.sy = sum_y; out.sz = sum_z;
     out.th = th; out.phi = phi + fobj; out.rt = rz_t; out.f = fobj; out.ok = ok;
@@ -1006,13 +1008,14 @@ struct ParkSolver {
     sincos(ps, &sn_, &cs_);
     double th = 0.0, phi = 0.0;
     bool bad = false;
+    LogAcc lacc;
     {
       const double ex = X - C.in.rx[k], ey = Y - C.in.ry[k], ep = ps - C.in.ryaw[k];
       phi += 1e-4 * v * v + 1e-3 * ex * ex + 1e-3 * ey * ey + P.w_yaw * ep * ep;
       if (pose_free) {
         const double g6[6] = {X - P.xyb[0], P.xyb[1] - X, Y - P.xyb[2], P.xyb[3] - Y, v + 1.0, 2.0 - v};
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); phi -= mu_b * log(g6[i]); }
+        for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); lacc.add(g6[i]); }
       }
     }
     if (k < N) {
@@ -1025,7 +1028,7 @@ struct ParkSolver {
       const double rs = WA(RS, k) + alpha * WA(dRS, k);
       const double g6[6] = {de + 0.6, 0.6 - de, ac + 0.4, 0.4 - ac, rs + 0.6, 0.6 - rs};
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); phi -= mu_b * log(g6[i]); }
+      for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); lacc.add(g6[i]); }
       th += dabs((wd - de) * ih - rs);
       DynOut dyn;
       dyn_eval(P, X, Y, ps, v, de, ac, t, dyn, nullptr, nullptr);
@@ -1046,13 +1049,13 @@ struct ParkSolver {
         const bool on = i < R.v;
         Qv.lam[i] = on ? WV(LAM, P.voff[j] + i, k) + alpha * WV(dLAM, P.voff[j] + i, k) : 1.0;
         Qv.zlam[i] = 0.0;
-        if (on) { bad |= !(Qv.lam[i] > 0.0); phi -= mu_b * log(Qv.lam[i]); }
+        if (on) { bad |= !(Qv.lam[i] > 0.0); lacc.add(Qv.lam[i]); }
       }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         Qv.mu[m] = WV(MU, 4 * j + m, k) + alpha * WV(dMU, 4 * j + m, k);
         Qv.zmu[m] = 0.0;
-        bad |= !(Qv.mu[m] > 0.0); phi -= mu_b * log(Qv.mu[m]);
+        bad |= !(Qv.mu[m] > 0.0); lacc.add(Qv.mu[m]);
       }
       Qv.sl = SDV ? WV(SL, j, k) + alpha * WV(dSL, j, k) : 0.0;
       Qv.sd = WV(SD, j, k) + alpha * WV(dSD, j, k);
@@ -1061,8 +1064,8 @@ struct ParkSolver {
       obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
       th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
       if (SDV) phi += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
-      { const double gap = Qv.sd - P.dmin; bad |= !(gap > 0.0); phi -= mu_b * log(gap); }
-      if (!SDV) { const double gap = 1.0 - Qv.sn; bad |= !(gap > 0.0); phi -= mu_b * log(gap); }
+      { const double gap = Qv.sd - P.dmin; bad |= !(gap > 0.0); lacc.add(gap); }
+      if (!SDV) { const double gap = 1.0 - Qv.sn; bad |= !(gap > 0.0); lacc.add(gap); }
     }
     if (k == 0 && !fix) {
       const double m = (double)(N + 1);
@@ -1070,6 +1073,7 @@ struct ParkSolver {
       bad |= !(gl > 0.0) || !(gu > 0.0);
       phi += m * (0.5 * t + t * t) - m * mu_b * (log(gl) + log(gu));
     }
+    phi -= mu_b * lacc.total();
     out.th = th;
     out.phi = bad ? 1e300 : phi;
   }
