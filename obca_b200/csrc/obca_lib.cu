@@ -10,6 +10,7 @@
 // There is NO CPU fallback: every compute entry point returns OBCA_ERR_NO_DEVICE without a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <string>
@@ -20,22 +21,13 @@
 #include "obca_dualws.cuh"
 #include "obca_eval.cuh"
 #include "obca_host.h"
+#include "obca_phased.cuh"
 
 using namespace obca;
 
 // ---------------------------------------------------------------------------------------------------------
 // device-side batch description
 // ---------------------------------------------------------------------------------------------------------
-struct BatchPtrs {
-  const double *x0, *xF, *rx, *ry, *ryaw, *xWS, *uWS, *lWS, *nWS;
-  double *xp, *up, *ts, *lp, *np, *sl, *duals;
-  int *exitflag, *iters;
-  double* kkt_err;
-  int B;
-  int retry;
-  unsigned long long* prof;   // optional: 8 per-phase cycle counters summed over the batch (device pointer)
-};
-
 #ifndef OBCA_MIN_BLOCKS
 #define OBCA_MIN_BLOCKS 3
 #endif
@@ -58,7 +50,7 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
     const int b = s_b;
     if (b >= bp.B) break;
     PkCtx C;
-    C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = s_ric; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
+    C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
     C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
     C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
     C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
@@ -331,6 +323,14 @@ struct DevCtx {
   unsigned long long* prof = nullptr;
   unsigned long long prof_host[8] = {0};
   char* stage = nullptr; size_t stage_bytes = 0;   // device staging for the host-pointer API
+  // phase-split driver (obca_phased.cuh)
+  double* slots = nullptr; size_t slots_bytes = 0;  // stage slots of every problem, B x (N+1) x GSTRIDE
+  char* pstate = nullptr; size_t pstate_bytes = 0;  // ProbState per problem
+  int* act = nullptr; size_t act_bytes = 0;         // two active lists
+  int* ncnt = nullptr;                              // device: n[0], n[1] (active counts), [2] tail work counter
+  int* h_n = nullptr;                               // pinned ring of active counts read back per round
+  cudaEvent_t evr[16] = {nullptr};
+  int last_rounds = 0, last_tail = 0;
   std::mutex mu;
 };
 static DevCtx g_dev[64];
@@ -349,6 +349,9 @@ static int get_ctx(int dev, DevCtx** out) {
     c.sms = pr.multiProcessorCount;
     CK(cudaMalloc(&c.counter, sizeof(int)));
     CK(cudaMalloc(&c.prof, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c.ncnt, 4 * sizeof(int)));
+    CK(cudaMallocHost(&c.h_n, 16 * sizeof(int)));
+    for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&c.evr[i], cudaEventDisableTiming));
     c.init = true;
   }
   *out = &c;
@@ -414,8 +417,89 @@ static int launch_solve(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// phase-split driver (obca_phased.cuh): rounds of [K_A, K_B, K_C] over the active problems, then the tail kernel
+// ---------------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int VM, bool SDV>
+static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const BatchPtrs& bp, int mode) {
+  PkLay L = make_layout(P, LocalDims<VM, SDV>::NFAC);
+  if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
+  const int B = bp.B, NS = P.N + 1;
+  const size_t smem = (size_t)NS * RSTRIDE * sizeof(double);
+  CK(cudaFuncSetAttribute(k_pk_phaseA<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_pk_tail<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pk_tail<VM, SDV>, L.NSP, smem));
+  if (occ < 1) occ = 1;
+  const int tail_cap = c.sms * occ;
+  int rc = ensure((void**)&c.W, &c.Wbytes, (size_t)B * L.total * L.NSP * sizeof(double));
+  if (rc) return rc;
+  rc = ensure((void**)&c.pstate, &c.pstate_bytes, (size_t)B * sizeof(ProbState));
+  if (rc) return rc;
+  ProbState* Sg = (ProbState*)c.pstate;
+  cudaStream_t st = c.st;
+  // mode 1: tail kernel only; mode 2: rounds until the active set fits one wave of the tail kernel; auto: by batch size
+  const int thresh = env_int("OBCA_TAIL_THRESH", tail_cap);
+  const bool rounds = mode == 2 || (mode == 0 && B > 2 * tail_cap);
+  c.last_rounds = 0; c.last_tail = B;
+  int h_init[4] = {B, 0, 0, 0};
+  CK(cudaMemcpyAsync(c.ncnt, h_init, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!rounds) {
+    const int grid = B < tail_cap ? B : tail_cap;
+    k_pk_tail<VM, SDV><<<grid, L.NSP, smem, st>>>(P, O, L, bp, c.W, Sg, nullptr, c.ncnt, c.ncnt + 2, 1);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  rc = ensure((void**)&c.slots, &c.slots_bytes, (size_t)B * NS * GSTRIDE * sizeof(double));
+  if (rc) return rc;
+  rc = ensure((void**)&c.act, &c.act_bytes, 2 * (size_t)B * sizeof(int));
+  if (rc) return rc;
+  int* act[2] = {c.act, c.act + B};
+  int cur = 0, fresh = 1, n_bound = B, done_r = 0, r = 0;
+  const int max_rounds = 8 * (O.max_iter + 8);
+  for (; r < max_rounds; ++r) {
+    CK(cudaMemsetAsync(c.ncnt + (1 - cur), 0, sizeof(int), st));
+    k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[cur], c.ncnt + cur, act[1 - cur],
+                                                      c.ncnt + (1 - cur), fresh);
+    k_pk_sweep<VM, SDV><<<(n_bound + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
+                                                                                              c.ncnt + (1 - cur));
+    k_pk_phaseC<VM, SDV><<<n_bound, L.NSP, 0, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[1 - cur], c.ncnt + (1 - cur));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c.h_n + (r & 15), c.ncnt + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c.evr[r & 15], st));
+    cur = 1 - cur; fresh = 0;
+    // the active set only shrinks: the count of any completed round bounds every later round
+    if (r - done_r >= 8) CK(cudaEventSynchronize(c.evr[done_r & 15]));
+    while (done_r <= r && cudaEventQuery(c.evr[done_r & 15]) == cudaSuccess) { n_bound = c.h_n[done_r & 15]; ++done_r; }
+    if (n_bound <= thresh) {
+      CK(cudaStreamSynchronize(st));
+      n_bound = c.h_n[r & 15];
+      ++r;
+      break;
+    }
+  }
+  c.last_rounds = r; c.last_tail = n_bound;
+  if (n_bound > 0) {
+    const int grid = n_bound < tail_cap ? n_bound : tail_cap;
+    k_pk_tail<VM, SDV><<<grid, L.NSP, smem, st>>>(P, O, L, bp, c.W, Sg, act[cur], c.ncnt + cur, c.ncnt + 2, 0);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
 static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, BatchPtrs bp, double* seconds) {
   const int vm = max_vob(P) <= 2 ? 2 : 4;
+  {  // problem, options and workspace layout -> __constant__ memory (stream-ordered with the kernels below)
+    const PkLay Lc = make_layout(P, nfac_for(P));
+    CK(cudaMemcpyToSymbolAsync(c_pkP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, c.st));
+    CK(cudaMemcpyToSymbolAsync(c_pkO, &O, sizeof(O), 0, cudaMemcpyHostToDevice, c.st));
+    CK(cudaMemcpyToSymbolAsync(c_pkL, &Lc, sizeof(Lc), 0, cudaMemcpyHostToDevice, c.st));
+  }
   CK(cudaMemsetAsync(c.prof, 0, 8 * sizeof(unsigned long long), c.st));
   bp.prof = c.prof;
   int rc;
@@ -423,8 +507,16 @@ static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, Bat
   if (!(P.signed_dist && vm == 2)) { set_err("fast build: only <2,true>"); return OBCA_ERR_UNSUPPORTED; }
   rc = launch_solve<2, true>(c, P, O, bp);
 #else
-  if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, bp) : launch_solve<4, true>(c, P, O, bp);
-  else rc = vm == 2 ? launch_solve<2, false>(c, P, O, bp) : launch_solve<4, false>(c, P, O, bp);
+  // OBCA_MODE: 0 auto (phase-split rounds for large batches, persistent tail kernel for small ones), 1 tail kernel only,
+  // 2 rounds always, 3 the monolithic persistent kernel k_parking_solve (kept as the cross-check of the phase split)
+  const int mode = env_int("OBCA_MODE", 0);
+  if (mode == 3) {
+    if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, bp) : launch_solve<4, true>(c, P, O, bp);
+    else rc = vm == 2 ? launch_solve<2, false>(c, P, O, bp) : launch_solve<4, false>(c, P, O, bp);
+  } else {
+    if (P.signed_dist) rc = vm == 2 ? launch_phased<2, true>(c, P, O, bp, mode) : launch_phased<4, true>(c, P, O, bp, mode);
+    else rc = vm == 2 ? launch_phased<2, false>(c, P, O, bp, mode) : launch_phased<4, false>(c, P, O, bp, mode);
+  }
 #endif
   if (rc) return rc;
   CK(cudaEventRecord(c.ev1, c.st));
@@ -461,6 +553,7 @@ static int launch_quad(DevCtx& c, const QuadProblem& P, const IpmOpts& O, const 
   const size_t need = (size_t)grid * L.total * L.NSP * sizeof(double);
   int rc = ensure((void**)&c.W, &c.Wbytes, need);
   if (rc) return rc;
+  CK(cudaMemcpyToSymbolAsync(c_pkO, &O, sizeof(O), 0, cudaMemcpyHostToDevice, c.st));   // IpmDriver reads the options here
   CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
   k_quad_solve<SDV><<<grid, L.NSP, smem, c.st>>>(P, O, L, bp, c.W, c.counter);
   CK(cudaGetLastError());

@@ -34,6 +34,20 @@
 
 namespace obca {
 
+// Problem description, options and workspace layout as seen by the per-stage functions.  On the device they live in
+// __constant__ memory (set by the host before every launch, stream-ordered): every workspace access WA(name, k) then
+// takes its array offset as an immediate constant-bank operand instead of a load from the context struct in local
+// memory followed by a dependent address computation.  The host emulation reads them through the context.
+#if defined(__CUDA_ARCH__)
+#define CTX_P(C) c_pkP
+#define CTX_O(C) c_pkO
+#define CTX_L(C) c_pkL
+#else
+#define CTX_P(C) (*(C).P)
+#define CTX_O(C) (*(C).O)
+#define CTX_L(C) ((C).L)
+#endif
+
 // ---- per-stage partial results that are reduced over the stages of one problem ----
 struct EvalPart {   // KKT-error / merit pieces
   double e_dual, e_pr, cmax, cmin, sy, sz, th, phi, rt, f;
@@ -106,6 +120,12 @@ struct PkLay {
   int total;
 };
 
+#if defined(__CUDACC__)
+__constant__ ParkProblem c_pkP;
+__constant__ IpmOpts c_pkO;
+__constant__ PkLay c_pkL;
+#endif
+
 inline PkLay make_layout(const ParkProblem& P, int nfac) {
   PkLay L;
   const int NS = P.N + 1;
@@ -160,6 +180,12 @@ struct ProbState {
   int n_kick;     // barrier kicks after line-search failures
   long long prof[8];   // device cycle counters per phase: eval, kkt, recover, merit, update, serial, n_merit, n_eval
   long long tmark;
+  // state machine of the phase-split driver (obca_phased.cuh): where the solve of this problem stands between kernels
+  int phase;        // PH_* below
+  int it;           // iteration counter of the current attempt (the `it` of IpmDriver::solve)
+  int attempt;      // 0: from the warm start, 1: the reference's second solve(m) from the last iterate
+  int first;        // theta_max / theta_min not yet initialised for this attempt
+  int iters_total;  // iterations of the finished attempts
 };
 
 struct PkInputs {
@@ -193,15 +219,19 @@ struct PkCtx {
   PkLay L;
   double* W;
   double* ric;     // (N+1) x RSTRIDE slots
+  const double* pp;  // where recover_stage finds rows 0..3 of P_{k+1} / p_{k+1}: slot base + stride (doubles).  The
+  int pps;           // persistent kernel and the emulation keep them in the stage slots (pp = ric, pps = RSTRIDE);
+                     // the phase-split driver reads them from the global slot array written by the sweep kernel.
   void* red_scratch;   // device: shared-memory scratch of block_reduce
   double* tile;        // device: 7*9+7 doubles of shared memory for the warp-cooperative KKT sweep
   ProbState* S;
   PkInputs in;
 };
 
-#define WA(name, k) (C.W[(size_t)(C.L.name) * C.L.NSP + (k)])
-#define WV(name, i, k) (C.W[(size_t)(C.L.name + (i)) * C.L.NSP + (k)])
+#define WA(name, k) (C.W[(size_t)(CTX_L(C).name) * CTX_L(C).NSP + (k)])
+#define WV(name, i, k) (C.W[(size_t)(CTX_L(C).name + (i)) * CTX_L(C).NSP + (k)])
 #define RIC(off, k) (C.ric[(k) * RSTRIDE + (off)])
+#define PPV(off, k) (C.pp[(size_t)(k) * C.pps + (off)])
 
 OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
   const double pl = dmin_(k1 * dmax(1.0, dabs(lo)), k2 * (hi - lo));
@@ -220,7 +250,7 @@ struct ParkSolver {
   // load rows / variables of block (k, j), optionally at the trial point  z + alpha dz
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD static void load_rows(const PkCtx& C, int j, ObsRows<VM>& R) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     R.v = P.vOb[j];
 #pragma unroll
     for (int i = 0; i < VM; ++i) {
@@ -232,7 +262,7 @@ struct ParkSolver {
     }
   }
   OBCA_HD static void load_vars(const PkCtx& C, int k, int j, const ObsRows<VM>& R, ObsVars<VM>& Q) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
 #pragma unroll
     for (int i = 0; i < VM; ++i) {
       const bool on = i < R.v;
@@ -255,8 +285,8 @@ struct ParkSolver {
   // restart != 0: re-initialise from the current iterate (the reference's second solve(m) restarts Ipopt from
   // JuMP's stored primal values, ParkingSignedDist.jl:256-263) instead of from the warm-start inputs.
   OBCA_HD_NI static void init_stage(const PkCtx& C, int k, int restart) {
-    const ParkProblem& P = *C.P;
-    const IpmOpts& O = *C.O;
+    const ParkProblem& P = CTX_P(C);
+    const IpmOpts& O = CTX_O(C);
     const int N = P.N;
     const bool pose_free = (k >= 1 && k <= N - 1);
     double X, Y, ps, v;
@@ -299,8 +329,8 @@ struct ParkSolver {
   }
   // slacks need the pushed primal point of the neighbours -> separate phase
   OBCA_HD_NI static void init_slacks(const PkCtx& C, int k) {
-    const ParkProblem& P = *C.P;
-    const IpmOpts& O = *C.O;
+    const ParkProblem& P = CTX_P(C);
+    const IpmOpts& O = CTX_O(C);
     const int N = P.N;
     const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
     double s, c;
@@ -329,7 +359,7 @@ struct ParkSolver {
   //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD_NI static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
     const bool fix = P.fix_time != 0;
@@ -532,7 +562,7 @@ struct ParkSolver {
           obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
         }
         double Sxx[6], rx3[3];
-        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, C.O->dc, Sxx, rx3, &WV(LF, j * C.L.nfac, k), C.L.NSP);
+        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, CTX_O(C).dc, Sxx, rx3, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP);
         if (pose_free) {
           RIC(RQ + sym_idx<NYV>(IX, IX), k) += Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += Sxx[2];
           RIC(RQ + sym_idx<NYV>(IY, IY), k) += Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += Sxx[5];
@@ -576,7 +606,7 @@ struct ParkSolver {
   //     returns 1 if every pivot is positive (KKT inertia (n, m, 0)).
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD static int kkt_solve(const PkCtx& C) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     ProbState& S = *C.S;
     const int N = P.N;
     const bool fix = P.fix_time != 0;
@@ -587,7 +617,7 @@ struct ParkSolver {
 #pragma unroll
     for (int i = 0; i < NSV; ++i) pn[i] = 0.0;
     // terminal value: regularised end-point rows  x_N == xF  (ParkingSignedDist.jl:128-131)
-    const double rho = 1.0 / C.O->dc;
+    const double rho = 1.0 / CTX_O(C).dc;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { Pn[sym_idx<NSV>(i, i)] = rho; pn[i] = -WV(PI, i, N - 1); }
     int ok = 1;
@@ -629,7 +659,7 @@ struct ParkSolver {
   // Light and strictly sequential: run by one thread.  The new multipliers of the dynamics rows are computed
   // afterwards, stage-parallel, in recover_stage().
   OBCA_HD static int kkt_root_forward(const PkCtx& C, double ptt, double pt) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     ProbState& S = *C.S;
     const int N = P.N;
     int ok = 1;
@@ -686,7 +716,7 @@ struct ParkSolver {
     int ok;
   };
   OBCA_HD static void kl_init(KktLane& L, int lane, double* tile, const PkCtx& C) {
-    const int N = C.P->N;
+    const int N = CTX_P(C).N;
     const int j = lane < NYV ? lane : NYV - 1;
 #pragma unroll
     for (int i = 0; i < NYV; ++i) L.qoff[i] = RQ + (i <= j ? sym_idx<NYV>(i, j) : sym_idx<NYV>(j, i));
@@ -701,15 +731,16 @@ struct ParkSolver {
     for (int b = 0; b < NSV; ++b) L.Prow[b] = 0.0;
     L.pl = 0.0;
     if (lane < 4) {                      // terminal value: rho |x_N - xF|^2 with multiplier estimate pi_{N-1}
-      L.Prow[lane] = 1.0 / C.O->dc;
+      L.Prow[lane] = 1.0 / CTX_O(C).dc;
       L.pl = -WV(PI, lane, N - 1);
     }
     L.ok = 1;
   }
-  OBCA_HD static void kl_step1(KktLane& L, int lane, double* slot, double* tile) {
+  // `slot`: stage model of stage k (read);  `next`: slot k+1, where P_{k+1} rows are parked for the multiplier recovery
+  OBCA_HD static void kl_step1(KktLane& L, int lane, const double* slot, double* tile, double* next) {
     {  // rows 0..3 of P_{k+1} / p_{k+1} -> slot k+1 (consumed Q/q space) for the multiplier recovery
-      double* const prs = (lane < 4) ? (slot + RSTRIDE + RPP + lane * NSV) : (tile + 125);
-      double* const pps = (lane < 4) ? (slot + RSTRIDE + Rpp + lane) : (tile + 132);
+      double* const prs = (lane < 4) ? (next + RPP + lane * NSV) : (tile + 125);
+      double* const pps = (lane < 4) ? (next + Rpp + lane) : (tile + 132);
 #pragma unroll
       for (int b = 0; b < NSV; ++b) prs[b] = L.Prow[b];
       *pps = L.pl;
@@ -727,7 +758,7 @@ struct ParkSolver {
     tr[IT] = tt; tr[IDE] = td; tr[IAC] = ta;
     tile[L.gs] = gl;
   }
-  OBCA_HD static void kl_step2(KktLane& L, int lane, double* slot, double* tile) {
+  OBCA_HD static void kl_step2(KktLane& L, int lane, const double* slot, double* tile) {
     const int j = lane < NYV ? lane : NYV - 1;
     double T[NSV];
 #pragma unroll
@@ -749,7 +780,8 @@ struct ParkSolver {
     for (int i = 0; i < NYV; ++i) hc[i] = L.H[i];
     tile[L.hvst] = L.hv;
   }
-  OBCA_HD static void kl_step3(KktLane& L, int lane, double* slot, double* tile) {
+  // `kout`: slot that receives the gains of stage k (the stage's own slot; a different address space in the sweep kernel)
+  OBCA_HD static void kl_step3(KktLane& L, int lane, double* kout, double* tile) {
     const double h77 = tile[91 + IDE], h78 = tile[91 + IAC], h88 = tile[100 + IAC];
     double det = h77 * h88 - h78 * h78;
     if (!(h77 > 0.0) || !(det > 0.0)) { L.ok = 0; det = 1e300; }
@@ -761,14 +793,14 @@ struct ParkSolver {
 #pragma unroll
     for (int i = 0; i < NSV; ++i) L.Prow[i] = L.H[i] + tile[91 + i] * K0 + tile[100 + i] * K1;   // new P(:, j) == row j
     L.pl = L.hv + L.H[IDE] * kf0 + L.H[IAC] * kf1;
-    double* const ks = (lane < NSV) ? (slot + RK + lane) : (tile + 133);
+    double* const ks = (lane < NSV) ? (kout + RK + lane) : (tile + 133);
     ks[0] = K0; ks[NSV] = K1;
-    if (lane == 0) { slot[RK + 14] = kf0; slot[RK + 15] = kf1; }
+    if (lane == 0) { kout[RK + 14] = kf0; kout[RK + 15] = kf1; }
   }
 
 #if defined(__CUDA_ARCH__)
   __device__ static int kkt_solve_warp(const PkCtx& C, double* tile) {
-    const ParkProblem& Pp = *C.P;
+    const ParkProblem& Pp = CTX_P(C);
     const int N = Pp.N;
     const int lane = threadIdx.x & 31;
     KktLane L;
@@ -776,7 +808,7 @@ struct ParkSolver {
     __syncwarp();
     for (int k = N - 1; k >= 0; --k) {
       double* const slot = C.ric + k * RSTRIDE;
-      kl_step1(L, lane, slot, tile);
+      kl_step1(L, lane, slot, tile, slot + RSTRIDE);
       __syncwarp();
       kl_step2(L, lane, slot, tile);
       __syncwarp();
@@ -802,8 +834,8 @@ struct ParkSolver {
     const int ur = lane & 1, xr = lane & 3;
     const unsigned FULL = 0xffffffffu;
     const double selx = (xr == 0) ? 1.0 : 0.0, sely = (xr == 1) ? 1.0 : 0.0;
-    double* const dxw = C.W + (size_t)(C.L.dX + xr) * C.L.NSP;      // dX, dY, dPS, dVL are consecutive arrays
-    double* const duw = C.W + (size_t)(C.L.dDE + ur) * C.L.NSP;     // dDE, dAC are consecutive arrays
+    double* const dxw = C.W + (size_t)(CTX_L(C).dX + xr) * CTX_L(C).NSP;      // dX, dY, dPS, dVL are consecutive arrays
+    double* const duw = C.W + (size_t)(CTX_L(C).dDE + ur) * CTX_L(C).NSP;     // dDE, dAC are consecutive arrays
     for (int k = 0; k < N; ++k) {
       const double* const slot = C.ric + k * RSTRIDE;
       const double* const kr = slot + RK + ur * NSV;
@@ -827,12 +859,12 @@ struct ParkSolver {
   // host emulation of the warp: the 32 lanes run each step one after the other (a step only reads what earlier
   // steps wrote, exactly what __syncwarp() guarantees on the device)
   static int kkt_solve_warp_emul(const PkCtx& C, double* tile) {
-    const int N = C.P->N;
+    const int N = CTX_P(C).N;
     KktLane L[32];
     for (int l = 0; l < 32; ++l) kl_init(L[l], l, tile, C);
     for (int k = N - 1; k >= 0; --k) {
       double* const slot = C.ric + k * RSTRIDE;
-      for (int l = 0; l < 32; ++l) kl_step1(L[l], l, slot, tile);
+      for (int l = 0; l < 32; ++l) kl_step1(L[l], l, slot, tile, slot + RSTRIDE);
       for (int l = 0; l < 32; ++l) kl_step2(L[l], l, slot, tile);
       for (int l = 0; l < 32; ++l) kl_step3(L[l], l, slot, tile);
       if (!L[0].ok) return 0;
@@ -854,7 +886,7 @@ struct ParkSolver {
   // K4a: recover local steps, slack steps; step-length partials; directional derivative of the barrier objective
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
     const bool fix = P.fix_time != 0;
@@ -874,9 +906,9 @@ struct ParkSolver {
       sn[IWD] = WA(dDE, k); sn[IWA] = WA(dAC, k); sn[IT] = S.dt;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        double acc = RIC(Rpp + i, k + 1);
+        double acc = PPV(Rpp + i, k + 1);
 #pragma unroll
-        for (int l = 0; l < NSV; ++l) acc += RIC(RPP + i * NSV + l, k + 1) * sn[l];
+        for (int l = 0; l < NSV; ++l) acc += PPV(RPP + i * NSV + l, k + 1) * sn[l];
         WV(PIn, i, k) = -acc;
       }
     }
@@ -933,7 +965,7 @@ struct ParkSolver {
         obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
       }
       ObsStep<VM> St;
-      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, &WV(LF, j * C.L.nfac, k), C.L.NSP, dX, dY, dP, St);
+      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP, dX, dY, dP, St);
       // un-permute lambda
       if (piv != 0) {
 #pragma unroll
@@ -995,7 +1027,7 @@ struct ParkSolver {
   // K4b: merit-function partials at the trial point z + alpha dz  (theta = ||c||_1, phi = barrier objective)
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD_NI static void merit_stage(const PkCtx& C, int k, double alpha, MeritPart& out) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
     const bool fix = P.fix_time != 0;
@@ -1093,10 +1125,10 @@ struct ParkSolver {
     zl = clipz(zl, q - lo, mu_b, ks); zu = clipz(zu, hi - q, mu_b, ks);
   }
   OBCA_HD_NI static void update_stage(const PkCtx& C, int k) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
-    const double mu_b = S.mu, ks = C.O->kappa_sigma;
+    const double mu_b = S.mu, ks = CTX_O(C).kappa_sigma;
     const double alpha = S.alpha, adu = S.a_du, ay = dmin_(S.alpha, S.a_du);   // alpha_for_y = min (:41)
     const bool pose_free = (k >= 1 && k <= N - 1);
     if (pose_free) {
@@ -1166,7 +1198,7 @@ struct ParkSolver {
 
   // write the solution of stage k in the reference's output layout
   OBCA_HD static void store_stage(const PkCtx& C, int k, const PkOutputs& o) {
-    const ParkProblem& P = *C.P;
+    const ParkProblem& P = CTX_P(C);
     const int N = P.N, NS = N + 1;
     o.xp[4 * k + 0] = WA(X, k); o.xp[4 * k + 1] = WA(Y, k); o.xp[4 * k + 2] = WA(PS, k); o.xp[4 * k + 3] = WA(VL, k);
     if (k < N) { o.up[2 * k + 0] = WA(DE, k); o.up[2 * k + 1] = WA(AC, k); }
@@ -1204,20 +1236,20 @@ struct ParkSolver {
 #if defined(__CUDA_ARCH__)
   __device__ static int kkt_solve_block(const PkCtx&) { return 0; }
 #endif
-  OBCA_HD static int n_stages(const PkCtx& C) { return C.P->N + 1; }
-  OBCA_HD static bool fixed_time(const PkCtx& C) { return C.P->fix_time != 0; }
+  OBCA_HD static int n_stages(const PkCtx& C) { return CTX_P(C).N + 1; }
+  OBCA_HD static bool fixed_time(const PkCtx& C) { return CTX_P(C).fix_time != 0; }
   OBCA_HD static void mult_counts(const PkCtx& C, double& n_mult, double& n_bmult) { mult_counts(*C.P, n_mult, n_bmult); }
   OBCA_HD static void init_scalars(const PkCtx& C, int restart) {
     ProbState& S = *C.S;
-    const IpmOpts& O = *C.O;
-    S.t = C.P->fix_time ? 1.0 : push_lo(restart ? S.t : 1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
+    const IpmOpts& O = CTX_O(C);
+    S.t = CTX_P(C).fix_time ? 1.0 : push_lo(restart ? S.t : 1.0, 0.8, 1.2, O.kappa1, O.kappa2);   // setvalue(timeScale, 1) (:214)
     S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
   }
   OBCA_HD static void update_scalars(const PkCtx& C) {
     ProbState& S = *C.S;
-    if (!C.P->fix_time) {
+    if (!CTX_P(C).fix_time) {
       double q = S.t, zl = S.zTL, zu = S.zTU;
-      upd_pair(q, S.dt, zl, zu, 0.8, 1.2, S.alpha, S.a_du, S.mu, C.O->kappa_sigma);
+      upd_pair(q, S.dt, zl, zu, 0.8, 1.2, S.alpha, S.a_du, S.mu, CTX_O(C).kappa_sigma);
       S.t = q; S.zTL = zl; S.zTU = zu;
     }
   }
@@ -1245,7 +1277,7 @@ struct IpmDriver {
   }
   OBCA_HD static double err_mu(const Ctx& C, double mu_t) {
     const ProbState& S = *C.S;
-    const IpmOpts& O = *C.O;
+    const IpmOpts& O = CTX_O(C);
     double n_mult, n_bmult;
     M::mult_counts(C, n_mult, n_bmult);
     const double sd = dmax(O.s_max, (S.sum_y + S.sum_z) / n_mult) / O.s_max;
@@ -1258,7 +1290,7 @@ struct IpmDriver {
   // the solve: all threads of the CTA call this with the same context
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD static void solve(const Ctx& C, int restart = 0) {
-    const IpmOpts& O = *C.O;
+    const IpmOpts& O = CTX_O(C);
     ProbState& S = *C.S;
     const int NS = M::n_stages(C);
 

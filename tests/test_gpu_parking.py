@@ -247,3 +247,37 @@ def test_dist_and_fixed_time_full_batch_rates(P):
         assert (r["exitflag"] == 1).mean() >= 0.97, (sd, fix, (r["exitflag"] == 1).mean())
         if fix:
             assert np.array_equal(r["ts"], np.ones_like(r["ts"]))
+
+
+@pytest.mark.parametrize("variant,fix", [("sd", 0), ("d", 0), ("sd", 1)])
+def test_phased_equals_persistent(P, variant, fix):
+    """The phase-split driver (rounds of phase kernels with the state in HBM, OBCA_MODE=2), its tail / small-batch
+    kernel (OBCA_MODE=1), the automatic hand-over between the two, and the monolithic persistent kernel
+    (OBCA_MODE=3) run the same arithmetic in the same order: outputs must be bit-identical."""
+    from obca_b200 import scenarios
+    sc = scenarios.reverse_parking_batch(200, 80, seed=5)
+    sd = 1 if variant == "sd" else 0
+    res = {}
+    old = {k: os.environ.get(k) for k in ("OBCA_MODE", "OBCA_TAIL_THRESH")}
+    try:
+        for name, mode, thresh in (("mono", "3", None), ("tail", "1", None), ("rounds", "2", "0"), ("handover", "2", "120")):
+            os.environ["OBCA_MODE"] = mode
+            if thresh is None:
+                os.environ.pop("OBCA_TAIL_THRESH", None)
+            else:
+                os.environ["OBCA_TAIL_THRESH"] = thresh
+            res[name] = solve(P, sc, fix=fix, sd=sd)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    ref = res["mono"]
+    assert ref["exitflag"].sum() >= 190
+    for name in ("tail", "rounds", "handover"):
+        r = res[name]
+        assert (r["iters"] == ref["iters"]).all(), (name, np.flatnonzero(r["iters"] != ref["iters"])[:8])
+        assert (r["exitflag"] == ref["exitflag"]).all(), name
+        for key in ("xp", "up", "ts", "lp", "np"):
+            assert np.array_equal(r[key], ref[key]), (name, key, float(np.abs(r[key] - ref[key]).max()))
