@@ -273,7 +273,7 @@ def gpu_arm(args):
     hbm, how = peaks()
     value = conv_all / (dev_s / args.steps)
     e2e_val = conv_h_all / (e2e_s / args.steps)
-    kernel_s = dev_s / args.steps                        # k_parking_solve dominates the event-bracketed step
+    kernel_s = dev_s / args.steps                        # the solver kernels are (all but the K2 launch) the event-bracketed step
     achieved = (evals_all / world) * ALG_BYTES_PER_EVAL / kernel_s / 1e9
     h2d = sum(int(v.numel()) * 8 for v in hin.values())
     d2h = sum(int(v.numel()) * 8 for v in hout.values()) + 8 * B
@@ -287,10 +287,10 @@ def gpu_arm(args):
             "clocks": sampler.result(),
             "e2e": {"value": e2e_val, "unit": "traj/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_parking_solve<2,true>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "whole solve: rounds of k_pk_phaseA/k_pk_sweep/k_pk_phaseC<2,true>, then k_pk_tail<2,true>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": None,
                          "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x (iterations+1) per problem (SURVEY 8d, fused K1); "
-                                 f"peak {how}; the persistent solver is FP64/latency bound, see DESIGN.md"}}
+                                 f"peak {how}; the solver is FP64-latency bound, see DESIGN.md and profiles/"}}
     # ---- K1 stand-alone (fused constraint / Lagrangian-gradient evaluation) at the solution points: HBM roofline ----
     nn = C.c_longlong(); mm = C.c_longlong()
     lib.obca_parking_eval_sizes(C.c_int(N), C.c_int(nOb), NP(vOb), C.c_int(1), C.byref(nn), C.byref(mm))
@@ -316,8 +316,21 @@ def gpu_arm(args):
                            "frac": k1_gbs / hbm, "traffic": None, "ms_per_launch": k1_ms,
                            "note": f"stand-alone fused K1: 8*(2n+2m+3(N+1)) = {int(k1_bytes / B)} B/problem/evaluation, B={B}; working set "
                                    f"{k1_bytes / 1e6:.0f} MB > L2; mean of 20 back-to-back launches"}
+    rnd = C.c_int(0); hand = C.c_int(0); kms = (C.c_double * 4)()
+    if lib.obca_last_schedule(C.c_int(local), C.byref(rnd), C.byref(hand), None) == 0:
+        line["config"]["schedule"] = {"phase_split_rounds": rnd.value, "handed_to_tail_kernel": hand.value}
+        line["gpu_launches"] = args.steps * (1 + 3 * rnd.value + (1 if hand.value > 0 else 0)) * 2    # device arm + e2e arm
+        # one extra, untimed solve with per-kernel events: which kernel dominates the step
+        os.environ["OBCA_PHASE_TIMING"] = "1"
+        step_dev()
+        os.environ.pop("OBCA_PHASE_TIMING", None)
+        if lib.obca_last_schedule(C.c_int(local), None, None, kms) == 0:
+            names = ["k_pk_phaseA (K1 assemble)", "k_pk_sweep (K3 KKT)", "k_pk_phaseC (K4 line search)", "k_pk_tail (persistent, all phases)"]
+            tot = sum(kms) or 1.0
+            line["kernel_share"] = {n: round(kms[i] / tot, 4) for i, n in enumerate(names)}
+            line["kernel_ms_serialised"] = {n: round(kms[i], 3) for i, n in enumerate(names)}
     prof = (C.c_ulonglong * 8)()
-    if lib.obca_last_profile(C.c_int(local), prof) == 0:
+    if lib.obca_last_profile(C.c_int(local), prof) == 0 and sum(prof[i] for i in range(6)) > 0:
         names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]
         tot = float(sum(prof[i] for i in range(6))) or 1.0
         line["phase_share"] = {n: round(prof[i] / tot, 4) for i, n in enumerate(names)}

@@ -127,8 +127,19 @@ int obca_check_quadcopter(int B, int N, const double* x, const double* u, const 
 
 /* Per-phase device cycle counters of the last obca_parking_solve_batch[_dev] on `device`, summed over the batch
  * (thread 0 of every CTA, clock64): out8 = {eval (K1), kkt (K3), recover, merit, update, serial sections,
- * #merit evaluations, #K1 evaluations}.  Diagnostic only. */
+ * #merit evaluations, #K1 evaluations}.  Only the monolithic kernel (OBCA_MODE=3) fills them; zeros otherwise.
+ * Diagnostic only. */
 int obca_last_profile(int device, unsigned long long* out8);
+
+/* How the last obca_parking_solve_batch[_dev] on `device` was scheduled (last chunk of the batch): number of
+ * phase-split rounds ([assemble, sweep, line-search] kernel triples over all active problems) and the number of
+ * problems handed to the persistent tail kernel afterwards (= the batch size when no rounds were run).  Environment
+ * overrides for experiments: OBCA_MODE (0 auto, 1 tail kernel only, 2 rounds always, 3 monolithic kernel),
+ * OBCA_TAIL_THRESH (hand-over point), OBCA_CHUNK (problems per chunk).  kernel_ms4 (may be NULL): with
+ * OBCA_PHASE_TIMING=1 in the environment the solve records CUDA events around every kernel (this serialises the
+ * host loop, so the solve itself runs slower) and reports the summed times of {assemble kernel, sweep kernel,
+ * line-search kernel, tail kernel} in milliseconds.  Diagnostic only. */
+int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms4);
 
 /* K1 stand-alone: fused evaluation of the parking NLP in the REFERENCE's formulation at B given points (no solve);
  * what JuMP's eval_g / eval_grad_f / eval_jac_g' * y do for Ipopt (ParkingSignedDist.jl:240), one thread per

@@ -12,7 +12,7 @@ SO_PATH = os.environ.get("OBCA_SO", os.path.join(HERE, "libobca.so"))   # OBCA_S
 
 SYMBOLS = ["obca_version", "obca_device_count", "obca_last_error", "obca_default_opts", "obca_parking_solve_batch",
            "obca_parking_solve_batch_dev", "obca_dualmultws_batch", "obca_check_parking",
-           "obca_parking_eval_batch_dev", "obca_parking_eval_sizes", "obca_last_profile",
+           "obca_parking_eval_batch_dev", "obca_parking_eval_sizes", "obca_last_profile", "obca_last_schedule",
            "obca_quadcopter_solve_batch", "obca_check_quadcopter"]
 
 

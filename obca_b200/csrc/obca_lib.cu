@@ -331,6 +331,7 @@ struct DevCtx {
   int* h_n = nullptr;                               // pinned ring of active counts read back per round
   cudaEvent_t evr[16] = {nullptr};
   int last_rounds = 0, last_tail = 0;
+  double phase_ms[4] = {0, 0, 0, 0};                // OBCA_PHASE_TIMING=1: summed event times of K_A, K_B, K_C, tail
   std::mutex mu;
 };
 static DevCtx g_dev[64];
@@ -444,7 +445,9 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
   ProbState* Sg = (ProbState*)c.pstate;
   cudaStream_t st = c.st;
   // mode 1: tail kernel only; mode 2: rounds until the active set fits one wave of the tail kernel; auto: by batch size
-  const int thresh = env_int("OBCA_TAIL_THRESH", tail_cap);
+  // hand-over point: measured on B200 (config 2, B = 4096) the solve time is flat for thresholds between B/4 and 3B/4
+  // and ~8 % higher for rounds-only or tail-only, so: half the batch, but never less than one wave of the tail kernel
+  const int thresh = env_int("OBCA_TAIL_THRESH", B / 2 > tail_cap ? B / 2 : tail_cap);
   const bool rounds = mode == 2 || (mode == 0 && B > 2 * tail_cap);
   c.last_rounds = 0; c.last_tail = B;
   int h_init[4] = {B, 0, 0, 0};
@@ -462,13 +465,20 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
   int* act[2] = {c.act, c.act + B};
   int cur = 0, fresh = 1, n_bound = B, done_r = 0, r = 0;
   const int max_rounds = 8 * (O.max_iter + 8);
+  const bool timing = env_int("OBCA_PHASE_TIMING", 0) != 0;      // development: per-kernel event times, summed per solve
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   for (; r < max_rounds; ++r) {
     CK(cudaMemsetAsync(c.ncnt + (1 - cur), 0, sizeof(int), st));
+    mark();
     k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[cur], c.ncnt + cur, act[1 - cur],
                                                       c.ncnt + (1 - cur), fresh);
+    mark();
     k_pk_sweep<VM, SDV><<<(n_bound + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
                                                                                               c.ncnt + (1 - cur));
+    mark();
     k_pk_phaseC<VM, SDV><<<n_bound, L.NSP, 0, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[1 - cur], c.ncnt + (1 - cur));
+    mark();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c.h_n + (r & 15), c.ncnt + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c.evr[r & 15], st));
@@ -484,10 +494,26 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
     }
   }
   c.last_rounds = r; c.last_tail = n_bound;
+  if (timing) {
+    CK(cudaStreamSynchronize(st));
+    double t[3] = {0, 0, 0};
+    for (size_t i = 0; i + 3 < tev.size(); i += 4)
+      for (int j = 0; j < 3; ++j) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[i + j], tev[i + j + 1]); t[j] += ms; }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    for (int j = 0; j < 3; ++j) c.phase_ms[j] = t[j];
+    c.phase_ms[3] = 0.0;
+  }
   if (n_bound > 0) {
     const int grid = n_bound < tail_cap ? n_bound : tail_cap;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     k_pk_tail<VM, SDV><<<grid, L.NSP, smem, st>>>(P, O, L, bp, c.W, Sg, act[cur], c.ncnt + cur, c.ncnt + 2, 0);
     CK(cudaGetLastError());
+    if (timing) {
+      cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); c.phase_ms[3] = ms;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
   }
   return 0;
 }
@@ -503,21 +529,36 @@ static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, Bat
   CK(cudaMemsetAsync(c.prof, 0, 8 * sizeof(unsigned long long), c.st));
   bp.prof = c.prof;
   int rc;
-#ifdef OBCA_FAST_BUILD   // development builds: only the config-2 instantiation
-  if (!(P.signed_dist && vm == 2)) { set_err("fast build: only <2,true>"); return OBCA_ERR_UNSUPPORTED; }
-  rc = launch_solve<2, true>(c, P, O, bp);
-#else
-  // OBCA_MODE: 0 auto (phase-split rounds for large batches, persistent tail kernel for small ones), 1 tail kernel only,
-  // 2 rounds always, 3 the monolithic persistent kernel k_parking_solve (kept as the cross-check of the phase split)
   const int mode = env_int("OBCA_MODE", 0);
-  if (mode == 3) {
-    if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, bp) : launch_solve<4, true>(c, P, O, bp);
-    else rc = vm == 2 ? launch_solve<2, false>(c, P, O, bp) : launch_solve<4, false>(c, P, O, bp);
-  } else {
-    if (P.signed_dist) rc = vm == 2 ? launch_phased<2, true>(c, P, O, bp, mode) : launch_phased<4, true>(c, P, O, bp, mode);
-    else rc = vm == 2 ? launch_phased<2, false>(c, P, O, bp, mode) : launch_phased<4, false>(c, P, O, bp, mode);
-  }
+  // large batches are solved in chunks so that the per-problem workspace (~0.25 MB) stays within a few GB
+  const int chunk = env_int("OBCA_CHUNK", 16384);
+  const int NSc = P.N + 1, Vc = P.V, nObc = P.nOb;
+  rc = 0;
+  for (int b0 = 0; b0 < bp.B && rc == 0; b0 += chunk) {
+    BatchPtrs q = bp;
+    q.B = bp.B - b0 < chunk ? bp.B - b0 : chunk;
+    const size_t o = (size_t)b0;
+    q.x0 += 4 * o; q.xF += 4 * o; q.rx += NSc * o; q.ry += NSc * o; q.ryaw += NSc * o; q.xWS += 4 * NSc * o; q.uWS += 2 * (size_t)P.N * o;
+    q.lWS += (size_t)Vc * NSc * o; q.nWS += (size_t)4 * nObc * NSc * o;
+    q.xp += 4 * NSc * o; q.up += 2 * (size_t)P.N * o; q.ts += NSc * o; q.lp += (size_t)Vc * NSc * o; q.np += (size_t)4 * nObc * NSc * o;
+    if (q.sl) q.sl += (size_t)nObc * NSc * o;
+    if (q.duals) q.duals += ((size_t)4 * P.N + (size_t)4 * nObc * NSc) * o;
+    q.exitflag += o; q.iters += o; q.kkt_err += o;
+#ifdef OBCA_FAST_BUILD   // development builds: only the config-2 instantiation
+    if (!(P.signed_dist && vm == 2)) { set_err("fast build: only <2,true>"); return OBCA_ERR_UNSUPPORTED; }
+    rc = mode == 3 ? launch_solve<2, true>(c, P, O, q) : launch_phased<2, true>(c, P, O, q, mode);
+#else
+    // OBCA_MODE: 0 auto (phase-split rounds for large batches, persistent tail kernel for small ones), 1 tail kernel only,
+    // 2 rounds always, 3 the monolithic persistent kernel k_parking_solve (kept as the cross-check of the phase split)
+    if (mode == 3) {
+      if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, q) : launch_solve<4, true>(c, P, O, q);
+      else rc = vm == 2 ? launch_solve<2, false>(c, P, O, q) : launch_solve<4, false>(c, P, O, q);
+    } else {
+      if (P.signed_dist) rc = vm == 2 ? launch_phased<2, true>(c, P, O, q, mode) : launch_phased<4, true>(c, P, O, q, mode);
+      else rc = vm == 2 ? launch_phased<2, false>(c, P, O, q, mode) : launch_phased<4, false>(c, P, O, q, mode);
+    }
 #endif
+  }
   if (rc) return rc;
   CK(cudaEventRecord(c.ev1, c.st));
   CK(cudaMemcpyAsync(c.prof_host, c.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st));
@@ -826,6 +867,14 @@ int obca_check_quadcopter(int B, int N, const double* x, const double* u, const 
 int obca_last_profile(int device, unsigned long long* out8) {
   if (device < 0 || device >= 64 || !out8 || !g_dev[device].init) { set_err("no profile"); return OBCA_ERR_ARG; }
   for (int i = 0; i < 8; ++i) out8[i] = g_dev[device].prof_host[i];
+  return 0;
+}
+
+int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms4) {
+  if (device < 0 || device >= 64 || !g_dev[device].init) { set_err("no schedule"); return OBCA_ERR_ARG; }
+  if (rounds) *rounds = g_dev[device].last_rounds;
+  if (handed_over) *handed_over = g_dev[device].last_tail;
+  if (kernel_ms4) for (int i = 0; i < 4; ++i) kernel_ms4[i] = g_dev[device].phase_ms[i];
   return 0;
 }
 

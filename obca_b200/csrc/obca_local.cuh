@@ -149,35 +149,58 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
   const double c3 = s3 * G.cr1 - mu_b * im3;
   const double c4 = s4 * G.cr2 - mu_b * im4;
 
-  // vectors over the ND unknowns: t3, t4 (rot rows after eliminating mu3, mu4) and Gt (dist row)
-  double t3[ND], t4[ND], Gt[ND];
-#pragma unroll
-  for (int i = 0; i < ND; ++i) { t3[i] = 0.0; t4[i] = 0.0; Gt[i] = 0.0; }
+  // Rank-one terms  s3 t3 t3' + s4 t4 t4' + Sd Gt Gt'  and the gradient  t3 c3 + t4 c4 + Gt yd0,  written out by
+  // sparsity pattern (t3, t4: rot rows after eliminating mu3, mu4; Gt: dist row after eliminating its slack):
+  //   t3 = { lambda_i: ah1_i, mu1: 1,        psi: e2 }
+  //   t4 = { lambda_i: ah2_i, mu2: 1,        psi: -e1 }
+  //   Gt = { lambda_i: gt_i,  mu1: -g1-g3,   mu2: -g2-g4,  sl: 1 (SD),  X: p1,  Y: p2,  psi: gP }
+  // (structural zeros are not multiplied: fewer FP64 operations and no registers for them)
+  const double gM1 = -g1 - g3, gM2 = -g2 - g4, gP = P.off * G.e2 - g3 * G.e2 + g4 * G.e1;
+  const double sM1 = Sd * gM1, sM2 = Sd * gM2, sP = Sd * gP, sX = Sd * G.p1, sY = Sd * G.p2;
+  const double s3e = s3 * G.e2, s4e = -s4 * G.e1;
 #pragma unroll
   for (int i = 0; i < VM; ++i) {
     if (i < R.v) {
-      t3[D::il(i)] = G.ah1[i];
-      t4[D::il(i)] = G.ah2[i];
-      Gt[D::il(i)] = G.rho[i] - g3 * G.ah1[i] - g4 * G.ah2[i];
+      const int li = D::il(i);
+      const double gti = G.rho[i] - g3 * G.ah1[i] - g4 * G.ah2[i];
+      const double a3 = s3 * G.ah1[i], a4 = s4 * G.ah2[i], sg = Sd * gti;
+#pragma unroll
+      for (int l = i; l < VM; ++l) {
+        if (l < R.v) {
+          const double gtl = G.rho[l] - g3 * G.ah1[l] - g4 * G.ah2[l];
+          M[sym_idx<ND>(li, D::il(l))] = a3 * G.ah1[l] + a4 * G.ah2[l] + sg * gtl;
+        }
+      }
+      M[sym_idx<ND>(li, D::I_MU1)] = a3 + sg * gM1;
+      M[sym_idx<ND>(li, D::I_MU2)] = a4 + sg * gM2;
+      if (SDV) M[sym_idx<ND>(li, D::I_SL)] = sg;
+      M[sym_idx<ND>(li, D::I_X)] = sg * G.p1;
+      M[sym_idx<ND>(li, D::I_Y)] = sg * G.p2;
+      M[sym_idx<ND>(li, D::I_P)] = a3 * G.e2 - a4 * G.e1 + sg * gP;
+      r[li] = G.ah1[i] * c3 + G.ah2[i] * c4 + gti * yd0;
     }
   }
-  t3[D::I_MU1] = 1.0; t4[D::I_MU2] = 1.0;
-  t3[D::I_P] = G.e2; t4[D::I_P] = -G.e1;
-  Gt[D::I_MU1] = -g1 - g3; Gt[D::I_MU2] = -g2 - g4;
-  if (SDV) Gt[D::I_SL] = 1.0;
-  Gt[D::I_X] = G.p1; Gt[D::I_Y] = G.p2; Gt[D::I_P] = P.off * G.e2 - g3 * G.e2 + g4 * G.e1;
-
-  // rank-one terms + gradient
-#pragma unroll
-  for (int i = 0; i < ND; ++i) {
-    if (SDV && i == 1) continue;   // y_norm row handled separately
-#pragma unroll
-    for (int j = i; j < ND; ++j) {
-      if (SDV && j == 1) continue;
-      M[sym_idx<ND>(i, j)] = s3 * t3[i] * t3[j] + s4 * t4[i] * t4[j] + Sd * Gt[i] * Gt[j];
-    }
-    r[i] = t3[i] * c3 + t4[i] * c4 + Gt[i] * yd0;
+  M[sym_idx<ND>(D::I_MU1, D::I_MU1)] = s3 + sM1 * gM1;
+  M[sym_idx<ND>(D::I_MU1, D::I_MU2)] = sM1 * gM2;
+  M[sym_idx<ND>(D::I_MU2, D::I_MU2)] = s4 + sM2 * gM2;
+  if (SDV) {
+    M[sym_idx<ND>(D::I_MU1, D::I_SL)] = sM1;
+    M[sym_idx<ND>(D::I_MU2, D::I_SL)] = sM2;
+    M[sym_idx<ND>(D::I_SL, D::I_SL)] = Sd;
+    M[sym_idx<ND>(D::I_SL, D::I_X)] = sX; M[sym_idx<ND>(D::I_SL, D::I_Y)] = sY; M[sym_idx<ND>(D::I_SL, D::I_P)] = sP;
+    r[D::I_SL] = yd0;
   }
+  M[sym_idx<ND>(D::I_MU1, D::I_X)] = sM1 * G.p1; M[sym_idx<ND>(D::I_MU1, D::I_Y)] = sM1 * G.p2;
+  M[sym_idx<ND>(D::I_MU1, D::I_P)] = s3e + sM1 * gP;
+  M[sym_idx<ND>(D::I_MU2, D::I_X)] = sM2 * G.p1; M[sym_idx<ND>(D::I_MU2, D::I_Y)] = sM2 * G.p2;
+  M[sym_idx<ND>(D::I_MU2, D::I_P)] = s4e + sM2 * gP;
+  M[sym_idx<ND>(D::I_X, D::I_X)] = sX * G.p1; M[sym_idx<ND>(D::I_X, D::I_Y)] = sX * G.p2; M[sym_idx<ND>(D::I_X, D::I_P)] = sX * gP;
+  M[sym_idx<ND>(D::I_Y, D::I_Y)] = sY * G.p2; M[sym_idx<ND>(D::I_Y, D::I_P)] = sY * gP;
+  M[sym_idx<ND>(D::I_P, D::I_P)] = s3e * G.e2 - s4e * G.e1 + sP * gP;
+  r[D::I_MU1] = c3 + gM1 * yd0;
+  r[D::I_MU2] = c4 + gM2 * yd0;
+  r[D::I_X] = G.p1 * yd0; r[D::I_Y] = G.p2 * yd0;
+  r[D::I_P] = G.e2 * c3 - G.e1 * c4 + gP * yd0;
   // Lagrangian Hessian + barrier diagonal of lambda
   const double ynorm = SDV ? Q.yn : Q.vn;   // multiplier of the norm row (row multiplier yI = vU for the Dist variant)
   double Sn = 0.0, yn0 = 0.0;
@@ -228,6 +251,14 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
 
   int ok = 1;
   // ---- elimination ----
+  // factor layout (strided by fs: workspace arrays): rows 0..NLT-1 of the upper triangle, then their rhs.  A row is
+  // written out as soon as it is final, which frees its registers for the rest of the elimination.
+  auto store_row = [&](int i) {
+    const int q0 = i * ND - (i * (i - 1)) / 2;
+#pragma unroll
+    for (int c_ = i; c_ < ND; ++c_) fac[(size_t)(q0 + c_ - i) * fs] = M[sym_idx<ND>(i, c_)];
+    fac[(size_t)(D::NM - 6 + i) * fs] = r[i];
+  };
   int first = 0;
   if (SDV) {
     // 2x2 pivot on (lambda_0, y_norm)
@@ -252,6 +283,7 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
     }
     // store inverse of the 2x2 block in place of it
     M[sym_idx<ND>(0, 0)] = i00; M[sym_idx<ND>(0, 1)] = i01; M[sym_idx<ND>(1, 1)] = i11;
+    store_row(0); store_row(1);
     first = 2;
   }
 #pragma unroll
@@ -267,21 +299,11 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
       for (int c_ = rr; c_ < ND; ++c_) M[sym_idx<ND>(rr, c_)] -= f * M[sym_idx<ND>(i, c_)];
       r[rr] -= f * r[i];
     }
+    store_row(i);
   }
   Sxx[0] = M[sym_idx<ND>(D::I_X, D::I_X)]; Sxx[1] = M[sym_idx<ND>(D::I_X, D::I_Y)]; Sxx[2] = M[sym_idx<ND>(D::I_X, D::I_P)];
   Sxx[3] = M[sym_idx<ND>(D::I_Y, D::I_Y)]; Sxx[4] = M[sym_idx<ND>(D::I_Y, D::I_P)]; Sxx[5] = M[sym_idx<ND>(D::I_P, D::I_P)];
   rx[0] = r[D::I_X]; rx[1] = r[D::I_Y]; rx[2] = r[D::I_P];
-  // factor: rows 0..NLT-1 of the upper triangle, then their rhs  (fac is strided by fs: workspace arrays)
-  {
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < D::NLT; ++i) {
-#pragma unroll
-      for (int c_ = i; c_ < ND; ++c_) { fac[(size_t)q * fs] = M[sym_idx<ND>(i, c_)]; ++q; }
-    }
-#pragma unroll
-    for (int i = 0; i < D::NLT; ++i) { fac[(size_t)q * fs] = r[i]; ++q; }
-  }
   return ok;
 }
 

@@ -352,9 +352,13 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   const int NS = P.N + 1;
   if (fresh) state_fresh(S); else state_load(S, Sg + b);
   __syncthreads();
-  PkCtx C; PkOutputs out;
-  pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
-  C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+  // the context is identical for every thread: one copy in shared memory (not one per thread in local memory)
+  __shared__ PkCtx C; __shared__ PkOutputs out;
+  if (threadIdx.x == 0) {
+    pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
+    C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+  }
+  __syncthreads();
   pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
   if (S.phase == PH_KKT) {
     double* g = slots + (size_t)b * NS * GSTRIDE;
@@ -509,10 +513,12 @@ k_pk_phaseC(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   if (Sg[b].phase != PH_RECOVER) return;
   const int NS = P.N + 1;
   state_load(S, Sg + b);
+  __shared__ PkCtx C; __shared__ PkOutputs out;
+  if (threadIdx.x == 0) {
+    pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
+    C.ric = nullptr; C.pp = slots + (size_t)b * NS * GSTRIDE; C.pps = GSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+  }
   __syncthreads();
-  PkCtx C; PkOutputs out;
-  pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
-  C.ric = nullptr; C.pp = slots + (size_t)b * NS * GSTRIDE; C.pps = GSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
   PhasedDriver<ParkSolver<VM, SDV> >::phase_C(C);
   state_store(Sg + b, S);
 }
@@ -535,6 +541,7 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
   __shared__ double s_red[4 * 12];
   __shared__ PkFinalScratch s_fin;
   __shared__ int s_i;
+  __shared__ PkCtx C; __shared__ PkOutputs out;
   typedef ParkSolver<VM, SDV> PS;
   const int n = *n_act;
   for (;;) {
@@ -544,10 +551,11 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
     if (i >= n) break;
     const int b = fresh ? i : act[i];
     if (fresh) state_fresh(S); else state_load(S, Sg + b);
+    if (threadIdx.x == 0) {
+      pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
+      C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
+    }
     __syncthreads();
-    PkCtx C; PkOutputs out;
-    pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
-    C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
     for (;;) {
       pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
       if (S.phase == PH_DONE) break;

@@ -381,6 +381,70 @@ struct ParkSolver {
     // Lagrangian gradient rows of the pose
     double rzX = 0.0, rzY = 0.0, rzP = 0.0, rzV = 0.0;
 
+    // Order of the sections: obstacle blocks first, then the state terms, the controls / dynamics last -- the local
+    // elimination of a block needs ~60 doubles in registers, so nothing else big (dynamics Jacobian, residuals) may be
+    // live across it; the dynamics outputs go straight into the stage slot.
+    // ---- (C) obstacle blocks ----
+    for (int j = 0; j < P.nOb; ++j) {
+      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
+      load_rows(C, j, R);
+      load_vars(C, k, j, R, Qv);
+      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      if (do_err) {
+        double rl[VM], rm[4], rs_, gx[3];
+        obs_lagr_grad<VM, SDV>(P, R, Qv, G, rl, rm, rs_, gx);
+        rzX += gx[0]; rzY += gx[1]; rzP += gx[2];
+#pragma unroll
+        for (int i = 0; i < VM; ++i) {
+          if (i < R.v) {
+            e_dual = dmax(e_dual, dabs(rl[i]));
+            const double cp = Qv.lam[i] * Qv.zlam[i];
+            cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+            sum_z += Qv.zlam[i];
+            lacc.add(Qv.lam[i]);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          e_dual = dmax(e_dual, dabs(rm[m]));
+          const double cp = Qv.mu[m] * Qv.zmu[m];
+          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+          sum_z += Qv.zmu[m];
+          lacc.add(Qv.mu[m]);
+        }
+        if (SDV) { e_dual = dmax(e_dual, dabs(rs_)); fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl; }
+        e_pr = dmax(e_pr, dmax(dmax(dabs(G.cn), dabs(G.cd)), dmax(dabs(G.cr1), dabs(G.cr2))));
+        th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
+        sum_y += dabs(Qv.yr1) + dabs(Qv.yr2) + Qv.vd + (SDV ? dabs(Qv.yn) : Qv.vn);
+        sum_z += Qv.vd + (SDV ? 0.0 : Qv.vn);
+        {
+          const double cp = (Qv.sd - P.dmin) * Qv.vd;
+          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+          lacc.add(Qv.sd - P.dmin);
+        }
+        if (!SDV) {
+          const double cp = (1.0 - Qv.sn) * Qv.vn;
+          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
+          lacc.add(1.0 - Qv.sn);
+        }
+      } else if (SDV) {
+        fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
+      }
+      if (do_asm) {
+        const int piv = choose_pivot<VM, SDV>(R, G);
+        if (piv != 0) {
+          swap_rows(R, Qv, piv);
+          obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+        }
+        double Sxx[6], rx3[3];
+        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, CTX_O(C).dc, Sxx, rx3, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP);
+        if (pose_free) {
+          RIC(RQ + sym_idx<NYV>(IX, IX), k) += Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += Sxx[2];
+          RIC(RQ + sym_idx<NYV>(IY, IY), k) += Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += Sxx[5];
+          RIC(Rq + IX, k) += rx3[0]; RIC(Rq + IY, k) += rx3[1]; RIC(Rq + IP, k) += rx3[2];
+        }
+      }
+    }
     // ---- (A) state objective + bounds ----
     {
       const double ex = X - C.in.rx[k], ey = Y - C.in.ry[k], ep = ps - C.in.ryaw[k];
@@ -411,9 +475,9 @@ struct ParkSolver {
       }
     }
     // ---- (B) controls, input-rate terms, steering-rate row, dynamics ----
-    DynOut dyn;
-    double r4[4] = {0, 0, 0, 0};
     if (has_u) {
+      DynOut dyn;
+      double r4[4];
       const double de = WA(DE, k), ac = WA(AC, k);
       const double wd = k > 0 ? WA(DE, k - 1) : 0.0, wa = k > 0 ? WA(AC, k - 1) : 0.0;
       const double h = t * P.Ts, ih = rcp(h), ih2 = ih * ih, it = rcp(t);
@@ -477,6 +541,14 @@ struct ParkSolver {
       else { xn[0] = WA(X, k + 1); xn[1] = WA(Y, k + 1); xn[2] = WA(PS, k + 1); xn[3] = WA(VL, k + 1); }
 #pragma unroll
       for (int i = 0; i < 4; ++i) r4[i] = dyn.f[i] - xn[i];
+      if (do_asm) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          RIC(RDYN + 5 * i + 0, k) = dyn.fx[i][0]; RIC(RDYN + 5 * i + 1, k) = dyn.fx[i][1]; RIC(RDYN + 5 * i + 2, k) = dyn.ft[i];
+          RIC(RDYN + 5 * i + 3, k) = dyn.fu[i][0]; RIC(RDYN + 5 * i + 4, k) = dyn.fu[i][1];
+          RIC(RR4 + i, k) = r4[i];
+        }
+      }
       // Lagrangian gradient: -A' pi on the pose rows
       if (pose_free) {
         rzX -= pi[0]; rzY -= pi[1];
@@ -509,67 +581,6 @@ struct ParkSolver {
         lacc.add(aDl); lacc.add(aDu); lacc.add(aAl); lacc.add(aAu); lacc.add(gl); lacc.add(gu);
       }
     }
-    // ---- (C) obstacle blocks ----
-    for (int j = 0; j < P.nOb; ++j) {
-      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
-      load_rows(C, j, R);
-      load_vars(C, k, j, R, Qv);
-      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
-      if (do_err) {
-        double rl[VM], rm[4], rs_, gx[3];
-        obs_lagr_grad<VM, SDV>(P, R, Qv, G, rl, rm, rs_, gx);
-        rzX += gx[0]; rzY += gx[1]; rzP += gx[2];
-#pragma unroll
-        for (int i = 0; i < VM; ++i) {
-          if (i < R.v) {
-            e_dual = dmax(e_dual, dabs(rl[i]));
-            const double cp = Qv.lam[i] * Qv.zlam[i];
-            cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-            sum_z += Qv.zlam[i];
-            lacc.add(Qv.lam[i]);
-          }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          e_dual = dmax(e_dual, dabs(rm[m]));
-          const double cp = Qv.mu[m] * Qv.zmu[m];
-          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-          sum_z += Qv.zmu[m];
-          lacc.add(Qv.mu[m]);
-        }
-        if (SDV) { e_dual = dmax(e_dual, dabs(rs_)); fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl; }
-        e_pr = dmax(e_pr, dmax(dmax(dabs(G.cn), dabs(G.cd)), dmax(dabs(G.cr1), dabs(G.cr2))));
-        th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
-        sum_y += dabs(Qv.yr1) + dabs(Qv.yr2) + Qv.vd + (SDV ? dabs(Qv.yn) : Qv.vn);
-        sum_z += Qv.vd + (SDV ? 0.0 : Qv.vn);
-        {
-          const double cp = (Qv.sd - P.dmin) * Qv.vd;
-          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-          lacc.add(Qv.sd - P.dmin);
-        }
-        if (!SDV) {
-          const double cp = (1.0 - Qv.sn) * Qv.vn;
-          cmax = dmax(cmax, cp); cmin = dmin_(cmin, cp);
-          lacc.add(1.0 - Qv.sn);
-        }
-      } else if (SDV) {
-        fobj += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
-      }
-      if (do_asm) {
-        const int piv = choose_pivot<VM, SDV>(R, G);
-        if (piv != 0) {
-          swap_rows(R, Qv, piv);
-          obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
-        }
-        double Sxx[6], rx3[3];
-        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, CTX_O(C).dc, Sxx, rx3, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP);
-        if (pose_free) {
-          RIC(RQ + sym_idx<NYV>(IX, IX), k) += Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += Sxx[2];
-          RIC(RQ + sym_idx<NYV>(IY, IY), k) += Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += Sxx[5];
-          RIC(Rq + IX, k) += rx3[0]; RIC(Rq + IY, k) += rx3[1]; RIC(Rq + IP, k) += rx3[2];
-        }
-      }
-    }
     // ---- (D) time-scale variable: objective (N+1)(0.5 t + t^2) (:89) and its (N+1) bound pairs ----
     if (k == 0 && !fix) {
       const double m = (double)(N + 1);
@@ -589,16 +600,6 @@ struct ParkSolver {
     if (do_err && pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
     out.e_dual = e_dual; out.e_pr = e_pr; out.cmax = cmax; out.cmin = cmin; out.sy = sum_y; out.sz = sum_z;
     out.th = th; out.phi = phi + fobj; out.rt = rz_t; out.f = fobj; out.ok = ok;
-    if (do_asm) {
-      if (has_u) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          RIC(RDYN + 5 * i + 0, k) = dyn.fx[i][0]; RIC(RDYN + 5 * i + 1, k) = dyn.fx[i][1]; RIC(RDYN + 5 * i + 2, k) = dyn.ft[i];
-          RIC(RDYN + 5 * i + 3, k) = dyn.fu[i][0]; RIC(RDYN + 5 * i + 4, k) = dyn.fu[i][1];
-          RIC(RR4 + i, k) = r4[i];
-        }
-      }
-    }
   }
 
   // ---------------------------------------------------------------------------------------------------
@@ -875,9 +876,16 @@ struct ParkSolver {
   }
 #endif
 
-  // fraction-to-the-boundary helpers
-  OBCA_HD static void ftb(double gap, double dgap, double tau, double& amax) {
-    if (dgap < 0.0) amax = dmin_(amax, -tau * gap * rcp(dgap));
+  // fraction-to-the-boundary helpers.  The largest step keeping every gap at (1 - tau) of its value is
+  // tau * min_i gap_i / (-dgap_i) over the shrinking gaps; the minimum is tracked as a fraction g/d and compared by
+  // cross-multiplication (all gaps and -dgap are positive), so that ONE division per stage replaces one per bound.
+  struct Ftb {
+    double g, d;
+    OBCA_HD Ftb() : g(1.0), d(0.0) {}
+    OBCA_HD double alpha(double tau) const { return d > 0.0 ? dmin_(1.0, tau * g / d) : 1.0; }
+  };
+  OBCA_HD static void ftb(double gap, double dgap, double, Ftb& a) {
+    if (dgap < 0.0 && gap * a.d < a.g * -dgap) { a.g = gap; a.d = -dgap; }
   }
   // dual step of a bound multiplier z with primal gap `gap` whose gap moves by dgap
   OBCA_HD static double dzb(double z, double gap, double dgap, double mu_b) { return (mu_b - z * dgap) * rcp(gap) - z; }
@@ -897,7 +905,8 @@ struct ParkSolver {
     const double dX = WA(dX, k), dY = WA(dY, k), dP = WA(dPS, k), dV = WA(dVL, k);
     double sn_, cs_;
     sincos(ps, &sn_, &cs_);
-    double apr = 1.0, adu = 1.0, dphi = 0.0;
+    Ftb apr, adu;
+    double dphi = 0.0;
     if (k < N) {
       // new multiplier of the dynamics row k:  pi+ = -(P_{k+1} s_{k+1} + p_{k+1})_x   (costate of the Riccati sweep)
       double sn[NSV];
@@ -1020,7 +1029,7 @@ struct ParkSolver {
       ftb(S.zTU, dzb(S.zTU, gu, -S.dt, mu_b), tau, adu);
       dphi += m * (0.5 + 2.0 * t - mu_b * rcp(gl) + mu_b * rcp(gu)) * S.dt;
     }
-    out.apr = apr; out.adu = adu; out.dphi = dphi;
+    out.apr = apr.alpha(tau); out.adu = adu.alpha(tau); out.dphi = dphi;
   }
 
   // ---------------------------------------------------------------------------------------------------

@@ -281,3 +281,23 @@ def test_phased_equals_persistent(P, variant, fix):
         assert (r["exitflag"] == ref["exitflag"]).all(), name
         for key in ("xp", "up", "ts", "lp", "np"):
             assert np.array_equal(r[key], ref[key]), (name, key, float(np.abs(r[key] - ref[key]).max()))
+
+
+def test_chunked_batches_equal_unchunked(P):
+    """Large batches are solved chunk by chunk (OBCA_CHUNK problems at a time): same outputs as one pass."""
+    from obca_b200 import scenarios
+    sc = scenarios.reverse_parking_batch(250, 80, seed=6)
+    old = os.environ.get("OBCA_CHUNK")
+    try:
+        os.environ.pop("OBCA_CHUNK", None)
+        a = solve(P, sc)
+        os.environ["OBCA_CHUNK"] = "96"
+        b = solve(P, sc)
+    finally:
+        if old is None:
+            os.environ.pop("OBCA_CHUNK", None)
+        else:
+            os.environ["OBCA_CHUNK"] = old
+    assert a["exitflag"].sum() >= 240
+    for key in ("xp", "up", "ts", "lp", "np", "iters", "exitflag"):
+        assert np.array_equal(a[key], b[key]), key
