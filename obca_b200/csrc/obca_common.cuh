@@ -101,6 +101,22 @@ struct LogAcc {
   OBCA_HD double total() { if (n) { sum += log(prod); prod = 1.0; n = 0; } return sum; }
 };
 
+#if defined(__CUDACC__)
+// Ampere-style asynchronous global -> shared copies (LDGSTS): the sweeps stream their per-stage data through small
+// shared-memory rings so that the HBM / L2 latency of stage k-1 hides behind the arithmetic of stage k.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#endif
+
 // packed upper-triangular index for an n x n symmetric matrix, i <= j
 template <int N>
 OBCA_HD constexpr int sym_idx(int i, int j) { return i * N - (i * (i - 1)) / 2 + (j - i); }

@@ -230,6 +230,7 @@ struct QBatchPtrs {
   int *exitflag, *iters;
   double* kkt_err;
   int B;
+  unsigned long long* prof;   // 8 per-phase cycle counters summed over the batch (see obca_last_profile)
 };
 
 template <bool SDV>
@@ -271,6 +272,8 @@ k_quad_solve(const __grid_constant__ QuadProblem P, const __grid_constant__ IpmO
       int ef = S.status == 1 ? 1 : 0;
       if (SDV && ef == 1 && tot > 1e-3) ef = 2;      // sum-slack gate, QuadcopterSignedDist.jl:283-288
       bp.exitflag[b] = ef; bp.iters[b] = S.iters; bp.kkt_err[b] = S.e0;
+      if (bp.prof)
+        for (int i = 0; i < 8; ++i) atomicAdd(bp.prof + i, (unsigned long long)S.prof[i]);
     }
     __syncthreads();
   }
@@ -815,7 +818,8 @@ int obca_quadcopter_solve_batch(int B, int N, const double* x0, const double* xF
   CK(cudaMemcpyAsync(dW, xWS, nx * 8, cudaMemcpyHostToDevice, st));
   QBatchPtrs bp;
   bp.x0 = d0; bp.xF = dF; bp.xWS = dW; bp.timeWS = timeWS; bp.xp = dxp; bp.up = dup; bp.ts = dts; bp.lp = dlp; bp.slack = dsl;
-  bp.exitflag = di; bp.iters = di + B; bp.kkt_err = derr; bp.B = B;
+  bp.exitflag = di; bp.iters = di + B; bp.kkt_err = derr; bp.B = B; bp.prof = c->prof;
+  CK(cudaMemsetAsync(c->prof, 0, 8 * sizeof(unsigned long long), st));
   CK(cudaEventRecord(c->ev0, st));
   rc = signed_dist ? launch_quad<true>(*c, P, O, bp) : launch_quad<false>(*c, P, O, bp);
   if (rc) return rc;
@@ -826,6 +830,7 @@ int obca_quadcopter_solve_batch(int B, int N, const double* x0, const double* xF
   CK(cudaMemcpyAsync(kkt_err, derr, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(exitflag, di, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(iters, di + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(c->prof_host, c->prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));

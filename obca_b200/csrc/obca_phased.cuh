@@ -214,14 +214,6 @@ struct PhasedDriver {
 // ------------------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 // ProbState <-> global memory, cooperatively, as 8-byte words
 static_assert(sizeof(ProbState) % 8 == 0, "ProbState must be a whole number of 8-byte words");
 __device__ __forceinline__ void state_load(ProbState& S, const ProbState* g) {

@@ -491,20 +491,60 @@ struct QuadSolver {
     return 1;
   }
   OBCA_HD static int kkt_host(const QCtx& C) { return kkt_dense(C); }
+  static constexpr int STG_N = QNQ + QNYV + QD_NJ + QNX;     // per-stage data of the sweep: Q 231 | q 21 | Jv 66 | r 12
   static constexpr int SM_P = 0, SM_p = SM_P + QNSV * QNSV, SM_g = SM_p + QNSV, SM_T = SM_g + QNSV, SM_H = SM_T + QNSV * QNYV,
-                       SM_hv = SM_H + QNYV * QNYV, SM_K = SM_hv + QNYV, SM_L = SM_K + QNU * (QNSV + 1), SM_J = SM_L + 16,
-                       SM_r = SM_J + QD_NJ, SM_s = SM_r + QNX, SM_u = SM_s + QNSV, SM_flag = SM_u + QNU, SM_Kall = SM_flag + 1;
+                       SM_hv = SM_H + QNYV * QNYV, SM_K = SM_hv + QNYV, SM_s = SM_K + QNU * (QNSV + 1), SM_u = SM_s + QNSV,
+                       SM_flag = SM_u + QNU, SM_STG = SM_flag + 1 + ((SM_flag + 1) & 1), SM_Kall = SM_STG + 2 * STG_N;
   static constexpr int KROW = QNU * (QNSV + 1);     // 72 gain entries per stage
   OBCA_HD static int smem_doubles(int N) { return SM_Kall + N * KROW; }
   static constexpr bool KKT_BLOCK = true;
 
 #if defined(__CUDA_ARCH__)
   // -------------------------------------------------------------------------------------------------
-  // Device version: the whole CTA cooperates on every stage of the sweep through shared memory (entry-parallel
-  // T = P Phi, H = Q + Phi' T, gains, value-function update; the 4x4 Cholesky is done by thread 0).  Same
-  // arithmetic as kkt_dense().  Shared layout (doubles), QSM_TOTAL in all:
-  //   P 17x17 | p 17 | g 17 | T 17x21 | H 21x21 | hv 21 | K 4x18 | Lc 16 | Jv 66 | r12 12 | s 17 | u 4 | flag 1 | Kall N x 72
+  // Device version: the whole CTA cooperates on every stage of the backward sweep through shared memory (entry-parallel
+  // T = P Phi, H = Q + Phi' T, gains, value-function update), four barriers per stage; the per-stage data (Q, q, the
+  // dynamics Jacobian values and residual: 330 doubles scattered over the [array][stage] workspace) is fetched one
+  // stage ahead with 8-byte cp.async into a double buffer, so no global-memory latency sits inside a stage.  The 4x4
+  // pivot block Huu is factored (LDL', no square roots) redundantly by each of the 18 threads that then solve one
+  // column of the gain.  The forward roll-out is run by warp 0 alone (shuffle-free, two __syncwarp per stage).
+  // Same elimination as kkt_dense(); P is computed for a <= b and mirrored.  Shared layout (doubles):
+  //   P 17x17 | p 17 | g 17 | T 17x21 | H 21x21 | hv 21 | K 4x18 | s 17 | u 4 | flag | stage buffers 2 x 330 | Kall N x 72
   // -------------------------------------------------------------------------------------------------
+  // ---- statically unrolled pieces of the sweep: Phi's sparsity (generated tables) is folded at compile time ----
+  // T(a, c) for the columns c = G, G+4, ... of one row a of P (held in registers);  G = warp index
+  template <int G>
+  __device__ static __forceinline__ void sweep_T_cols(const double (&Pr)[QNSV], const double* Jv, double* Trow) {
+    constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
+    constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
+    constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
+#pragma unroll
+    for (int c = G; c < QNYV; c += 4) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = CPT[c]; q < CPT[c + 1]; ++q) acc += Pr[JR[CIX[q]]] * Jv[CIX[q]];
+      if (c >= QIU) acc += Pr[QIW + (c - QIU)];
+      if (c == QIT) acc += Pr[QIT];
+      Trow[c] = acc;
+    }
+  }
+  // H(c1, c2) = Q(c1, c2) + Phi(:, c1)' T(:, c2) for the rows c1 = G, G+4, ... and one column c2 (T(:, c2) in registers);
+  // c2 == QNYV stands for the gradient column: hv(c1) = q(c1) + Phi(:, c1)' g
+  template <int G>
+  __device__ static __forceinline__ void sweep_H_rows(const double (&Tc)[QNSV], int c2, const double* Qs, const double* qv,
+                                                      const double* Jv, double* H, double* hv) {
+    constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
+    constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
+    constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
+#pragma unroll
+    for (int c1 = G; c1 < QNYV; c1 += 4) {
+      double acc = (c2 < QNYV) ? Qs[c1 <= c2 ? sym_idx<QNYV>(c1, c2) : sym_idx<QNYV>(c2, c1)] : qv[c1];
+#pragma unroll
+      for (int q = CPT[c1]; q < CPT[c1 + 1]; ++q) acc += Jv[CIX[q]] * Tc[JR[CIX[q]]];
+      if (c1 >= QIU) acc += Tc[QIW + (c1 - QIU)];
+      if (c1 == QIT) acc += Tc[QIT];
+      if (c2 < QNYV) H[c1 * QNYV + c2] = acc; else hv[c1] = acc;
+    }
+  }
   __device__ static int kkt_solve_block(const QCtx& C) {
     const QuadProblem& Pp = *C.P;
     ProbState& S = *C.S;
@@ -512,110 +552,136 @@ struct QuadSolver {
     const int tid = threadIdx.x, nt = blockDim.x;
     double* sm = C.tile;
     double *P = sm + SM_P, *p = sm + SM_p, *g = sm + SM_g, *T = sm + SM_T, *H = sm + SM_H, *hv = sm + SM_hv, *K = sm + SM_K,
-           *Lc = sm + SM_L, *Jv = sm + SM_J, *r12 = sm + SM_r, *sv = sm + SM_s, *uv = sm + SM_u, *Kall = sm + SM_Kall;
+           *sv = sm + SM_s, *uv = sm + SM_u, *stg = sm + SM_STG, *Kall = sm + SM_Kall;
     static constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
     static constexpr int JC[QD_NJ] = OBCA_QD_J_COL;
     static constexpr int RPT[QNX + 1] = OBCA_QD_ROW_PTR;
     static constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
     static constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
     const double rho = 1.0 / C.O->dc;
+    const size_t nsp = (size_t)C.L.NSP;
+    const double* const gQ = C.W + (size_t)C.L.QS * nsp;     // QS, qs, JV, R12 are consecutive arrays of the workspace
+    auto prefetch = [&](int k, int buf, int first, int count) {   // elements [first, first+count) of stage k
+      if (k >= 0 && k < N)
+        for (int e = tid; e < count; e += nt) cp_async8(stg + buf * STG_N + first + e, gQ + (size_t)(first + e) * nsp + k);
+      cp_async_commit();
+    };
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    // the (at most two) entries a <= b of the value function this thread updates in every stage
+    int pa[2] = {-1, -1}, pb[2] = {-1, -1};
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * nt;
+      if (e < QNP) {
+        int a = 0, off = e;
+        while (off >= QNSV - a) { off -= QNSV - a; ++a; }
+        pa[i] = a; pb[i] = a + off;
+      }
+    }
     for (int e = tid; e < QNSV * QNSV; e += nt) P[e] = (e / QNSV == e % QNSV && e / QNSV < QNX) ? rho : 0.0;
     for (int a = tid; a < QNSV; a += nt) p[a] = a < QNX ? -QA(PI, a, N - 1) : 0.0;
     if (tid == 0) sm[SM_flag] = 1.0;
-    __syncthreads();
+    prefetch(N - 1, (N - 1) & 1, 0, STG_N);
     for (int k = N - 1; k >= 0; --k) {
-      // rows 0..11 of P_{k+1}, p_{k+1} for the multiplier recovery; stage data into shared memory
+      const double* const Qs = stg + (k & 1) * STG_N;
+      const double* const qv = Qs + QNQ;
+      const double* const Jv = qv + QNYV;
+      const double* const r12 = Jv + QD_NJ;
+      prefetch(k - 1, (k - 1) & 1, 0, STG_N);
+      cp_async_wait<1>();
+      __syncthreads();                     // stage data landed; P, p of stage k+1 final
+      // rows 0..11 of P_{k+1}, p_{k+1} for the multiplier recovery (fire-and-forget stores)
       for (int e = tid; e < QNX * QNSV; e += nt) QA(RP, e, k + 1) = P[e];
-      for (int i = tid; i < QNX; i += nt) { QA(RP, QNX * QNSV + i, k + 1) = p[i]; r12[i] = QA(R12, i, k); }
-      for (int e = tid; e < QD_NJ; e += nt) Jv[e] = QA(JV, e, k);
-      __syncthreads();
-      // g = p + P r~ ;  T = P Phi
-      for (int a = tid; a < QNSV; a += nt) {
-        double acc = p[a];
-        for (int l = 0; l < QNX; ++l) acc += P[a * QNSV + l] * r12[l];
-        g[a] = acc;
-      }
-      for (int e = tid; e < QNSV * QNYV; e += nt) {
-        const int a = e / QNYV, c = e - a * QNYV;
-        double acc = 0.0;
-        for (int q = CPT[c]; q < CPT[c + 1]; ++q) { const int z = CIX[q]; acc += P[a * QNSV + JR[z]] * Jv[z]; }
-        if (c >= QIU) acc += P[a * QNSV + QIW + (c - QIU)];
-        if (c == QIT) acc += P[a * QNSV + QIT];
-        T[e] = acc;
-      }
-      __syncthreads();
-      // H = Q + Phi' T ; hv = q + Phi' g
-      for (int e = tid; e < QNYV * QNYV; e += nt) {
-        const int c1 = e / QNYV, c2 = e - c1 * QNYV;
-        double acc = QA(QS, sym_idx_any<QNYV>(c1, c2), k);
-        for (int q = CPT[c1]; q < CPT[c1 + 1]; ++q) { const int z = CIX[q]; acc += Jv[z] * T[JR[z] * QNYV + c2]; }
-        if (c1 >= QIU) acc += T[(QIW + c1 - QIU) * QNYV + c2];
-        if (c1 == QIT) acc += T[QIT * QNYV + c2];
-        H[e] = acc;
-      }
-      for (int c = tid; c < QNYV; c += nt) {
-        double acc = QA(qs, c, k);
-        for (int q = CPT[c]; q < CPT[c + 1]; ++q) { const int z = CIX[q]; acc += Jv[z] * g[JR[z]]; }
-        if (c >= QIU) acc += g[QIW + c - QIU];
-        if (c == QIT) acc += g[QIT];
-        hv[c] = acc;
+      for (int i = tid; i < QNX; i += nt) QA(RP, QNX * QNSV + i, k + 1) = p[i];
+      // g = p + P r~ ;  T = P Phi:  lane a < 17 of every warp holds row a of P; warp w computes the columns w, w+4, ...
+      if (lane < QNSV) {
+        double Pr[QNSV];
+#pragma unroll
+        for (int l = 0; l < QNSV; ++l) Pr[l] = P[lane * QNSV + l];
+        for (int gi = warp; gi < 4; gi += nwarp) {
+          if (gi == 0) {
+            double acc = p[lane];
+#pragma unroll
+            for (int l = 0; l < QNX; ++l) acc += Pr[l] * r12[l];
+            g[lane] = acc;
+            sweep_T_cols<0>(Pr, Jv, T + lane * QNYV);
+          } else if (gi == 1) sweep_T_cols<1>(Pr, Jv, T + lane * QNYV);
+          else if (gi == 2) sweep_T_cols<2>(Pr, Jv, T + lane * QNYV);
+          else sweep_T_cols<3>(Pr, Jv, T + lane * QNYV);
+        }
       }
       __syncthreads();
-      // Cholesky of Huu (4x4)
-      if (tid == 0) {
+      // H = Q + Phi' T ; hv = q + Phi' g:  lane c2 <= 21 holds column c2 of T (21: g); warp w computes the rows w, w+4, ...
+      if (lane <= QNYV) {
+        double Tc[QNSV];
+#pragma unroll
+        for (int l = 0; l < QNSV; ++l) Tc[l] = (lane < QNYV) ? T[l * QNYV + lane] : g[l];
+        for (int gi = warp; gi < 4; gi += nwarp) {
+          if (gi == 0) sweep_H_rows<0>(Tc, lane, Qs, qv, Jv, H, hv);
+          else if (gi == 1) sweep_H_rows<1>(Tc, lane, Qs, qv, Jv, H, hv);
+          else if (gi == 2) sweep_H_rows<2>(Tc, lane, Qs, qv, Jv, H, hv);
+          else sweep_H_rows<3>(Tc, lane, Qs, qv, Jv, H, hv);
+        }
+      }
+      __syncthreads();
+      // K = -Huu^{-1} [Hus | hu]: column c = 0..17, one thread per column, each with its own LDL' of Huu
+      if (tid <= QNSV) {
+        const int c = tid;
+        double Lm[QNU][QNU], dd[QNU], di[QNU];      // unit lower factor, pivots d and 1/d
         int ok = 1;
-        for (int a = 0; a < QNU; ++a)
-          for (int b = 0; b <= a; ++b) {
+#pragma unroll
+        for (int a = 0; a < QNU; ++a) {
+#pragma unroll
+          for (int b = 0; b < a; ++b) {
             double acc = H[(QIU + a) * QNYV + QIU + b];
-            for (int l = 0; l < b; ++l) acc -= Lc[a * 4 + l] * Lc[b * 4 + l];
-            if (a == b) { if (!(acc > 0.0)) { ok = 0; acc = 1e300; } Lc[a * 4 + a] = sqrt(acc); }
-            else Lc[a * 4 + b] = acc / Lc[b * 4 + b];
+#pragma unroll
+            for (int l = 0; l < b; ++l) acc -= Lm[a][l] * Lm[b][l] * dd[l];
+            Lm[a][b] = acc * di[b];
           }
-        if (!ok) sm[SM_flag] = 0.0;
-      }
-      __syncthreads();
-      if (sm[SM_flag] == 0.0) return 0;
-      // K = -Huu^{-1} [Hus | hu]   (column c = 0..17, one thread per column)
-      for (int c = tid; c <= QNSV; c += nt) {
+          double d = H[(QIU + a) * QNYV + QIU + a];
+#pragma unroll
+          for (int l = 0; l < a; ++l) d -= Lm[a][l] * Lm[a][l] * dd[l];
+          if (!(d > 0.0)) { ok = 0; d = 1e300; }
+          dd[a] = d; di[a] = 1.0 / d;
+        }
+        if (!ok && tid == 0) sm[SM_flag] = 0.0;
         double y4[QNU], k4[QNU];
+#pragma unroll
         for (int a = 0; a < QNU; ++a) {
           double acc = c < QNSV ? H[(QIU + a) * QNYV + c] : hv[QIU + a];
-          for (int l = 0; l < a; ++l) acc -= Lc[a * 4 + l] * y4[l];
-          y4[a] = acc / Lc[a * 4 + a];
+#pragma unroll
+          for (int l = 0; l < a; ++l) acc -= Lm[a][l] * y4[l];
+          y4[a] = acc;
         }
+#pragma unroll
         for (int a = QNU - 1; a >= 0; --a) {
-          double acc = y4[a];
-          for (int l = a + 1; l < QNU; ++l) acc -= Lc[l * 4 + a] * k4[l];
-          k4[a] = acc / Lc[a * 4 + a];
+          double acc = y4[a] * di[a];
+#pragma unroll
+          for (int l = a + 1; l < QNU; ++l) acc -= Lm[l][a] * k4[l];
+          k4[a] = acc;
         }
+#pragma unroll
         for (int a = 0; a < QNU; ++a) { K[a * (QNSV + 1) + c] = -k4[a]; Kall[k * KROW + a * (QNSV + 1) + c] = -k4[a]; }
       }
       __syncthreads();
-      // value function of stage k
-      for (int e = tid; e < QNSV * QNSV; e += nt) {
-        const int a = e / QNSV, b = e - a * QNSV;
+      if (sm[SM_flag] == 0.0) { cp_async_wait<0>(); return 0; }
+      // value function of stage k (a <= b, mirrored); the barrier at the top of the next stage publishes it
+      for (int i = 0; i < 2; ++i) {
+        const int a = pa[i], b = pb[i];
+        if (a < 0) continue;
         double v = H[a * QNYV + b];
+#pragma unroll
         for (int l = 0; l < QNU; ++l) v += H[a * QNYV + QIU + l] * K[l * (QNSV + 1) + b];
-        P[e] = v;
+        P[a * QNSV + b] = v; P[b * QNSV + a] = v;
       }
       for (int a = tid; a < QNSV; a += nt) {
         double acc = hv[a];
+#pragma unroll
         for (int l = 0; l < QNU; ++l) acc += H[a * QNYV + QIU + l] * K[l * (QNSV + 1) + QNSV];
         p[a] = acc;
       }
-      __syncthreads();
-      // symmetrise (the entry-parallel update computes P(a,b) and P(b,a) separately)
-      for (int e = tid; e < QNSV * QNSV; e += nt) {
-        const int a = e / QNSV, b = e - a * QNSV;
-        if (a < b) { const double v = 0.5 * (P[e] + P[b * QNSV + a]); T[e] = v; }
-      }
-      __syncthreads();
-      for (int e = tid; e < QNSV * QNSV; e += nt) {
-        const int a = e / QNSV, b = e - a * QNSV;
-        if (a < b) { P[e] = T[e]; P[b * QNSV + a] = T[e]; }
-      }
-      __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
     // root
     if (tid == 0) {
       const double ptt = P[QIT * QNSV + QIT];
@@ -624,33 +690,47 @@ struct QuadSolver {
     }
     __syncthreads();
     if (sm[SM_flag] == 0.0) return 0;
-    // forward roll-out (2 barriers per stage)
-    for (int a = tid; a < QNSV; a += nt) sv[a] = (a == QIT) ? S.dt : 0.0;
-    __syncthreads();
-    for (int k = 0; k < N; ++k) {
-      if (tid < QNU) {
-        const double* kr = Kall + k * KROW + tid * (QNSV + 1);
-        double acc = kr[QNSV];
-        for (int c = 0; c < QNSV; ++c) acc += kr[c] * sv[c];
-        uv[tid] = acc;
-        QA(dU, tid, k) = acc;
+    // forward roll-out: warp 0 alone; Jv and r of the next stage are prefetched while the current one is applied
+    if (tid < 32) {
+      const int lane = tid;
+      constexpr int FW0 = QNQ + QNYV, FWN = QD_NJ + QNX;       // Jv | r
+      auto pf = [&](int k, int buf) {
+        if (k < N)
+          for (int e = lane; e < FWN; e += 32) cp_async8(stg + buf * STG_N + FW0 + e, gQ + (size_t)(FW0 + e) * nsp + k);
+        cp_async_commit();
+      };
+      if (lane < QNSV) sv[lane] = (lane == QIT) ? S.dt : 0.0;
+      pf(0, 0);
+      __syncwarp();
+      for (int k = 0; k < N; ++k) {
+        pf(k + 1, (k + 1) & 1);
+        if (lane < QNU) {
+          const double* kr = Kall + k * KROW + lane * (QNSV + 1);
+          double acc = kr[QNSV];
+#pragma unroll
+          for (int c = 0; c < QNSV; ++c) acc += kr[c] * sv[c];
+          uv[lane] = acc;
+          QA(dU, lane, k) = acc;
+        }
+        cp_async_wait<1>();
+        __syncwarp();
+        const double* const Jv = stg + (k & 1) * STG_N + FW0;
+        const double* const r12 = Jv + QD_NJ;
+        double snv = 0.0;
+        if (lane < QNX) {
+          snv = r12[lane];
+          for (int q = RPT[lane]; q < RPT[lane + 1]; ++q) { const int c = JC[q]; snv += Jv[q] * (c < QNSV ? sv[c] : uv[c - QIU]); }
+          if (k + 1 < N) QA(dX, lane, k + 1) = snv; else S.eNq[lane] = snv;
+        }
+        __syncwarp();
+        if (lane < QNX) sv[lane] = snv;
+        else if (lane < QNX + QNU) sv[lane] = uv[lane - QNX];
+        __syncwarp();
       }
-      for (int e = tid; e < QD_NJ; e += nt) Jv[e] = QA(JV, e, k);
-      for (int i = tid; i < QNX; i += nt) r12[i] = QA(R12, i, k);
-      __syncthreads();
-      double snv = 0.0;
-      if (tid < QNX) {
-        snv = r12[tid];
-        for (int q = RPT[tid]; q < RPT[tid + 1]; ++q) { const int c = JC[q]; snv += Jv[q] * (c < QNSV ? sv[c] : uv[c - QIU]); }
-        if (k + 1 < N) QA(dX, tid, k + 1) = snv; else S.eNq[tid] = snv;
-      }
-      __syncthreads();
-      if (tid < QNX) sv[tid] = snv;
-      else if (tid < QNX + QNU) sv[tid] = uv[tid - QNX];
-      __syncthreads();
+      cp_async_wait<0>();
+      for (int i = lane; i < QNX; i += 32) { QA(dX, i, 0) = 0.0; QA(dX, i, N) = 0.0; }
+      if (lane < QNU) QA(dU, lane, N) = 0.0;
     }
-    for (int i = tid; i < QNX; i += nt) { QA(dX, i, 0) = 0.0; QA(dX, i, N) = 0.0; }
-    for (int a = tid; a < QNU; a += nt) QA(dU, a, N) = 0.0;
     __syncthreads();
     return 1;
   }
