@@ -37,6 +37,7 @@ N_HORIZON = 80
 WORKLOAD = "reverse-parking SD var-time, N=80, 3 obstacles vOb=[2,2,1] (BASELINE config 2)"
 # fused K1 (J/H never reach HBM): 8*(2n+2m+n_par), n=2185, m=1460, n_par=243
 ALG_BYTES_PER_EVAL = 8 * (2 * 2185 + 2 * 1460 + 243)
+NCU_TRAFFIC_PHASEA_FULL_LAUNCH = 468033280 + 942673152     # bytes, profiles/ncu_summary_r01.md (k_pk_phaseA<2,1>)
 
 
 def peaks():
@@ -329,6 +330,21 @@ def gpu_arm(args):
             tot = sum(kms) or 1.0
             line["kernel_share"] = {n: round(kms[i] / tot, 4) for i, n in enumerate(names)}
             line["kernel_ms_serialised"] = {n: round(kms[i], 3) for i, n in enumerate(names)}
+            pr = (C.c_ulonglong * 8)()
+            if lib.obca_last_profile(C.c_int(local), pr) == 0 and pr[7] > 0 and kms[0] > 0 and rnd.value > 0:
+                # dominant kernel: the fused K1 kernel of the rounds.  Algorithmic bytes = 60 264 B per problem per evaluation
+                # (fused variant) x the evaluations the kernel ran (device counter), over its event-timed launches.
+                ev_a = int(pr[7])
+                ach = ev_a * ALG_BYTES_PER_EVAL / (kms[0] * 1e-3) / 1e9
+                line["roofline_solve"] = line["roofline"]
+                line["roofline"] = {"bound": "hbm", "kernel": "k_pk_phaseA<2,true>", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                                    "frac": ach / hbm, "traffic": NCU_TRAFFIC_PHASEA_FULL_LAUNCH,
+                                    "launches": rnd.value, "ms_per_launch": kms[0] / rnd.value, "evaluations": ev_a,
+                                    "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x {ev_a} K1 evaluations inside the {rnd.value} launches of "
+                                            f"one solve (device counter) / their summed CUDA-event time; peak {how}; traffic = dram read+write of "
+                                            "one launch with all 4096 problems active (ncu --set full, profiles/ncu_summary_r01.md: 0.47 + 0.94 GB "
+                                            "for 4096 x 1.44 evaluations = 4x the algorithmic bytes: local factors and stage slots cross HBM between "
+                                            "the phase kernels); the kernel is latency bound (issue 16 %), see DESIGN.md section 5"}
     prof = (C.c_ulonglong * 8)()
     if lib.obca_last_profile(C.c_int(local), prof) == 0 and sum(prof[i] for i in range(6)) > 0:
         names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]

@@ -127,8 +127,9 @@ int obca_check_quadcopter(int B, int N, const double* x, const double* u, const 
 
 /* Per-phase device cycle counters of the last obca_parking_solve_batch[_dev] on `device`, summed over the batch
  * (thread 0 of every CTA, clock64): out8 = {eval (K1), kkt (K3), recover, merit, update, serial sections,
- * #merit evaluations, #K1 evaluations}.  Only the monolithic kernel (OBCA_MODE=3) fills them; zeros otherwise.
- * Diagnostic only. */
+ * #merit evaluations, #K1 evaluations}.  The cycle counters are filled by the monolithic kernel (OBCA_MODE=3) and by the
+ * quadcopter kernel; the default phase-split schedule reports only out8[7] = K1 evaluations inside the assemble
+ * kernel launches and out8[6] = K1 evaluations inside the tail kernel.  Diagnostic only. */
 int obca_last_profile(int device, unsigned long long* out8);
 
 /* How the last obca_parking_solve_batch[_dev] on `device` was scheduled (last chunk of the batch): number of

@@ -82,7 +82,14 @@ OBCA_HD IpmOpts default_opts() {
 // denominator.  (A single-precision-seeded Newton reciprocal was measured on B200 and was SLOWER than the IEEE
 // division here: the solver kernel is instruction-fetch / issue bound and the inline range checks cost more than
 // nvcc's own division fast path.)
+#if defined(__CUDA_ARCH__) && defined(OBCA_RCP_CALL)
+// one out-of-line copy of the IEEE division: the solver kernels are instruction-fetch bound (their straight-line code
+// is several hundred KB), and every inlined division is ~25 instructions plus a slow path
+__device__ __noinline__ double rcp_call(double x) { return 1.0 / x; }
+OBCA_HD double rcp(double x) { return rcp_call(x); }
+#else
 OBCA_HD double rcp(double x) { return 1.0 / x; }
+#endif
 
 OBCA_HD double dmax(double a, double b) { return a > b ? a : b; }
 OBCA_HD double dmin_(double a, double b) { return a < b ? a : b; }

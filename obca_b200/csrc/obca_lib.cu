@@ -233,8 +233,11 @@ struct QBatchPtrs {
   unsigned long long* prof;   // 8 per-phase cycle counters summed over the batch (see obca_last_profile)
 };
 
+#ifndef OBCA_MINB_Q
+#define OBCA_MINB_Q 2
+#endif
 template <bool SDV>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, OBCA_MINB_Q)
 k_quad_solve(const __grid_constant__ QuadProblem P, const __grid_constant__ IpmOpts O, const QLay L, const QBatchPtrs bp,
              double* __restrict__ Wall, int* __restrict__ counter) {
   extern __shared__ double s_kkt[];      // QuadSolver::smem_doubles(N): block-cooperative KKT sweep

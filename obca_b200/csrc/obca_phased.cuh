@@ -57,7 +57,7 @@ struct PhasedDriver {
       part_init(ep);
       OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, false, true, e1); part_merge(ep, e1); }
       OBCA_REDUCE(ep);
-      OBCA_SERIAL { S.ok = ep.ok; S.phase = PH_KKT; }
+      OBCA_SERIAL { S.ok = ep.ok; S.phase = PH_KKT; S.prof[7]++; }
       OBCA_SYNC();
       return;
     }
@@ -86,6 +86,7 @@ struct PhasedDriver {
     OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
     OBCA_REDUCE(ep);
     OBCA_SERIAL {
+      S.prof[7]++;
       D::apply_errors(C, ep);
       S.ok = ep.ok;
       if (S.first) {
@@ -116,7 +117,7 @@ struct PhasedDriver {
       part_init(ep);
       OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
       OBCA_REDUCE(ep);
-      OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; }
+      OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; }
       OBCA_SYNC();
     }
   }
@@ -344,6 +345,7 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   const int NS = P.N + 1;
   if (fresh) state_fresh(S); else state_load(S, Sg + b);
   __syncthreads();
+  if (threadIdx.x == 0) S.prof[7] = 0;      // K1 evaluations of this launch (diagnostic counter, see obca_last_profile)
   // the context is identical for every thread: one copy in shared memory (not one per thread in local memory)
   __shared__ PkCtx C; __shared__ PkOutputs out;
   if (threadIdx.x == 0) {
@@ -360,7 +362,10 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
     }
   }
   state_store(Sg + b, S);
-  if (threadIdx.x == 0 && S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
+  if (threadIdx.x == 0) {
+    if (bp.prof) atomicAdd(bp.prof + 7, (unsigned long long)S.prof[7]);
+    if (S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -544,6 +549,7 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
     const int b = fresh ? i : act[i];
     if (fresh) state_fresh(S); else state_load(S, Sg + b);
     if (threadIdx.x == 0) {
+      S.prof[7] = 0;
       pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
       C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
     }
@@ -560,6 +566,7 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
       __syncthreads();
       if (S.phase == PH_RECOVER) PhasedDriver<PS>::phase_C(C);
     }
+    if (threadIdx.x == 0 && bp.prof) atomicAdd(bp.prof + 6, (unsigned long long)S.prof[7]);
     __syncthreads();
   }
 }

@@ -641,7 +641,7 @@ struct QuadSolver {
 #pragma unroll
           for (int l = 0; l < a; ++l) d -= Lm[a][l] * Lm[a][l] * dd[l];
           if (!(d > 0.0)) { ok = 0; d = 1e300; }
-          dd[a] = d; di[a] = 1.0 / d;
+          dd[a] = d; di[a] = __drcp_rn(d);
         }
         if (!ok && tid == 0) sm[SM_flag] = 0.0;
         double y4[QNU], k4[QNU];
