@@ -317,16 +317,17 @@ def gpu_arm(args):
                            "frac": k1_gbs / hbm, "traffic": None, "ms_per_launch": k1_ms,
                            "note": f"stand-alone fused K1: 8*(2n+2m+3(N+1)) = {int(k1_bytes / B)} B/problem/evaluation, B={B}; working set "
                                    f"{k1_bytes / 1e6:.0f} MB > L2; mean of 20 back-to-back launches"}
-    rnd = C.c_int(0); hand = C.c_int(0); kms = (C.c_double * 4)()
+    rnd = C.c_int(0); hand = C.c_int(0); kms = (C.c_double * 5)()
     if lib.obca_last_schedule(C.c_int(local), C.byref(rnd), C.byref(hand), None) == 0:
         line["config"]["schedule"] = {"phase_split_rounds": rnd.value, "handed_to_tail_kernel": hand.value}
-        line["gpu_launches"] = args.steps * (1 + 3 * rnd.value + (1 if hand.value > 0 else 0)) * 2    # device arm + e2e arm
+        line["gpu_launches"] = args.steps * (2 + 6 * rnd.value + (1 if hand.value > 0 else 0)) * 2    # device arm + e2e arm
         # one extra, untimed solve with per-kernel events: which kernel dominates the step
         os.environ["OBCA_PHASE_TIMING"] = "1"
         step_dev()
         os.environ.pop("OBCA_PHASE_TIMING", None)
         if lib.obca_last_schedule(C.c_int(local), None, None, kms) == 0:
-            names = ["k_pk_phaseA (K1 assemble)", "k_pk_sweep (K3 KKT)", "k_pk_phaseC (K4 line search)", "k_pk_tail (persistent, all phases)"]
+            names = ["k_pk_block (K1 constraint blocks, pass 1)", "k_pk_phaseA (K1 stage terms + assemble; + pass 2)", "k_pk_sweep (K3 KKT)",
+                     "k_pk_phaseC (K4 line search + update)", "k_pk_tail (persistent, all phases)"]
             tot = sum(kms) or 1.0
             line["kernel_share"] = {n: round(kms[i] / tot, 4) for i, n in enumerate(names)}
             line["kernel_ms_serialised"] = {n: round(kms[i], 3) for i, n in enumerate(names)}

@@ -136,11 +136,11 @@ int obca_last_profile(int device, unsigned long long* out8);
  * phase-split rounds ([assemble, sweep, line-search] kernel triples over all active problems) and the number of
  * problems handed to the persistent tail kernel afterwards (= the batch size when no rounds were run).  Environment
  * overrides for experiments: OBCA_MODE (0 auto, 1 tail kernel only, 2 rounds always, 3 monolithic kernel),
- * OBCA_TAIL_THRESH (hand-over point), OBCA_CHUNK (problems per chunk).  kernel_ms4 (may be NULL): with
+ * OBCA_TAIL_THRESH (hand-over point), OBCA_CHUNK (problems per chunk).  kernel_ms5 (may be NULL): with
  * OBCA_PHASE_TIMING=1 in the environment the solve records CUDA events around every kernel (this serialises the
- * host loop, so the solve itself runs slower) and reports the summed times of {assemble kernel, sweep kernel,
- * line-search kernel, tail kernel} in milliseconds.  Diagnostic only. */
-int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms4);
+ * host loop, so the solve itself runs slower) and reports the summed times of {block kernel (pass 1), assemble kernel
+ * (+ second pass), sweep kernel, line-search kernel, tail kernel} in milliseconds.  Diagnostic only. */
+int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms5);
 
 /* K1 stand-alone: fused evaluation of the parking NLP in the REFERENCE's formulation at B given points (no solve);
  * what JuMP's eval_g / eval_grad_f / eval_jac_g' * y do for Ipopt (ParkingSignedDist.jl:240), one thread per

@@ -50,7 +50,7 @@ k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ I
     const int b = s_b;
     if (b >= bp.B) break;
     PkCtx C;
-    C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
+    C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.bo = nullptr; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
     C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
     C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
     C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
@@ -333,11 +333,12 @@ struct DevCtx {
   double* slots = nullptr; size_t slots_bytes = 0;  // stage slots of every problem, B x (N+1) x GSTRIDE
   char* pstate = nullptr; size_t pstate_bytes = 0;  // ProbState per problem
   int* act = nullptr; size_t act_bytes = 0;         // two active lists
+  double* bo = nullptr; size_t bo_bytes = 0;        // block hand-over records, B x nOb x BO_N x NSP
   int* ncnt = nullptr;                              // device: n[0], n[1] (active counts), [2] tail work counter
   int* h_n = nullptr;                               // pinned ring of active counts read back per round
   cudaEvent_t evr[16] = {nullptr};
   int last_rounds = 0, last_tail = 0;
-  double phase_ms[4] = {0, 0, 0, 0};                // OBCA_PHASE_TIMING=1: summed event times of K_A, K_B, K_C, tail
+  double phase_ms[5] = {0, 0, 0, 0, 0};                // OBCA_PHASE_TIMING=1: summed event times of K_A, K_B, K_C, tail
   std::mutex mu;
 };
 static DevCtx g_dev[64];
@@ -469,16 +470,31 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
   rc = ensure((void**)&c.act, &c.act_bytes, 2 * (size_t)B * sizeof(int));
   if (rc) return rc;
   int* act[2] = {c.act, c.act + B};
-  int cur = 0, fresh = 1, n_bound = B, done_r = 0, r = 0;
+  rc = ensure((void**)&c.bo, &c.bo_bytes, (size_t)B * P.nOb * BO_N * L.NSP * sizeof(double));
+  if (rc) return rc;
+  int cur = 0, n_bound = B, done_r = 0, r = 0;
   const int max_rounds = 8 * (O.max_iter + 8);
   const bool timing = env_int("OBCA_PHASE_TIMING", 0) != 0;      // development: per-kernel event times, summed per solve
   std::vector<cudaEvent_t> tev;
   auto mark = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  const int per = P.nOb * NS;
+  auto blk_grid = [&](int n) { return (int)(((long long)n * per + 127) / 128); };
+  // initial points: the assemble kernel in "fresh" mode only runs the initialisation and leaves every problem in PH_EVAL
+  CK(cudaMemsetAsync(c.ncnt + 1, 0, sizeof(int), st));
+  k_pk_phaseA<VM, SDV><<<B, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, nullptr, c.ncnt, act[1], c.ncnt + 1, 1, 1);
+  CK(cudaGetLastError());
+  cur = 1;
   for (; r < max_rounds; ++r) {
     CK(cudaMemsetAsync(c.ncnt + (1 - cur), 0, sizeof(int), st));
     mark();
-    k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[cur], c.ncnt + cur, act[1 - cur],
-                                                      c.ncnt + (1 - cur), fresh);
+    k_pk_block<VM, SDV><<<blk_grid(n_bound), 128, 0, st>>>(P, L, c.W, c.bo, Sg, act[cur], c.ncnt + cur, 1);
+    mark();
+    k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[cur], c.ncnt + cur, act[1 - cur],
+                                                      c.ncnt + (1 - cur), 0, 1);
+    // second pass for the problems whose barrier parameter was reduced by the first one
+    k_pk_block<VM, SDV><<<blk_grid(n_bound), 128, 0, st>>>(P, L, c.W, c.bo, Sg, act[1 - cur], c.ncnt + (1 - cur), 2);
+    k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[1 - cur], c.ncnt + (1 - cur), nullptr,
+                                                      nullptr, 0, 2);
     mark();
     k_pk_sweep<VM, SDV><<<(n_bound + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
                                                                                               c.ncnt + (1 - cur));
@@ -488,7 +504,7 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c.h_n + (r & 15), c.ncnt + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c.evr[r & 15], st));
-    cur = 1 - cur; fresh = 0;
+    cur = 1 - cur;
     // the active set only shrinks: the count of any completed round bounds every later round
     if (r - done_r >= 8) CK(cudaEventSynchronize(c.evr[done_r & 15]));
     while (done_r <= r && cudaEventQuery(c.evr[done_r & 15]) == cudaSuccess) { n_bound = c.h_n[done_r & 15]; ++done_r; }
@@ -517,7 +533,7 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
     CK(cudaGetLastError());
     if (timing) {
       cudaEventRecord(e1, st); cudaEventSynchronize(e1);
-      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); c.phase_ms[3] = ms;
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); c.phase_ms[4] = ms;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
   }
@@ -878,11 +894,11 @@ int obca_last_profile(int device, unsigned long long* out8) {
   return 0;
 }
 
-int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms4) {
+int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms5) {
   if (device < 0 || device >= 64 || !g_dev[device].init) { set_err("no schedule"); return OBCA_ERR_ARG; }
   if (rounds) *rounds = g_dev[device].last_rounds;
   if (handed_over) *handed_over = g_dev[device].last_tail;
-  if (kernel_ms4) for (int i = 0; i < 4; ++i) kernel_ms4[i] = g_dev[device].phase_ms[i];
+  if (kernel_ms5) for (int i = 0; i < 5; ++i) kernel_ms5[i] = g_dev[device].phase_ms[i];
   return 0;
 }
 

@@ -22,7 +22,7 @@
 
 namespace obca {
 
-enum { PH_INIT = 0, PH_EVAL = 1, PH_UPDATE = 2, PH_REASM = 3, PH_KKT = 4, PH_RECOVER = 5, PH_END = 6, PH_DONE = 7 };
+enum { PH_INIT = 0, PH_EVAL = 1, PH_EVAL2 = 2, PH_REASM = 3, PH_KKT = 4, PH_RECOVER = 5, PH_END = 6, PH_DONE = 7 };
 constexpr int GSTRIDE = 80;   // doubles per stage slot in global memory: RSTRIDE rounded up to a 16-byte multiple
 
 struct BatchPtrs {
@@ -45,8 +45,23 @@ struct PhasedDriver {
   typedef typename M::Ctx Ctx;
   typedef IpmDriver<M> D;
 
-  // A: [init | accept the step] -> evaluate at the new iterate, convergence test, barrier update (+ re-evaluation),
-  //    or re-assembly with a larger delta_w.  Leaves phase = PH_KKT (stage models ready) or PH_END (attempt over).
+  // A: [init] -> evaluate at the current iterate, convergence test, barrier update (+ re-evaluation), or re-assembly
+  //    with a larger delta_w.  Leaves phase = PH_KKT (stage models ready) or PH_END (attempt over).
+  //    BLK (phase-split rounds): the obstacle blocks come from the flat block kernel through C.bo, so an evaluation can only
+  //    run when that kernel has seen the current iterate / barrier parameter: after the initial point the function returns
+  //    with PH_EVAL, after a barrier update with PH_EVAL2, and is called again once the blocks have been refreshed.
+  template <bool BLK>
+  __device__ static void eval_all(const Ctx& C, bool do_err, EvalPart& ep) {
+    const int NS = M::n_stages(C);
+    part_init(ep);
+    OBCA_FOR_STAGES(k, NS) {
+      EvalPart e1;
+      if (BLK) M::stage_eval_blk(C, k, do_err, true, e1); else M::stage_eval(C, k, do_err, true, e1);
+      part_merge(ep, e1);
+    }
+    OBCA_REDUCE(ep);
+  }
+  template <bool BLK>
   __device__ static void phase_A(const Ctx& C) {
     const IpmOpts& O = CTX_O(C);
     ProbState& S = *C.S;
@@ -54,9 +69,7 @@ struct PhasedDriver {
     const int ph = S.phase;
     EvalPart ep;
     if (ph == PH_REASM) {
-      part_init(ep);
-      OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, false, true, e1); part_merge(ep, e1); }
-      OBCA_REDUCE(ep);
+      eval_all<BLK>(C, false, ep);
       OBCA_SERIAL { S.ok = ep.ok; S.phase = PH_KKT; S.prof[7]++; }
       OBCA_SYNC();
       return;
@@ -73,53 +86,50 @@ struct PhasedDriver {
       OBCA_FOR_STAGES(k, NS) M::init_stage(C, k, restart);
       OBCA_SYNC();
       OBCA_FOR_STAGES(k, NS) M::init_slacks(C, k);
+      // (S.phase may only change behind a barrier: every thread read it on entry)
+      OBCA_SERIAL { S.phase = PH_EVAL; }
       OBCA_SYNC();
-    } else if (ph == PH_UPDATE) {
-      OBCA_FOR_STAGES(k, NS) M::update_stage(C, k);
-      OBCA_SERIAL { M::update_scalars(C); S.it++; }
-      OBCA_SYNC();
+      if (BLK) return;
     }
-    // (PH_EVAL: barrier kick -- new direction from the same iterate, `it` already advanced by phase C)
-    OBCA_SERIAL { S.dw = 0.0; }
-    OBCA_SYNC();
-    part_init(ep);
-    OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
-    OBCA_REDUCE(ep);
-    OBCA_SERIAL {
-      S.prof[7]++;
-      D::apply_errors(C, ep);
-      S.ok = ep.ok;
-      if (S.first) {
-        S.theta_max = 1e4 * dmax(1.0, S.th_k);
-        S.theta_min = 1e-4 * dmax(1.0, S.th_k);
-        S.first = 0;
-      }
-      S.e0 = D::err_mu(C, 0.0);
-      S.iters = S.it;
-      S.flag = 0;
-      if (S.e0 <= O.tol && S.e_dual <= O.dual_inf_tol && S.e_pr <= O.constr_viol_tol && S.e_cmax <= O.compl_inf_tol) {
-        S.status = 1; S.flag = 1;
-      } else if (S.it >= O.max_iter) {
-        S.status = 0; S.flag = 1;
-      } else {
-        bool changed = false;
-        while (S.mu > O.mu_min && D::err_mu(C, S.mu) <= O.kappa_eps * S.mu) {
-          S.mu = dmax(O.mu_min, dmin_(O.kappa_mu * S.mu, pow(S.mu, O.theta_mu)));
-          S.tau = dmax(O.tau_min, 1.0 - S.mu);
-          changed = true;
+    if (ph != PH_EVAL2) {
+      // (PH_EVAL: new iterate -- or a barrier kick: new direction from the same iterate)
+      OBCA_SERIAL { S.dw = 0.0; }
+      OBCA_SYNC();
+      eval_all<BLK>(C, true, ep);
+      OBCA_SERIAL {
+        S.prof[7]++;
+        D::apply_errors(C, ep);
+        S.ok = ep.ok;
+        if (S.first) {
+          S.theta_max = 1e4 * dmax(1.0, S.th_k);
+          S.theta_min = 1e-4 * dmax(1.0, S.th_k);
+          S.first = 0;
         }
-        if (changed) { S.nfilt = 0; S.flag = 2; }
+        S.e0 = D::err_mu(C, 0.0);
+        S.iters = S.it;
+        S.flag = 0;
+        if (S.e0 <= O.tol && S.e_dual <= O.dual_inf_tol && S.e_pr <= O.constr_viol_tol && S.e_cmax <= O.compl_inf_tol) {
+          S.status = 1; S.flag = 1;
+        } else if (S.it >= O.max_iter) {
+          S.status = 0; S.flag = 1;
+        } else {
+          bool changed = false;
+          while (S.mu > O.mu_min && D::err_mu(C, S.mu) <= O.kappa_eps * S.mu) {
+            S.mu = dmax(O.mu_min, dmin_(O.kappa_mu * S.mu, pow(S.mu, O.theta_mu)));
+            S.tau = dmax(O.tau_min, 1.0 - S.mu);
+            changed = true;
+          }
+          if (changed) { S.nfilt = 0; S.flag = 2; }
+        }
+        S.phase = (S.flag == 1) ? PH_END : (S.flag == 2 ? PH_EVAL2 : PH_KKT);
       }
-      S.phase = (S.flag == 1) ? PH_END : PH_KKT;
-    }
-    OBCA_SYNC();
-    if (S.flag == 2) {   // mu changed: the barrier terms of the stage models (and phi) are stale
-      part_init(ep);
-      OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
-      OBCA_REDUCE(ep);
-      OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; }
       OBCA_SYNC();
+      if (S.flag != 2 || BLK) return;
     }
+    // mu changed: the barrier terms of the stage models (and phi) are stale
+    eval_all<BLK>(C, true, ep);
+    OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; S.phase = PH_KKT; }
+    OBCA_SYNC();
   }
 
   // B (serial part, one thread, after the sweep): Ipopt's inertia-correction bookkeeping.  `ok`: 1 if every pivot of
@@ -137,8 +147,8 @@ struct PhasedDriver {
     S.phase = ok > 0 ? PH_RECOVER : (ok == 0 ? PH_REASM : PH_END);
   }
 
-  // C: recover the full step, step lengths, filter line search.  Leaves PH_UPDATE (accepted), PH_EVAL (barrier kick)
-  //    or PH_END (line-search failure).
+  // C: recover the full step, step lengths, filter line search, and -- when a step is accepted -- the iterate update.
+  //    Leaves PH_EVAL (new iterate, or barrier kick: same iterate, new barrier parameter) or PH_END (line-search failure).
   __device__ static void phase_C(const Ctx& C) {
     const IpmOpts& O = CTX_O(C);
     ProbState& S = *C.S;
@@ -202,12 +212,17 @@ struct PhasedDriver {
             }
           }
         }
-        if (S.flag == 1) S.phase = PH_UPDATE;
+        if (S.flag == 1) S.phase = PH_EVAL;
         else if (S.flag == -2) { S.it++; S.phase = PH_EVAL; }
         else if (S.flag == -1) S.phase = PH_END;
       }
       OBCA_SYNC();
       if (S.flag != 0) break;
+    }
+    if (S.flag == 1) {      // accept
+      OBCA_FOR_STAGES(k, NS) M::update_stage(C, k);
+      OBCA_SERIAL { M::update_scalars(C); S.it++; }
+      OBCA_SYNC();
     }
   }
 };
@@ -232,7 +247,7 @@ template <int VM, bool SDV>
 __device__ __forceinline__ void pk_make_ctx(PkCtx& C, PkOutputs& out, const ParkProblem& P, const IpmOpts& O, const PkLay& L,
                                             const BatchPtrs& bp, int b, double* W) {
   const int N = P.N, NS = N + 1, V = P.V, nOb = P.nOb;
-  C.P = &P; C.O = &O; C.L = L; C.W = W;
+  C.P = &P; C.O = &O; C.L = L; C.W = W; C.bo = nullptr;
   C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
   C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
   C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
@@ -305,14 +320,15 @@ __device__ void pk_end_of_attempt(const PkCtx& C, const PkOutputs& out, const Ba
   __syncthreads();
 }
 
-// phase A of one problem including the attempt bookkeeping; returns with phase in {PH_KKT, PH_DONE}
-template <int VM, bool SDV>
+// phase A of one problem including the attempt bookkeeping; returns with phase in {PH_KKT, PH_DONE} (BLK: also PH_EVAL /
+// PH_EVAL2 when the block kernel has to run first)
+template <int VM, bool SDV, bool BLK>
 __device__ __forceinline__ void pk_step_A(const PkCtx& C, const PkOutputs& out, const BatchPtrs& bp, int b, PkFinalScratch& F) {
   ProbState& S = *C.S;
   for (;;) {
     if (S.phase == PH_END) pk_end_of_attempt<VM, SDV>(C, out, bp, b, F);
     if (S.phase == PH_DONE) return;
-    PhasedDriver<ParkSolver<VM, SDV> >::phase_A(C);
+    PhasedDriver<ParkSolver<VM, SDV> >::template phase_A<BLK>(C);
     if (S.phase != PH_END) return;
   }
 }
@@ -325,6 +341,52 @@ __device__ __forceinline__ void state_fresh(ProbState& S) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K_blk: the OBCA constraint blocks of K1 as a flat streaming kernel -- one thread per (active problem, obstacle, stage),
+// consecutive threads = consecutive stages, so every warp reads contiguous slices of the stacked (x, lambda, mu, sl, duals)
+// arrays; no shared memory, no barriers.  Each thread evaluates the signed-distance rows of its block, their
+// Lagrangian-gradient / KKT-error pieces, condenses the block onto the stage pose and writes the local factor
+// (workspace) and the 22-double hand-over record read by k_pk_phaseA.  pass 1: new iterates (PH_EVAL) and
+// inertia-correction re-assemblies (PH_REASM); pass 2: problems whose barrier parameter was just reduced (PH_EVAL2).
+// ------------------------------------------------------------------------------------------------------------
+#ifndef OBCA_MINB_BLK
+#define OBCA_MINB_BLK 3
+#endif
+template <int VM, bool SDV>
+__global__ void __launch_bounds__(128, OBCA_MINB_BLK)
+k_pk_block(const __grid_constant__ ParkProblem P, const PkLay L, double* __restrict__ Wall, double* __restrict__ BOall,
+           const ProbState* __restrict__ Sg, const int* __restrict__ act, const int* __restrict__ n_act, int pass) {
+  const int NS = P.N + 1, per = P.nOb * NS;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = (int)(idx / per);
+  if (a >= *n_act) return;
+  const int rem = (int)(idx - (long long)a * per);
+  const int j = rem / NS, k = rem - j * NS;
+  const int b = act[a];
+  const ProbState* S = Sg + b;
+  const int ph = S->phase;
+  bool do_err;
+  double dw;
+  if (pass == 1) {
+    if (ph == PH_EVAL) { do_err = true; dw = 0.0; }
+    else if (ph == PH_REASM) { do_err = false; dw = S->dw; }
+    else return;
+  } else {
+    if (ph != PH_EVAL2) return;
+    do_err = true; dw = 0.0;
+  }
+  const double mu_b = S->mu;
+  PkCtx C;
+  C.W = Wall + (size_t)b * L.total * L.NSP;
+  C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
+  const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
+  double sn_, cs_;
+  sincos(ps, &sn_, &cs_);
+  BlockOut B;
+  ParkSolver<VM, SDV>::block_eval(C, k, j, X, Y, cs_, sn_, mu_b, dw, do_err, true, B);
+  ParkSolver<VM, SDV>::block_store(C, k, j, B);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K_A: one CTA per active problem
 // ------------------------------------------------------------------------------------------------------------
 #ifndef OBCA_MINB_A
@@ -334,8 +396,8 @@ template <int VM, bool SDV>
 __global__ void __launch_bounds__(128, OBCA_MINB_A)
 k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
             double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
-            const int* __restrict__ act_in, const int* __restrict__ n_in, int* __restrict__ act_out, int* __restrict__ n_out,
-            int fresh) {
+            double* __restrict__ BOall, const int* __restrict__ act_in, const int* __restrict__ n_in, int* __restrict__ act_out,
+            int* __restrict__ n_out, int fresh, int pass) {
   extern __shared__ double s_ric[];     // (N+1) x RSTRIDE stage slots, assembled here, streamed out for the sweep kernel
   __shared__ ProbState S;
   __shared__ double s_red[4 * 12];
@@ -343,6 +405,7 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   if ((int)blockIdx.x >= *n_in) return;
   const int b = fresh ? (int)blockIdx.x : act_in[blockIdx.x];
   const int NS = P.N + 1;
+  if (pass == 2 && Sg[b].phase != PH_EVAL2) return;      // second pass of a round: only problems whose barrier parameter changed
   if (fresh) state_fresh(S); else state_load(S, Sg + b);
   __syncthreads();
   if (threadIdx.x == 0) S.prof[7] = 0;      // K1 evaluations of this launch (diagnostic counter, see obca_last_profile)
@@ -351,9 +414,10 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   if (threadIdx.x == 0) {
     pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
     C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+    C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
   }
   __syncthreads();
-  pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
+  pk_step_A<VM, SDV, true>(C, out, bp, b, s_fin);
   if (S.phase == PH_KKT) {
     double* g = slots + (size_t)b * NS * GSTRIDE;
     for (int i = threadIdx.x; i < NS * RSTRIDE; i += blockDim.x) {
@@ -364,7 +428,7 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   state_store(Sg + b, S);
   if (threadIdx.x == 0) {
     if (bp.prof) atomicAdd(bp.prof + 7, (unsigned long long)S.prof[7]);
-    if (S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
+    if (pass == 1 && S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
   }
 }
 
@@ -555,7 +619,7 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
     }
     __syncthreads();
     for (;;) {
-      pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
+      pk_step_A<VM, SDV, false>(C, out, bp, b, s_fin);
       if (S.phase == PH_DONE) break;
       if (threadIdx.x < 32) {
         int ok = S.ok;

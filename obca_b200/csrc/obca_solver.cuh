@@ -103,6 +103,16 @@ __device__ __forceinline__ void block_reduce(T& v, void* scratch) {
 #define OBCA_REDUCE(v)
 #endif
 
+// ---- what one (stage, obstacle) OBCA block contributes to its stage (K1): computed in line by the persistent kernels,
+//      or by the flat block kernel of the phase-split driver, which hands it over through global memory ----
+struct BlockOut {
+  double Sxx[6], rx3[3];   // Schur complement and gradient on the pose (X, Y, psi)      (assembly)
+  double gx[3];            // the block's rows of the Lagrangian gradient on the pose    (errors)
+  double e_dual, e_pr, cmax, cmin, sum_y, sum_z, th, lsum, fobj;   // KKT-error / merit partials; lsum = sum of log(gap)
+  int ok;                  // 1: every local pivot had the sign required for inertia (n, m, 0)
+};
+constexpr int BO_N = 22;   // doubles per block in the global hand-over array (ok stored as a double)
+
 // ---- workspace layout: every entry is an array of NSP doubles indexed by stage ----
 struct PkLay {
   int NSP;
@@ -219,6 +229,7 @@ struct PkCtx {
   PkLay L;
   double* W;
   double* ric;     // (N+1) x RSTRIDE slots
+  double* bo;        // phase-split driver: per-problem block hand-over array, [obstacle][BO_N][NSP]; nullptr otherwise
   const double* pp;  // where recover_stage finds rows 0..3 of P_{k+1} / p_{k+1}: slot base + stride (doubles).  The
   int pps;           // persistent kernel and the emulation keep them in the stage slots (pp = ric, pps = RSTRIDE);
                      // the phase-split driver reads them from the global slot array written by the sweep kernel.
@@ -355,37 +366,20 @@ struct ParkSolver {
   }
 
   // ---------------------------------------------------------------------------------------------------
-  // P1 (K1): fused evaluation at the current iterate.
-  //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
+  // K1, one (stage k, obstacle j) block: residuals / KKT-error partials (do_err) and the condensation of the block onto
+  // the stage pose with the local factor stored in the workspace (do_asm).  (X, Y, cs_, sn_) = pose of the stage.
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD_NI static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
+  OBCA_HD static void block_eval(const PkCtx& C, int k, int j, double X, double Y, double cs_, double sn_, double mu_b,
+                                 double dw, bool do_err, bool do_asm, BlockOut& B) {
     const ParkProblem& P = CTX_P(C);
-    const ProbState& S = *C.S;
-    const int N = P.N;
-    const bool fix = P.fix_time != 0;
-    const double mu_b = S.mu, dw = S.dw;
-    const bool pose_free = (k >= 1 && k <= N - 1);
-    const bool has_u = k < N;
-    const double t = fix ? 1.0 : S.t;
-    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k), v = WA(VL, k);
-    double sn_, cs_;
-    sincos(ps, &sn_, &cs_);
-
-    // the stage model (packed 9x9 Q, q) is accumulated directly in the stage slot (shared memory on the device)
+    double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, fobj = 0.0;
+    LogAcc lacc;
+    B.gx[0] = B.gx[1] = B.gx[2] = 0.0;
+    B.ok = 1;
 #pragma unroll
-    for (int i = 0; i < NQ + NYV; ++i) RIC(RQ + i, k) = 0.0;
-    double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0;
-    double rz_t = 0.0;
-    int ok = 1;
-    LogAcc lacc;   // barrier terms: phi -= mu * sum(log gap)
-    // Lagrangian gradient rows of the pose
-    double rzX = 0.0, rzY = 0.0, rzP = 0.0, rzV = 0.0;
-
-    // Order of the sections: obstacle blocks first, then the state terms, the controls / dynamics last -- the local
-    // elimination of a block needs ~60 doubles in registers, so nothing else big (dynamics Jacobian, residuals) may be
-    // live across it; the dynamics outputs go straight into the stage slot.
-    // ---- (C) obstacle blocks ----
-    for (int j = 0; j < P.nOb; ++j) {
+    for (int i = 0; i < 6; ++i) B.Sxx[i] = 0.0;
+    B.rx3[0] = B.rx3[1] = B.rx3[2] = 0.0;
+    {
       ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
       load_rows(C, j, R);
       load_vars(C, k, j, R, Qv);
@@ -393,7 +387,7 @@ struct ParkSolver {
       if (do_err) {
         double rl[VM], rm[4], rs_, gx[3];
         obs_lagr_grad<VM, SDV>(P, R, Qv, G, rl, rm, rs_, gx);
-        rzX += gx[0]; rzY += gx[1]; rzP += gx[2];
+        B.gx[0] = gx[0]; B.gx[1] = gx[1]; B.gx[2] = gx[2];
 #pragma unroll
         for (int i = 0; i < VM; ++i) {
           if (i < R.v) {
@@ -436,12 +430,99 @@ struct ParkSolver {
           swap_rows(R, Qv, piv);
           obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
         }
-        double Sxx[6], rx3[3];
-        ok &= obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, CTX_O(C).dc, Sxx, rx3, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP);
+        B.ok = obs_condense<VM, SDV>(P, R, Qv, G, mu_b, dw, CTX_O(C).dc, B.Sxx, B.rx3, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP);
+      }
+    }
+    B.e_dual = e_dual; B.e_pr = e_pr; B.cmax = cmax; B.cmin = cmin; B.sum_y = sum_y; B.sum_z = sum_z; B.th = th;
+    B.lsum = do_err ? lacc.total() : 0.0; B.fobj = fobj;
+  }
+  // hand-over of a block through global memory (phase-split driver): [obstacle][field][stage]
+  OBCA_HD static void block_store(const PkCtx& C, int k, int j, const BlockOut& B) {
+    double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
+    const size_t st = CTX_L(C).NSP;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o[i * st] = B.Sxx[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[(6 + i) * st] = B.rx3[i]; o[(9 + i) * st] = B.gx[i]; }
+    o[12 * st] = B.e_dual; o[13 * st] = B.e_pr; o[14 * st] = B.cmax; o[15 * st] = B.cmin; o[16 * st] = B.sum_y;
+    o[17 * st] = B.sum_z; o[18 * st] = B.th; o[19 * st] = B.lsum; o[20 * st] = B.fobj; o[21 * st] = (double)B.ok;
+  }
+  OBCA_HD static void block_load(const PkCtx& C, int k, int j, bool do_err, bool do_asm, BlockOut& B) {
+    const double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
+    const size_t st = CTX_L(C).NSP;
+    if (do_asm) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) B.Sxx[i] = o[i * st];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) B.rx3[i] = o[(6 + i) * st];
+      B.ok = o[21 * st] != 0.0;
+    }
+    if (do_err) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) B.gx[i] = o[(9 + i) * st];
+      B.e_dual = o[12 * st]; B.e_pr = o[13 * st]; B.cmax = o[14 * st]; B.cmin = o[15 * st]; B.sum_y = o[16 * st];
+      B.sum_z = o[17 * st]; B.th = o[18 * st]; B.lsum = o[19 * st];
+    }
+    B.fobj = o[20 * st];
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // P1 (K1): fused evaluation at the current iterate.
+  //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD_NI static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
+    stage_eval_t<false>(C, k, do_err, do_asm, out);
+  }
+  OBCA_HD_NI static void stage_eval_blk(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
+    stage_eval_t<true>(C, k, do_err, do_asm, out);
+  }
+  // BLK: the obstacle blocks were evaluated by the flat block kernel and are read from the hand-over array C.bo
+  template <bool BLK>
+  OBCA_HD static void stage_eval_t(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
+    const ParkProblem& P = CTX_P(C);
+    const ProbState& S = *C.S;
+    const int N = P.N;
+    const bool fix = P.fix_time != 0;
+    const double mu_b = S.mu, dw = S.dw;
+    const bool pose_free = (k >= 1 && k <= N - 1);
+    const bool has_u = k < N;
+    const double t = fix ? 1.0 : S.t;
+    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k), v = WA(VL, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+
+    // the stage model (packed 9x9 Q, q) is accumulated directly in the stage slot (shared memory on the device)
+#pragma unroll
+    for (int i = 0; i < NQ + NYV; ++i) RIC(RQ + i, k) = 0.0;
+    double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0;
+    double rz_t = 0.0;
+    int ok = 1;
+    LogAcc lacc;   // barrier terms: phi -= mu * sum(log gap)
+    double lsum_blocks = 0.0;
+    // Lagrangian gradient rows of the pose
+    double rzX = 0.0, rzY = 0.0, rzP = 0.0, rzV = 0.0;
+
+    // Order of the sections: obstacle blocks first, then the state terms, the controls / dynamics last -- the local
+    // elimination of a block needs ~60 doubles in registers, so nothing else big (dynamics Jacobian, residuals) may be
+    // live across it; the dynamics outputs go straight into the stage slot.
+    // ---- (C) obstacle blocks ----
+    for (int j = 0; j < P.nOb; ++j) {
+      BlockOut bo;
+      if (BLK) block_load(C, k, j, do_err, do_asm, bo);
+      else block_eval(C, k, j, X, Y, cs_, sn_, mu_b, dw, do_err, do_asm, bo);
+      if (do_err) {
+        rzX += bo.gx[0]; rzY += bo.gx[1]; rzP += bo.gx[2];
+        e_dual = dmax(e_dual, bo.e_dual); e_pr = dmax(e_pr, bo.e_pr);
+        cmax = dmax(cmax, bo.cmax); cmin = dmin_(cmin, bo.cmin);
+        sum_y += bo.sum_y; sum_z += bo.sum_z; th += bo.th; lsum_blocks += bo.lsum;
+      }
+      fobj += bo.fobj;
+      if (do_asm) {
+        ok &= bo.ok;
         if (pose_free) {
-          RIC(RQ + sym_idx<NYV>(IX, IX), k) += Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += Sxx[2];
-          RIC(RQ + sym_idx<NYV>(IY, IY), k) += Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += Sxx[5];
-          RIC(Rq + IX, k) += rx3[0]; RIC(Rq + IY, k) += rx3[1]; RIC(Rq + IP, k) += rx3[2];
+          RIC(RQ + sym_idx<NYV>(IX, IX), k) += bo.Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += bo.Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += bo.Sxx[2];
+          RIC(RQ + sym_idx<NYV>(IY, IY), k) += bo.Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += bo.Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += bo.Sxx[5];
+          RIC(Rq + IX, k) += bo.rx3[0]; RIC(Rq + IY, k) += bo.rx3[1]; RIC(Rq + IP, k) += bo.rx3[2];
         }
       }
     }
@@ -596,7 +677,7 @@ struct ParkSolver {
         phi -= m * mu_b * (log(gl) + log(gu));
       }
     }
-    if (do_err) phi -= mu_b * lacc.total();
+    if (do_err) phi -= mu_b * (lacc.total() + lsum_blocks);
     if (do_err && pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
     out.e_dual = e_dual; out.e_pr = e_pr; out.cmax = cmax; out.cmin = cmin; out.sy = sum_y; out.sz = sum_z;
     out.th = th; out.phi = phi + fobj; out.rt = rz_t; out.f = fobj; out.ok = ok;
