@@ -37,7 +37,8 @@ N_HORIZON = 80
 WORKLOAD = "reverse-parking SD var-time, N=80, 3 obstacles vOb=[2,2,1] (BASELINE config 2)"
 # fused K1 (J/H never reach HBM): 8*(2n+2m+n_par), n=2185, m=1460, n_par=243
 ALG_BYTES_PER_EVAL = 8 * (2 * 2185 + 2 * 1460 + 243)
-NCU_TRAFFIC_PHASEA_FULL_LAUNCH = 468033280 + 942673152     # bytes, profiles/ncu_summary_r01.md (k_pk_phaseA<2,1>)
+NCU_TRAFFIC_BLOCK_FULL_LAUNCH = 203172608 + 526765056      # bytes, profiles/ncu_summary_r01.md (k_pk_block<2,1>, 4096 problems)
+NCU_TRAFFIC_K1_FULL_ROUND = (203172608 + 526765056) + (260452352 + 227575296) + (14526464 + 4274944) + (23077632 + 358144)
 
 
 def peaks():
@@ -333,19 +334,28 @@ def gpu_arm(args):
             line["kernel_ms_serialised"] = {n: round(kms[i], 3) for i, n in enumerate(names)}
             pr = (C.c_ulonglong * 8)()
             if lib.obca_last_profile(C.c_int(local), pr) == 0 and pr[7] > 0 and kms[0] > 0 and rnd.value > 0:
-                # dominant kernel: the fused K1 kernel of the rounds.  Algorithmic bytes = 60 264 B per problem per evaluation
-                # (fused variant) x the evaluations the kernel ran (device counter), over its event-timed launches.
-                ev_a = int(pr[7])
-                ach = ev_a * ALG_BYTES_PER_EVAL / (kms[0] * 1e-3) / 1e9
+                ev1, ev2 = int(pr[7]), int(pr[5])            # K1 evaluations in the first / second pass of the rounds (device counters)
+                # K1 of the rounds = k_pk_block (constraint blocks) + k_pk_phaseA (stage terms, assembly, reductions): the largest
+                # group of the step.  Algorithmic bytes: SURVEY 8d, fused variant, 60 264 B per problem per evaluation.
+                t_k1 = (kms[0] + kms[1]) * 1e-3
+                ach = (ev1 + ev2) * ALG_BYTES_PER_EVAL / t_k1 / 1e9
                 line["roofline_solve"] = line["roofline"]
-                line["roofline"] = {"bound": "hbm", "kernel": "k_pk_phaseA<2,true>", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                                    "frac": ach / hbm, "traffic": NCU_TRAFFIC_PHASEA_FULL_LAUNCH,
-                                    "launches": rnd.value, "ms_per_launch": kms[0] / rnd.value, "evaluations": ev_a,
-                                    "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x {ev_a} K1 evaluations inside the {rnd.value} launches of "
-                                            f"one solve (device counter) / their summed CUDA-event time; peak {how}; traffic = dram read+write of "
-                                            "one launch with all 4096 problems active (ncu --set full, profiles/ncu_summary_r01.md: 0.47 + 0.94 GB "
-                                            "for 4096 x 1.44 evaluations = 4x the algorithmic bytes: local factors and stage slots cross HBM between "
-                                            "the phase kernels); the kernel is latency bound (issue 16 %), see DESIGN.md section 5"}
+                line["roofline"] = {"bound": "hbm", "kernel": "K1 of the rounds: k_pk_block<2,true> + k_pk_phaseA<2,true>", "achieved": ach,
+                                    "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": NCU_TRAFFIC_K1_FULL_ROUND,
+                                    "launches": 4 * rnd.value, "ms_per_round": 1e3 * t_k1 / rnd.value, "evaluations": ev1 + ev2,
+                                    "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x {ev1 + ev2} K1 evaluations of one solve (device counters) / "
+                                            f"summed CUDA-event time of the block + assemble launches; peak {how}; traffic = dram read+write of the four "
+                                            "K1 launches of one round with all 4096 problems active (ncu --set full, profiles/ncu_summary_r01.md): 3.5x "
+                                            "the algorithmic bytes, because local factors, hand-over records and stage slots cross HBM between kernels"}
+                # the flat block kernel by itself: what it must move by construction, no re-reads
+                blk_bytes = 8.0 * (61 + 201) * NS
+                ach_b = ev1 * blk_bytes / (kms[0] * 1e-3) / 1e9
+                line["roofline_block"] = {"bound": "hbm", "kernel": "k_pk_block<2,true> (first pass)", "achieved": ach_b, "peak": hbm, "unit": "GB/s",
+                                          "frac": ach_b / hbm, "traffic": NCU_TRAFFIC_BLOCK_FULL_LAUNCH, "ms_per_launch": kms[0] / rnd.value,
+                                          "note": f"own algorithmic bytes: per problem and evaluation 8 x (61 read + 201 written doubles) x (N+1) = {int(blk_bytes)} B "
+                                                  f"(pose + block variables in; local factor 45 + hand-over record 22 per block out) x {ev1} evaluations / "
+                                                  "event time of its launches; ncu on a full launch: 0.20 GB read + 0.53 GB written in 209 us = 3.5 TB/s "
+                                                  "(53 % of the measured peak) for 0.695 GB algorithmic"}
     prof = (C.c_ulonglong * 8)()
     if lib.obca_last_profile(C.c_int(local), prof) == 0 and sum(prof[i] for i in range(6)) > 0:
         names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]

@@ -128,8 +128,8 @@ int obca_check_quadcopter(int B, int N, const double* x, const double* u, const 
 /* Per-phase device cycle counters of the last obca_parking_solve_batch[_dev] on `device`, summed over the batch
  * (thread 0 of every CTA, clock64): out8 = {eval (K1), kkt (K3), recover, merit, update, serial sections,
  * #merit evaluations, #K1 evaluations}.  The cycle counters are filled by the monolithic kernel (OBCA_MODE=3) and by the
- * quadcopter kernel; the default phase-split schedule reports only out8[7] = K1 evaluations inside the assemble
- * kernel launches and out8[6] = K1 evaluations inside the tail kernel.  Diagnostic only. */
+ * quadcopter kernel; the default phase-split schedule reports only the K1 evaluation counts: out8[7] = first pass of the
+ * rounds (block + assemble kernels), out8[5] = second pass (after a barrier update), out8[6] = inside the tail kernel.  Diagnostic only. */
 int obca_last_profile(int device, unsigned long long* out8);
 
 /* How the last obca_parking_solve_batch[_dev] on `device` was scheduled (last chunk of the batch): number of

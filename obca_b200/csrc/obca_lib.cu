@@ -518,12 +518,12 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
   c.last_rounds = r; c.last_tail = n_bound;
   if (timing) {
     CK(cudaStreamSynchronize(st));
-    double t[3] = {0, 0, 0};
-    for (size_t i = 0; i + 3 < tev.size(); i += 4)
-      for (int j = 0; j < 3; ++j) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[i + j], tev[i + j + 1]); t[j] += ms; }
+    double t[4] = {0, 0, 0, 0};      // five marks per round: | block | assemble (+ second pass) | sweep | line search |
+    for (size_t i = 0; i + 4 < tev.size(); i += 5)
+      for (int j = 0; j < 4; ++j) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[i + j], tev[i + j + 1]); t[j] += ms; }
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
-    for (int j = 0; j < 3; ++j) c.phase_ms[j] = t[j];
-    c.phase_ms[3] = 0.0;
+    for (int j = 0; j < 4; ++j) c.phase_ms[j] = t[j];
+    c.phase_ms[4] = 0.0;
   }
   if (n_bound > 0) {
     const int grid = n_bound < tail_cap ? n_bound : tail_cap;

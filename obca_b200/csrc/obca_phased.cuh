@@ -427,7 +427,7 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   }
   state_store(Sg + b, S);
   if (threadIdx.x == 0) {
-    if (bp.prof) atomicAdd(bp.prof + 7, (unsigned long long)S.prof[7]);
+    if (bp.prof) atomicAdd(bp.prof + (pass == 1 ? 7 : 5), (unsigned long long)S.prof[7]);
     if (pass == 1 && S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
   }
 }
