@@ -496,7 +496,7 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
     k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[1 - cur], c.ncnt + (1 - cur), nullptr,
                                                       nullptr, 0, 2);
     mark();
-    k_pk_sweep<VM, SDV><<<(n_bound + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
+    k_pk_sweep<VM, SDV><<<(n_bound + 2 * SWEEP_WARPS - 1) / (2 * SWEEP_WARPS), 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
                                                                                               c.ncnt + (1 - cur));
     mark();
     k_pk_phaseC<VM, SDV><<<n_bound, L.NSP, 0, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[1 - cur], c.ncnt + (1 - cur));

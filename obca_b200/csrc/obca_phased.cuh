@@ -4,7 +4,7 @@
 // every phase of an iteration runs as its own kernel over ALL active problems of the batch, each with the launch
 // shape that suits it:
 //     k_pk_phaseA   CTA per problem, thread per stage : accept step -> K1 evaluate + assemble -> barrier update
-//     k_pk_sweep    WARP per problem                   : K3 stage-banded KKT sweep, stage slots streamed from HBM
+//     k_pk_sweep    HALF-WARP per problem              : K3 stage-banded KKT sweep, stage slots streamed from HBM
 //                                                        through a cp.async ring; inertia-correction bookkeeping
 //     k_pk_phaseC   CTA per problem, thread per stage : K4 step recovery, fraction-to-the-boundary, filter line search
 // The iterate, the step, the local factors and the stage slots of every problem live in HBM (layout: problem-major,
@@ -433,56 +433,71 @@ k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K_B: warp per problem.  Backward Riccati sweep + forward roll-out with the stage slots streamed from global memory
+// K_B: half-warp per problem.  Backward Riccati sweep + forward roll-out with the stage slots streamed from global memory
 // (each slot = 640 contiguous bytes) through a 4-deep cp.async ring; gains and the P_{k+1} rows needed by the
 // multiplier recovery are written back in place (consumed Q/q space of the slots).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SWEEP_DEPTH = 4;
-constexpr int SWEEP_WARP_DOUBLES = SWEEP_DEPTH * GSTRIDE + 144;   // ring + exchange tile (ParkSolver::TILE_DOUBLES)
 
-__device__ __forceinline__ void sweep_prefetch(double* ring, const double* gslots, int k, int lane) {
-  if (k >= 0) {
+// ------------------------------------------------------------------------------------------------------------
+// Two problems per warp: the lane code of the sweep uses 9 of 32 lanes, so each HALF-warp runs one problem (lanes 0..15 /
+// 16..31, same instruction stream, own ring / exchange tile / pointers).  Halves the instruction and shared-memory traffic
+// per sweep; the kernel is issue / MIO bound (profiles/ncu_summary_r01.md).  A half without work (odd count, problem not
+// waiting for a sweep, local pivots already failed) executes along on valid memory with every global write redirected
+// to a shared-memory dump area.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SWEEP_HALF_DOUBLES = SWEEP_DEPTH * GSTRIDE + 144 + 48 + 4;   // ring + tile + dump + 4 (bank offset between the halves)
+
+__device__ __forceinline__ void sweep_prefetch16(double* ring, const double* gslots, int k, int hl, int n) {
+  if (k >= 0 && k < n) {
     double* dst = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
     const double* src = gslots + (size_t)k * GSTRIDE;
-    cp_async16(dst + 2 * lane, src + 2 * lane);
-    if (lane < 8) cp_async16(dst + 64 + 2 * lane, src + 64 + 2 * lane);
+    cp_async16(dst + 2 * hl, src + 2 * hl);
+    cp_async16(dst + 32 + 2 * hl, src + 32 + 2 * hl);
+    if (hl < 8) cp_async16(dst + 64 + 2 * hl, src + 64 + 2 * hl);
   }
-  cp_async_commit();      // (possibly empty) group: keeps the group count uniform
+  cp_async_commit();
 }
 
+// run: this half has a sweep to do (uniform within the half).  Returns 1 if the half's sweep found inertia (n, m, 0).
 template <int VM, bool SDV>
-__device__ int pk_sweep_global(const ParkProblem& Pp, const IpmOpts& O, const PkLay& Lay, double* W, double* gslots,
-                               ProbState* Sgl, double* ring, double* tile) {
+__device__ int pk_sweep_pair(const ParkProblem& Pp, const IpmOpts& O, const PkLay& Lay, double* W, double* gslots,
+                             ProbState* Sgl, bool run, double* ring, double* tile, double* dump) {
   typedef ParkSolver<VM, SDV> PS;
   const int N = Pp.N;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, hl = lane & 15, base = lane & 16;
+  const unsigned FULL = 0xffffffffu;
   PkCtx C;
   C.P = &Pp; C.O = &O; C.L = Lay; C.W = W;
   typename PS::KktLane L;
-  PS::kl_init(L, lane, tile, C);
-  sweep_prefetch(ring, gslots, N - 1, lane);
-  sweep_prefetch(ring, gslots, N - 2, lane);
-  sweep_prefetch(ring, gslots, N - 3, lane);
+  // kl_init zeroes tile[70 .. 90] with 21 lanes; a half has 16
+  PS::kl_init(L, hl, tile, C);
+  if (hl < 5) tile[86 + hl] = 0.0;
+  sweep_prefetch16(ring, gslots, N - 1, hl, N);
+  sweep_prefetch16(ring, gslots, N - 2, hl, N);
+  sweep_prefetch16(ring, gslots, N - 3, hl, N);
   __syncwarp();
   for (int k = N - 1; k >= 0; --k) {
-    sweep_prefetch(ring, gslots, k - 3, lane);      // into the ring entry of slot k+1, consumed one step ago
-    cp_async_wait<3>();                             // slot k has landed (this lane's part)
+    sweep_prefetch16(ring, gslots, k - 3, hl, N);
+    cp_async_wait<3>();
     __syncwarp();
     const double* slot = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
     double* gk = gslots + (size_t)k * GSTRIDE;
-    PS::kl_step1(L, lane, slot, tile, gk + GSTRIDE);
+    const bool wr = run && L.ok;
+    PS::kl_step1(L, hl, slot, tile, wr ? gk + GSTRIDE : dump);
     __syncwarp();
-    PS::kl_step2(L, lane, slot, tile);
+    PS::kl_step2(L, hl, slot, tile);
     __syncwarp();
-    PS::kl_step3(L, lane, gk, tile);
+    PS::kl_step3(L, hl, wr ? gk : dump, tile);
     __syncwarp();
-    if (!L.ok) break;
+    if (!__any_sync(FULL, run && L.ok)) break;      // both halves have nothing (left) to do
   }
   cp_async_wait<0>();
-  if (!L.ok) return 0;
-  int ok = 1;
-  if (lane == IT) { tile[63] = L.Prow[IT]; tile[64] = L.pl; }
-  __threadfence();       // gains written above are re-read below through cp.async
+  const bool good = run && L.ok;
+  if (!__any_sync(FULL, good)) return 0;
+  int ok = good ? 1 : 0;
+  if (hl == IT) { tile[63] = L.Prow[IT]; tile[64] = L.pl; }
+  __threadfence();
   __syncwarp();
   double dt = 0.0;
   if (!Pp.fix_time) {
@@ -490,48 +505,39 @@ __device__ int pk_sweep_global(const ParkProblem& Pp, const IpmOpts& O, const Pk
     if (!(ptt > 0.0)) { ok = 0; ptt = 1e300; }
     dt = -tile[64] / ptt;
   }
-  if (lane == 0) Sgl->dt = dt;
-  // ---- forward roll-out (same lane code as ParkSolver::kkt_solve_warp) ----
+  if (hl == 0 && good) Sgl->dt = dt;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
-  const int ur = lane & 1, xr = lane & 3;
-  const unsigned FULL = 0xffffffffu;
+  const int ur = hl & 1, xr = hl & 3;
   const double selx = (xr == 0) ? 1.0 : 0.0, sely = (xr == 1) ? 1.0 : 0.0;
   double* const dxw = W + (size_t)(Lay.dX + xr) * Lay.NSP;
   double* const duw = W + (size_t)(Lay.dDE + ur) * Lay.NSP;
   __syncwarp();
-  // ring entries are indexed by k & 3 again; going upwards the prefetch distance is +3
-  auto pf = [&](int k) {
-    if (k < N) {
-      double* dst = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
-      const double* src = gslots + (size_t)k * GSTRIDE;
-      cp_async16(dst + 2 * lane, src + 2 * lane);
-      if (lane < 8) cp_async16(dst + 64 + 2 * lane, src + 64 + 2 * lane);
-    }
-    cp_async_commit();
-  };
-  pf(0); pf(1); pf(2);
+  sweep_prefetch16(ring, gslots, 0, hl, N); sweep_prefetch16(ring, gslots, 1, hl, N); sweep_prefetch16(ring, gslots, 2, hl, N);
   for (int k = 0; k < N; ++k) {
-    pf(k + 3);
+    sweep_prefetch16(ring, gslots, k + 3, hl, N);
     cp_async_wait<3>();
     __syncwarp();
     const double* const slot = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
     const double* const kr = slot + RK + ur * NSV;
     double u = slot[RK + 14 + ur] + kr[0] * s0 + kr[1] * s1 + kr[2] * s2 + kr[3] * s3 + kr[4] * s4 + kr[5] * s5 + kr[6] * dt;
-    const double u0 = __shfl_sync(FULL, u, 0), u1 = __shfl_sync(FULL, u, 1);
+    const double u0 = __shfl_sync(FULL, u, base + 0), u1 = __shfl_sync(FULL, u, base + 1);
     const double* const dr = slot + RDYN + 5 * xr;
     double sn = slot[RR4 + xr] + selx * s0 + sely * s1 + dr[0] * s2 + dr[1] * s3 + dr[2] * dt + dr[3] * u0 + dr[4] * u1;
-    if (lane < 2) duw[k] = u;
-    s0 = __shfl_sync(FULL, sn, 0); s1 = __shfl_sync(FULL, sn, 1); s2 = __shfl_sync(FULL, sn, 2); s3 = __shfl_sync(FULL, sn, 3);
+    if (hl < 2 && good) duw[k] = u;
+    s0 = __shfl_sync(FULL, sn, base + 0); s1 = __shfl_sync(FULL, sn, base + 1); s2 = __shfl_sync(FULL, sn, base + 2);
+    s3 = __shfl_sync(FULL, sn, base + 3);
     s4 = u0; s5 = u1;
-    if (lane < 4) {
+    if (hl < 4 && good) {
       if (k + 1 < N) dxw[k + 1] = sn;
       else Sgl->eN[xr] = sn;
     }
-    __syncwarp();     // everybody is done with this ring entry before it is refilled
+    __syncwarp();
   }
   cp_async_wait<0>();
-  if (lane < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
-  if (lane < 2) duw[N] = 0.0;
+  if (good) {
+    if (hl < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
+    if (hl < 2) duw[N] = 0.0;
+  }
   return ok;
 }
 
@@ -541,19 +547,26 @@ __global__ void __launch_bounds__(32 * SWEEP_WARPS)
 k_pk_sweep(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L,
            double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
            const int* __restrict__ act, const int* __restrict__ n_act) {
-  __shared__ __align__(16) double s_w[SWEEP_WARPS][SWEEP_WARP_DOUBLES];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * SWEEP_WARPS + warp;
-  if (idx >= *n_act) return;
-  const int b = act[idx];
+  __shared__ __align__(16) double s_w[SWEEP_WARPS][2 * SWEEP_HALF_DOUBLES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const int n = *n_act;
+  const int first = (blockIdx.x * SWEEP_WARPS + warp) * 2;
+  if (first >= n) return;
+  const int idx = first + half;
+  const bool valid = idx < n;
+  const int b = act[valid ? idx : first];              // a half without a problem reads its partner's (valid) memory
   ProbState* S = Sg + b;
-  if (S->phase != PH_KKT) return;
-  int ok = S->ok;
+  const bool active = valid && S->phase == PH_KKT;
+  if (!__any_sync(0xffffffffu, active)) return;
   const int NS = P.N + 1;
-  if (ok) ok = pk_sweep_global<VM, SDV>(P, O, L, Wall + (size_t)b * L.total * L.NSP, slots + (size_t)b * NS * GSTRIDE, S,
-                                        s_w[warp], s_w[warp] + SWEEP_DEPTH * GSTRIDE);
+  const bool run = active && S->ok != 0;
+  double* hw = s_w[warp] + half * SWEEP_HALF_DOUBLES;
+  int ok = 0;
+  if (__any_sync(0xffffffffu, run))
+    ok = pk_sweep_pair<VM, SDV>(P, O, L, Wall + (size_t)b * L.total * L.NSP, slots + (size_t)b * NS * GSTRIDE, S, run, hw,
+                                hw + SWEEP_DEPTH * GSTRIDE, hw + SWEEP_DEPTH * GSTRIDE + 144);
   __syncwarp();
-  if (lane == 0) PhasedDriver<ParkSolver<VM, SDV> >::phase_B_serial(*S, O, ok);
+  if (hl == 0 && active) PhasedDriver<ParkSolver<VM, SDV> >::phase_B_serial(*S, O, run ? ok : 0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
