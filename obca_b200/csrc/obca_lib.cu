@@ -499,7 +499,8 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
     k_pk_sweep<VM, SDV><<<(n_bound + 2 * SWEEP_WARPS - 1) / (2 * SWEEP_WARPS), 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
                                                                                               c.ncnt + (1 - cur));
     mark();
-    k_pk_phaseC<VM, SDV><<<n_bound, L.NSP, 0, st>>>(P, O, L, bp, c.W, c.slots, Sg, act[1 - cur], c.ncnt + (1 - cur));
+    k_pk_rblock<VM, SDV><<<blk_grid(n_bound), 128, 0, st>>>(P, L, c.W, c.bo, Sg, act[1 - cur], c.ncnt + (1 - cur));
+    k_pk_phaseC<VM, SDV><<<n_bound, L.NSP, 0, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[1 - cur], c.ncnt + (1 - cur));
     mark();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c.h_n + (r & 15), c.ncnt + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st));

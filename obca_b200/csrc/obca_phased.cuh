@@ -149,13 +149,18 @@ struct PhasedDriver {
 
   // C: recover the full step, step lengths, filter line search, and -- when a step is accepted -- the iterate update.
   //    Leaves PH_EVAL (new iterate, or barrier kick: same iterate, new barrier parameter) or PH_END (line-search failure).
+  template <bool BLK>
   __device__ static void phase_C(const Ctx& C) {
     const IpmOpts& O = CTX_O(C);
     ProbState& S = *C.S;
     const int NS = M::n_stages(C);
     StepPart sp;
     part_init(sp);
-    OBCA_FOR_STAGES(k, NS) { StepPart s1; M::recover_stage(C, k, s1); part_merge(sp, s1); }
+    OBCA_FOR_STAGES(k, NS) {
+      StepPart s1;
+      if (BLK) M::recover_stage_blk(C, k, s1); else M::recover_stage(C, k, s1);
+      part_merge(sp, s1);
+    }
     OBCA_REDUCE(sp);
     OBCA_SERIAL {
       const double apr = sp.apr, adu = sp.adu, dphi = sp.dphi;
@@ -570,6 +575,38 @@ k_pk_sweep(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpt
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K_rblk: step recovery of the OBCA blocks as a flat streaming kernel (same thread mapping as k_pk_block): reads the local
+// factor written by k_pk_block and the pose step of the sweep, writes the steps of (lambda, mu, sl) and the new multipliers
+// of the block's rows into the workspace, and a 5-double record (tightest primal / dual fractions to the boundary, barrier
+// directional derivative) for k_pk_phaseC.
+// ------------------------------------------------------------------------------------------------------------
+template <int VM, bool SDV>
+__global__ void __launch_bounds__(128, OBCA_MINB_BLK)
+k_pk_rblock(const __grid_constant__ ParkProblem P, const PkLay L, double* __restrict__ Wall, double* __restrict__ BOall,
+            const ProbState* __restrict__ Sg, const int* __restrict__ act, const int* __restrict__ n_act) {
+  const int NS = P.N + 1, per = P.nOb * NS;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = (int)(idx / per);
+  if (a >= *n_act) return;
+  const int rem = (int)(idx - (long long)a * per);
+  const int j = rem / NS, k = rem - j * NS;
+  const int b = act[a];
+  const ProbState* S = Sg + b;
+  if (S->phase != PH_RECOVER) return;
+  const double mu_b = S->mu, dw = S->dw;
+  PkCtx C;
+  C.W = Wall + (size_t)b * L.total * L.NSP;
+  C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
+  const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
+  const double dX = WA(dX, k), dY = WA(dY, k), dP = WA(dPS, k);
+  double sn_, cs_;
+  sincos(ps, &sn_, &cs_);
+  typename ParkSolver<VM, SDV>::RBlockOut rb;
+  ParkSolver<VM, SDV>::block_recover(C, k, j, X, Y, cs_, sn_, dX, dY, dP, mu_b, dw, rb);
+  ParkSolver<VM, SDV>::rblock_store(C, k, j, rb);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K_C: one CTA per active problem
 // ------------------------------------------------------------------------------------------------------------
 #ifndef OBCA_MINB_C
@@ -578,7 +615,7 @@ k_pk_sweep(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpt
 template <int VM, bool SDV>
 __global__ void __launch_bounds__(128, OBCA_MINB_C)
 k_pk_phaseC(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
-            double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
+            double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg, double* __restrict__ BOall,
             const int* __restrict__ act, const int* __restrict__ n_act) {
   __shared__ ProbState S;
   __shared__ double s_red[4 * 12];
@@ -591,9 +628,10 @@ k_pk_phaseC(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOp
   if (threadIdx.x == 0) {
     pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
     C.ric = nullptr; C.pp = slots + (size_t)b * NS * GSTRIDE; C.pps = GSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+    C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
   }
   __syncthreads();
-  PhasedDriver<ParkSolver<VM, SDV> >::phase_C(C);
+  PhasedDriver<ParkSolver<VM, SDV> >::template phase_C<true>(C);
   state_store(Sg + b, S);
 }
 
@@ -641,7 +679,7 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
         if (threadIdx.x == 0) PhasedDriver<PS>::phase_B_serial(S, O, ok);
       }
       __syncthreads();
-      if (S.phase == PH_RECOVER) PhasedDriver<PS>::phase_C(C);
+      if (S.phase == PH_RECOVER) PhasedDriver<PS>::template phase_C<false>(C);
     }
     if (threadIdx.x == 0 && bp.prof) atomicAdd(bp.prof + 6, (unsigned long long)S.prof[7]);
     __syncthreads();

@@ -974,7 +974,93 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // K4a: recover local steps, slack steps; step-length partials; directional derivative of the barrier objective
   // ---------------------------------------------------------------------------------------------------
-  OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) {
+  // ---------------------------------------------------------------------------------------------------
+  // K4a, one (stage k, obstacle j) block: step of the local unknowns from the factor stored by block_eval and the pose step
+  // (dX, dY, dP); fraction-to-the-boundary and barrier-derivative partials of the block.
+  // ---------------------------------------------------------------------------------------------------
+  struct RBlockOut { double apr_g, apr_d, adu_g, adu_d, dphi; };
+  OBCA_HD static void block_recover(const PkCtx& C, int k, int j, double X, double Y, double cs_, double sn_, double dX, double dY,
+                                    double dP, double mu_b, double dw, RBlockOut& rbo) {
+    const ParkProblem& P = CTX_P(C);
+    const double tau = 0.0;      // (unused by ftb: the fractions are scaled by tau when the stage is finished)
+    Ftb apr, adu;
+    double dphi = 0.0;
+    {
+      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
+      load_rows(C, j, R);
+      load_vars(C, k, j, R, Qv);
+      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      const int piv = choose_pivot<VM, SDV>(R, G);
+      if (piv != 0) {
+        swap_rows(R, Qv, piv);
+        obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+      }
+      ObsStep<VM> St;
+      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP, dX, dY, dP, St);
+      // un-permute lambda
+      if (piv != 0) {
+#pragma unroll
+        for (int i = 1; i < VM; ++i)
+          if (i == piv) {
+            double tmp = St.dlam[0]; St.dlam[0] = St.dlam[i]; St.dlam[i] = tmp;
+            tmp = Qv.lam[0]; Qv.lam[0] = Qv.lam[i]; Qv.lam[i] = tmp;
+            tmp = Qv.zlam[0]; Qv.zlam[0] = Qv.zlam[i]; Qv.zlam[i] = tmp;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < VM; ++i) {
+        if (i < R.v) {
+          WV(dLAM, P.voff[j] + i, k) = St.dlam[i];
+          ftb(Qv.lam[i], St.dlam[i], tau, apr);
+          ftb(Qv.zlam[i], dzb(Qv.zlam[i], Qv.lam[i], St.dlam[i], mu_b), tau, adu);
+          dphi += -mu_b * rcp(Qv.lam[i]) * St.dlam[i];
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        WV(dMU, 4 * j + m, k) = St.dmu[m];
+        ftb(Qv.mu[m], St.dmu[m], tau, apr);
+        ftb(Qv.zmu[m], dzb(Qv.zmu[m], Qv.mu[m], St.dmu[m], mu_b), tau, adu);
+        dphi += -mu_b * rcp(Qv.mu[m]) * St.dmu[m];
+      }
+      if (SDV) {
+        WV(dSL, j, k) = St.dsl; WV(YNn, j, k) = St.yn_new;
+        dphi += (1e2 + 2e4 * Qv.sl) * St.dsl;
+      }
+      WV(YRn, 2 * j, k) = St.yr1_new; WV(YRn, 2 * j + 1, k) = St.yr2_new;
+      WV(dSD, j, k) = St.dsd;
+      {
+        const double gap = Qv.sd - P.dmin;
+        ftb(gap, St.dsd, tau, apr);
+        ftb(Qv.vd, dzb(Qv.vd, gap, St.dsd, mu_b), tau, adu);
+        dphi += -mu_b * rcp(gap) * St.dsd;
+      }
+      if (!SDV) {
+        WV(dSN, j, k) = St.dsn;
+        const double gap = 1.0 - Qv.sn;
+        ftb(gap, -St.dsn, tau, apr);
+        ftb(Qv.vn, dzb(Qv.vn, gap, -St.dsn, mu_b), tau, adu);
+        dphi += mu_b * rcp(gap) * St.dsn;
+      }
+    }
+    rbo.apr_g = apr.g; rbo.apr_d = apr.d; rbo.adu_g = adu.g; rbo.adu_d = adu.d; rbo.dphi = dphi;
+  }
+  OBCA_HD static void rblock_store(const PkCtx& C, int k, int j, const RBlockOut& r) {
+    double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
+    const size_t st = CTX_L(C).NSP;
+    o[0] = r.apr_g; o[st] = r.apr_d; o[2 * st] = r.adu_g; o[3 * st] = r.adu_d; o[4 * st] = r.dphi;
+  }
+  OBCA_HD static void rblock_load(const PkCtx& C, int k, int j, RBlockOut& r) {
+    const double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
+    const size_t st = CTX_L(C).NSP;
+    r.apr_g = o[0]; r.apr_d = o[st]; r.adu_g = o[2 * st]; r.adu_d = o[3 * st]; r.dphi = o[4 * st];
+  }
+
+  OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) { recover_stage_t<false>(C, k, out); }
+  OBCA_HD_NI static void recover_stage_blk(const PkCtx& C, int k, StepPart& out) { recover_stage_t<true>(C, k, out); }
+  // BLK: the obstacle blocks were recovered by the flat kernel k_pk_rblock; their step-length / merit partials are read from C.bo
+  template <bool BLK>
+  OBCA_HD static void recover_stage_t(const PkCtx& C, int k, StepPart& out) {
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1045,62 +1131,12 @@ struct ParkSolver {
               (-mu_b * rcp(gl) + mu_b * rcp(gu)) * drs;
     }
     for (int j = 0; j < P.nOb; ++j) {
-      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
-      load_rows(C, j, R);
-      load_vars(C, k, j, R, Qv);
-      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
-      const int piv = choose_pivot<VM, SDV>(R, G);
-      if (piv != 0) {
-        swap_rows(R, Qv, piv);
-        obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
-      }
-      ObsStep<VM> St;
-      obs_recover<VM, SDV>(P, R, Qv, G, mu_b, dw, &WV(LF, j * CTX_L(C).nfac, k), CTX_L(C).NSP, dX, dY, dP, St);
-      // un-permute lambda
-      if (piv != 0) {
-#pragma unroll
-        for (int i = 1; i < VM; ++i)
-          if (i == piv) {
-            double tmp = St.dlam[0]; St.dlam[0] = St.dlam[i]; St.dlam[i] = tmp;
-            tmp = Qv.lam[0]; Qv.lam[0] = Qv.lam[i]; Qv.lam[i] = tmp;
-            tmp = Qv.zlam[0]; Qv.zlam[0] = Qv.zlam[i]; Qv.zlam[i] = tmp;
-          }
-      }
-#pragma unroll
-      for (int i = 0; i < VM; ++i) {
-        if (i < R.v) {
-          WV(dLAM, P.voff[j] + i, k) = St.dlam[i];
-          ftb(Qv.lam[i], St.dlam[i], tau, apr);
-          ftb(Qv.zlam[i], dzb(Qv.zlam[i], Qv.lam[i], St.dlam[i], mu_b), tau, adu);
-          dphi += -mu_b * rcp(Qv.lam[i]) * St.dlam[i];
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        WV(dMU, 4 * j + m, k) = St.dmu[m];
-        ftb(Qv.mu[m], St.dmu[m], tau, apr);
-        ftb(Qv.zmu[m], dzb(Qv.zmu[m], Qv.mu[m], St.dmu[m], mu_b), tau, adu);
-        dphi += -mu_b * rcp(Qv.mu[m]) * St.dmu[m];
-      }
-      if (SDV) {
-        WV(dSL, j, k) = St.dsl; WV(YNn, j, k) = St.yn_new;
-        dphi += (1e2 + 2e4 * Qv.sl) * St.dsl;
-      }
-      WV(YRn, 2 * j, k) = St.yr1_new; WV(YRn, 2 * j + 1, k) = St.yr2_new;
-      WV(dSD, j, k) = St.dsd;
-      {
-        const double gap = Qv.sd - P.dmin;
-        ftb(gap, St.dsd, tau, apr);
-        ftb(Qv.vd, dzb(Qv.vd, gap, St.dsd, mu_b), tau, adu);
-        dphi += -mu_b * rcp(gap) * St.dsd;
-      }
-      if (!SDV) {
-        WV(dSN, j, k) = St.dsn;
-        const double gap = 1.0 - Qv.sn;
-        ftb(gap, -St.dsn, tau, apr);
-        ftb(Qv.vn, dzb(Qv.vn, gap, -St.dsn, mu_b), tau, adu);
-        dphi += mu_b * rcp(gap) * St.dsn;
-      }
+      RBlockOut rb;
+      if (BLK) rblock_load(C, k, j, rb);
+      else block_recover(C, k, j, X, Y, cs_, sn_, dX, dY, dP, mu_b, dw, rb);
+      ftb(rb.apr_g, -rb.apr_d, tau, apr);      // merge the block's tightest fractions (d = 0: no shrinking gap in the block)
+      ftb(rb.adu_g, -rb.adu_d, tau, adu);
+      dphi += rb.dphi;
     }
     if (k == 0 && !fix) {
       const double m = (double)(N + 1);
