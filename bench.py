@@ -367,6 +367,23 @@ def gpu_arm(args):
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": "port",
                                 "sample": f"{cores} problems of the same batch (seed 0), {wall:.1f} s wall, mean {per:.1f} s/solve, "
                                           f"mean {it:.0f} iterations; oracle/ipm_ref.py sparse path = IPOPT stand-in, not IPOPT"}
+        # second CPU figure: the SAME structure-exploiting algorithm as the kernels (block condensation + Riccati sweep), i.e. the
+        # per-stage CUDA source compiled by g++ for the host (tests/emul, test infrastructure: the emulation the CPU tests check
+        # the kernels' arithmetic with), one problem per OpenMP thread.  What a CPU gets out of this solver design; not IPOPT.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+            import emul
+            nprob = min(256, 2 * host_cores())
+            scc = scenarios.reverse_parking_batch(nprob, N, seed=0)
+            t0 = time.time()
+            lpe, npe, _, _ = emul.dualmultws_batch(scc)
+            re_ = emul.solve_batch(scc, 0, "sd", None, lpe, npe)
+            wall_e = time.time() - t0
+            line["cpu_structured"] = {"value": float((re_["status"] == 1).sum()) / wall_e, "unit": "traj/s", "cores": host_cores(),
+                                      "kind": "port (host build of the kernels' own per-stage source, OpenMP over problems)",
+                                      "sample": f"{nprob} problems of the same batch (seed 0), {wall_e:.1f} s wall, DualMultWS + solve"}
+        except Exception as e:      # the emulation is optional test infrastructure
+            line["cpu_structured"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
