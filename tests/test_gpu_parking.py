@@ -301,3 +301,29 @@ def test_chunked_batches_equal_unchunked(P):
     assert a["exitflag"].sum() >= 240
     for key in ("xp", "up", "ts", "lp", "np", "iters", "exitflag"):
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("nob,N", [(4, 80), (3, 100)])
+def test_phased_rounds_other_shapes(P, nob, N):
+    """The phase-split rounds on the other template instantiations / horizons: 4-obstacle parallel parking (ragged half-space
+    counts) and a horizon that is not 80 -- same outputs as the monolithic kernel, feasible by the reference checker."""
+    from obca_b200 import scenarios
+    sc = scenarios.parallel_parking_batch(160, N, seed=3, n_obstacles=nob)
+    old = {k: os.environ.get(k) for k in ("OBCA_MODE", "OBCA_TAIL_THRESH")}
+    try:
+        os.environ["OBCA_MODE"] = "3"
+        ref = solve(P, sc)
+        os.environ["OBCA_MODE"] = "2"; os.environ["OBCA_TAIL_THRESH"] = "40"
+        r = solve(P, sc)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert ref["exitflag"].sum() >= 150
+    for key in ("xp", "up", "ts", "lp", "np", "iters", "exitflag"):
+        assert np.array_equal(r[key], ref[key]), key
+    feas, e7, strict = P.check_parking_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"],
+                                             sc["b"], r["xp"], r["up"], r["lp"], r["np"], r["ts"], 0, 1, r["sl"])
+    assert feas[r["exitflag"] == 1].all()
