@@ -321,14 +321,14 @@ def gpu_arm(args):
     rnd = C.c_int(0); hand = C.c_int(0); kms = (C.c_double * 5)()
     if lib.obca_last_schedule(C.c_int(local), C.byref(rnd), C.byref(hand), None) == 0:
         line["config"]["schedule"] = {"phase_split_rounds": rnd.value, "handed_to_tail_kernel": hand.value}
-        line["gpu_launches"] = args.steps * (2 + 6 * rnd.value + (1 if hand.value > 0 else 0)) * 2    # device arm + e2e arm
+        line["gpu_launches"] = args.steps * (2 + 7 * rnd.value + (1 if hand.value > 0 else 0)) * 2    # device arm + e2e arm
         # one extra, untimed solve with per-kernel events: which kernel dominates the step
         os.environ["OBCA_PHASE_TIMING"] = "1"
         step_dev()
         os.environ.pop("OBCA_PHASE_TIMING", None)
         if lib.obca_last_schedule(C.c_int(local), None, None, kms) == 0:
             names = ["k_pk_block (K1 constraint blocks, pass 1)", "k_pk_phaseA (K1 stage terms + assemble; + pass 2)", "k_pk_sweep (K3 KKT)",
-                     "k_pk_phaseC (K4 line search + update)", "k_pk_tail (persistent, all phases)"]
+                     "k_pk_rblock + k_pk_phaseC (K4 recovery, line search, update)", "k_pk_tail (persistent, all phases)"]
             tot = sum(kms) or 1.0
             line["kernel_share"] = {n: round(kms[i] / tot, 4) for i, n in enumerate(names)}
             line["kernel_ms_serialised"] = {n: round(kms[i], 3) for i, n in enumerate(names)}
