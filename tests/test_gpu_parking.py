@@ -327,3 +327,36 @@ def test_phased_rounds_other_shapes(P, nob, N):
     feas, e7, strict = P.check_parking_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"],
                                              sc["b"], r["xp"], r["up"], r["lp"], r["np"], r["ts"], 0, 1, r["sl"])
     assert feas[r["exitflag"] == 1].all()
+
+
+@pytest.mark.parametrize("variant", ["d", "sd"])
+def test_gpu_solution_equals_independent_sqp(P, variant):
+    """The library's output against scipy's SLSQP (an active-set SQP method that shares nothing with the interior-point code)
+    on the reference-formulation NLP of the oracle, straight-in reverse parking, N = 12: same primal point (x, timeScale, u).
+    (lambda, mu are not unique where a distance constraint is inactive.)"""
+    import obca_b200
+    from scipy.optimize import minimize
+    from oracle.dualmultws_ref import dualmultws_ipm
+    from oracle.parking_nlp import build_parking_nlp, initial_point
+    from oracle.parking_solve import solver_view
+    from test_oracle_cross_solver import dense, straight_in
+    N = 12
+    sc = straight_in(N)
+    o = obca_b200.default_opts(); o.tol = 1e-8; o.mu_min = 1e-9
+    r = solve(P, sc, sd=1 if variant == "sd" else 0, opts=o)
+    assert r["exitflag"][0] == 1
+    nlp = solver_view(build_parking_nlp(sc["x0"][0], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
+                                        sc["rx"][0], sc["ry"][0], sc["ryaw"][0], 0, variant))
+    lay = nlp.lay
+    gL, gU = nlp.gL, nlp.gU
+    mL, mU = np.isfinite(gL), np.isfinite(gU)
+    cons = [dict(type="eq", fun=nlp.cE, jac=lambda z: dense(nlp.JE(z))),
+            dict(type="ineq", fun=lambda z: np.concatenate([(nlp.g(z) - gL)[mL], (gU - nlp.g(z))[mU]]),
+                 jac=lambda z: np.vstack([dense(nlp.JI(z))[mL], -dense(nlp.JI(z))[mU]]))]
+    lWS, nWS, _, _ = dualmultws_ipm(N, 3, sc["vOb"], sc["A"], sc["b"], sc["rx"][0], sc["ry"][0], sc["ryaw"][0], sc["ego"])
+    z0 = initial_point(lay, sc["xWS"][0], sc["uWS"][0], lWS, nWS)
+    bounds = [(None if not np.isfinite(lo) else lo, None if not np.isfinite(hi) else hi) for lo, hi in zip(nlp.zL, nlp.zU)]
+    q = minimize(nlp.f, z0, jac=nlp.grad, method="SLSQP", constraints=cons, bounds=bounds, options=dict(ftol=1e-14, maxiter=500))
+    assert q.status == 0, q.message
+    xp, up, ts = lay.unpack(q.x)[:3]
+    assert np.abs(r["xp"][0] - xp).max() < 1e-5 and np.abs(r["up"][0] - up).max() < 1e-5 and np.abs(r["ts"][0] - ts).max() < 1e-5

@@ -1,0 +1,74 @@
+"""Pinning the oracle's IPOPT stand-in with an INDEPENDENT solver: scipy's SLSQP -- an
+active-set SQP method that shares nothing with the interior-point code except the NLP callbacks -- is run on the same
+reference-formulation NLP (oracle/parking_nlp.py) from the same warm start.  On a small straight-in reverse-parking problem
+both must stop at the same primal point; the kernels' own arithmetic (tests/emul) must land there too.
+(The OBCA multipliers lambda, mu are not unique where a distance constraint is inactive, so only (x, timeScale, u) and the
+objective are compared.)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+import emul                                      # noqa: E402
+from obca_b200 import scenarios                  # noqa: E402
+from oracle import ipm_ref                       # noqa: E402
+from oracle.dualmultws_ref import dualmultws_ipm  # noqa: E402
+from oracle.parking_nlp import initial_point     # noqa: E402
+from oracle.parking_solve import solve_parking   # noqa: E402
+
+
+def straight_in(N):
+    """Car above the slot of main.jl:99-108, already aligned with it: reverse straight in (feasible in N = 12 steps)."""
+    sc = scenarios.reverse_parking_scenario()
+    x0 = np.array([0.0, 5.0, np.pi / 2, 0.0])
+    xF = sc["xF"]
+    Ts, L = 0.6, 2.7
+    ys = np.linspace(x0[1], xF[1], N + 1)
+    xWS = np.stack([np.zeros(N + 1), ys, np.full(N + 1, np.pi / 2), np.full(N + 1, -(x0[1] - xF[1]) / (N * Ts))], 1)
+    xWS[0, 3] = 0.0; xWS[-1, 3] = 0.0
+    uWS = np.zeros((N, 2))
+    sc.update(B=1, N=N, Ts=Ts, L=L, ego=np.array([3.7, 1.0, 1.0, 1.0]), XYbounds=np.array([-15.0, 15.0, 1.0, 10.0]),
+              x0=x0[None], rx=xWS[None, :, 0].copy(), ry=xWS[None, :, 1].copy(), ryaw=xWS[None, :, 2].copy(), xWS=xWS[None], uWS=uWS[None])
+    return sc
+
+
+def dense(M):
+    return M.toarray() if hasattr(M, "toarray") else np.asarray(M)
+
+
+@pytest.mark.parametrize("variant", ["d", "sd"])
+def test_slsqp_and_ipm_standin_and_kernel_sources_agree(variant):
+    N = 12
+    sc = straight_in(N)
+    a = (sc["x0"][0], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
+         sc["rx"][0], sc["ry"][0], sc["ryaw"][0], 0, sc["xWS"][0], sc["uWS"][0])
+    out, res, nlp = solve_parking(*a, variant, None, None, ipm_ref.IpmOptions(tol=1e-9, max_iter=300))
+    assert res.status == 1
+    lay = nlp.lay
+    # ---- independent solver: SLSQP on the same callbacks, same starting point as the reference (ParkingSignedDist.jl:213-222) ----
+    gL, gU = nlp.gL, nlp.gU
+    mL, mU = np.isfinite(gL), np.isfinite(gU)
+    cons = [dict(type="eq", fun=nlp.cE, jac=lambda z: dense(nlp.JE(z))),
+            dict(type="ineq", fun=lambda z: np.concatenate([(nlp.g(z) - gL)[mL], (gU - nlp.g(z))[mU]]),
+                 jac=lambda z: np.vstack([dense(nlp.JI(z))[mL], -dense(nlp.JI(z))[mU]]))]
+    lWS, nWS, _, _ = dualmultws_ipm(N, 3, sc["vOb"], sc["A"], sc["b"], sc["rx"][0], sc["ry"][0], sc["ryaw"][0], sc["ego"])
+    z_start = initial_point(lay, sc["xWS"][0], sc["uWS"][0], lWS, nWS)
+    bounds = [(None if not np.isfinite(lo) else lo, None if not np.isfinite(hi) else hi) for lo, hi in zip(nlp.zL, nlp.zU)]
+    r = minimize(nlp.f, z_start, jac=nlp.grad, method="SLSQP", constraints=cons, bounds=bounds, options=dict(ftol=1e-14, maxiter=500))
+    assert r.status == 0, r.message
+    assert np.abs(nlp.cE(r.x)).max() < 1e-9
+    prim = slice(0, lay.oL)                      # x, timeScale, u
+    assert np.abs(r.x[prim] - res.z[prim]).max() < 1e-6
+    assert abs(r.fun - nlp.f(res.z)) < 1e-7
+    # ---- the kernels' own per-stage source (host build) on the same problem ----
+    lp, npp, _, _ = emul.dualmultws_batch(sc)
+    o = emul.default_opts(); o.tol = 1e-8; o.mu_min = 1e-9
+    k = emul.solve_batch(sc, 0, variant, o, lp, npp)
+    assert k["status"][0] == 1
+    xp, up, ts = lay.unpack(r.x)[:3]
+    assert np.abs(k["xp"][0].T - xp).max() < 1e-5 and np.abs(k["up"][0].T - up).max() < 1e-5 and np.abs(k["ts"][0] - ts).max() < 1e-5
