@@ -33,7 +33,7 @@ struct LocalDims {
   static constexpr int I_X = NLT, I_Y = NLT + 1, I_P = NLT + 2;
   static constexpr int ND = NLT + 3;
   static constexpr int NM = ND * (ND + 1) / 2;
-  static constexpr int NFAC = NM - 6 + NLT;       // rows of eliminated unknowns (upper part) + their rhs
+  static constexpr int NFAC = 4 * NLT;            // local step as an affine map of the pose step: a + B (dX, dY, dpsi)
   OBCA_HD static constexpr int il(int i) { return i == 0 ? 0 : i + YN; }   // position of lambda_i
 };
 
@@ -251,14 +251,6 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
 
   int ok = 1;
   // ---- elimination ----
-  // factor layout (strided by fs: workspace arrays): rows 0..NLT-1 of the upper triangle, then their rhs.  A row is
-  // written out as soon as it is final, which frees its registers for the rest of the elimination.
-  auto store_row = [&](int i) {
-    const int q0 = i * ND - (i * (i - 1)) / 2;
-#pragma unroll
-    for (int c_ = i; c_ < ND; ++c_) fac[(size_t)(q0 + c_ - i) * fs] = M[sym_idx<ND>(i, c_)];
-    fac[(size_t)(D::NM - 6 + i) * fs] = r[i];
-  };
   int first = 0;
   if (SDV) {
     // 2x2 pivot on (lambda_0, y_norm)
@@ -283,7 +275,6 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
     }
     // store inverse of the 2x2 block in place of it
     M[sym_idx<ND>(0, 0)] = i00; M[sym_idx<ND>(0, 1)] = i01; M[sym_idx<ND>(1, 1)] = i11;
-    store_row(0); store_row(1);
     first = 2;
   }
 #pragma unroll
@@ -299,11 +290,36 @@ OBCA_HD int obs_condense(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
       for (int c_ = rr; c_ < ND; ++c_) M[sym_idx<ND>(rr, c_)] -= f * M[sym_idx<ND>(i, c_)];
       r[rr] -= f * r[i];
     }
-    store_row(i);
   }
   Sxx[0] = M[sym_idx<ND>(D::I_X, D::I_X)]; Sxx[1] = M[sym_idx<ND>(D::I_X, D::I_Y)]; Sxx[2] = M[sym_idx<ND>(D::I_X, D::I_P)];
   Sxx[3] = M[sym_idx<ND>(D::I_Y, D::I_Y)]; Sxx[4] = M[sym_idx<ND>(D::I_Y, D::I_P)]; Sxx[5] = M[sym_idx<ND>(D::I_P, D::I_P)];
   rx[0] = r[D::I_X]; rx[1] = r[D::I_Y]; rx[2] = r[D::I_P];
+  // Local step as an affine map of the pose step:  x_loc = a + B (dX, dY, dpsi).  Four back-substitutions through the
+  // eliminated rows (rhs: -r, and minus the three coupling columns); 4 NLT doubles go to the workspace instead of the
+  // NM - 6 + NLT of the triangular factor, and the recovery becomes 3 multiply-adds per unknown.
+  //   fac[(4 i + 0) fs] = a_i,   fac[(4 i + 1 + m) fs] = B_i,m   (m = X, Y, psi)
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double x[D::NLT];
+#pragma unroll
+    for (int i = D::NLT - 1; i >= first; --i) {
+      double acc = (m == 0) ? -r[i] : -M[sym_idx<ND>(i, D::NLT + m - 1)];
+#pragma unroll
+      for (int c_ = i + 1; c_ < D::NLT; ++c_) acc -= M[sym_idx<ND>(i, c_)] * x[c_];
+      x[i] = acc * M[sym_idx<ND>(i, i)];      // stored inverse pivot
+    }
+    if (SDV) {
+      double b0 = (m == 0) ? -r[0] : -M[sym_idx<ND>(0, D::NLT + m - 1)];
+      double b1 = (m == 0) ? -r[1] : -M[sym_idx<ND>(1, D::NLT + m - 1)];
+#pragma unroll
+      for (int c_ = 2; c_ < D::NLT; ++c_) { b0 -= M[sym_idx<ND>(0, c_)] * x[c_]; b1 -= M[sym_idx<ND>(1, c_)] * x[c_]; }
+      const double i00 = M[sym_idx<ND>(0, 0)], i01 = M[sym_idx<ND>(0, 1)], i11 = M[sym_idx<ND>(1, 1)];
+      x[0] = i00 * b0 + i01 * b1;
+      x[1] = i01 * b0 + i11 * b1;
+    }
+#pragma unroll
+    for (int i = 0; i < D::NLT; ++i) fac[(size_t)(4 * i + m) * fs] = x[i];
+  }
   return ok;
 }
 
@@ -323,28 +339,10 @@ OBCA_HD void obs_recover(const ParkProblem& P, const ObsRows<VM>& R, const ObsVa
   constexpr int ND = D::ND;
   double x[ND];
   x[D::I_X] = dX; x[D::I_Y] = dY; x[D::I_P] = dP;
-  // row i of the factor starts at roff(i) = sum_{r<i} (ND - r); the rhs follows the NM - 6 matrix entries
-#define OBCA_ROFF(i) ((i) * ND - ((i) * ((i) - 1)) / 2)
-#define OBCA_FAC(e) fac[(size_t)(e) * fs]
-  constexpr int RH = D::NM - 6;
-  constexpr int first = SDV ? 2 : 0;
 #pragma unroll
-  for (int i = D::NLT - 1; i >= first; --i) {
-    double acc = -OBCA_FAC(RH + i);
-#pragma unroll
-    for (int c_ = i + 1; c_ < ND; ++c_) acc -= OBCA_FAC(OBCA_ROFF(i) + (c_ - i)) * x[c_];
-    x[i] = acc * OBCA_FAC(OBCA_ROFF(i));   // stored inverse pivot
-  }
-  if (SDV) {
-    double b0 = -OBCA_FAC(RH + 0), b1 = -OBCA_FAC(RH + 1);
-#pragma unroll
-    for (int c_ = 2; c_ < ND; ++c_) { b0 -= OBCA_FAC(OBCA_ROFF(0) + c_) * x[c_]; b1 -= OBCA_FAC(OBCA_ROFF(1) + (c_ - 1)) * x[c_]; }
-    const double i00 = OBCA_FAC(OBCA_ROFF(0)), i01 = OBCA_FAC(OBCA_ROFF(0) + 1), i11 = OBCA_FAC(OBCA_ROFF(1));
-    x[0] = i00 * b0 + i01 * b1;
-    x[1] = i01 * b0 + i11 * b1;
-  }
-#undef OBCA_ROFF
-#undef OBCA_FAC
+  for (int i = 0; i < D::NLT; ++i)
+    x[i] = fac[(size_t)(4 * i) * fs] + fac[(size_t)(4 * i + 1) * fs] * dX + fac[(size_t)(4 * i + 2) * fs] * dY +
+           fac[(size_t)(4 * i + 3) * fs] * dP;
   const double g3 = P.g[2], g4 = P.g[3];
   double t3d = x[D::I_MU1] + G.e2 * dP, t4d = x[D::I_MU2] - G.e1 * dP;
   double Gd = (-P.g[0] - g3) * x[D::I_MU1] + (-P.g[1] - g4) * x[D::I_MU2] + G.p1 * dX + G.p2 * dY +
