@@ -37,8 +37,22 @@ N_HORIZON = 80
 WORKLOAD = "reverse-parking SD var-time, N=80, 3 obstacles vOb=[2,2,1] (BASELINE config 2)"
 # fused K1 (J/H never reach HBM): 8*(2n+2m+n_par), n=2185, m=1460, n_par=243
 ALG_BYTES_PER_EVAL = 8 * (2 * 2185 + 2 * 1460 + 243)
-NCU_TRAFFIC_BLOCK_FULL_LAUNCH = 203172608 + 526765056      # bytes, profiles/ncu_summary_r01.md (k_pk_block<2,1>, 4096 problems)
-NCU_TRAFFIC_K1_FULL_ROUND = (203172608 + 526765056) + (260452352 + 227575296) + (14526464 + 4274944) + (23077632 + 358144)
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the round kernels with all 4096 problems active, from the committed ncu capture
+    (profiles/ncu_traffic_r01.json, written by tools/ncu_traffic.py from `ncu --set full`).  Returns (block kernel first pass,
+    the four K1 launches of a round) or (None, None)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if not os.path.exists(p):
+        return None, None
+    L = json.load(open(p))["launches"]
+    tot = lambda e: e["dram_read_bytes"] + e["dram_write_bytes"]
+    blk = [e for e in L if e["kernel"].startswith("k_pk_block")]
+    pa = [e for e in L if e["kernel"].startswith("k_pk_phaseA")]
+    if len(blk) < 2 or len(pa) < 2:
+        return None, None
+    return tot(blk[0]), tot(blk[0]) + tot(blk[1]) + tot(pa[0]) + tot(pa[1])
 
 
 def peaks():
@@ -341,21 +355,21 @@ def gpu_arm(args):
                 ach = (ev1 + ev2) * ALG_BYTES_PER_EVAL / t_k1 / 1e9
                 line["roofline_solve"] = line["roofline"]
                 line["roofline"] = {"bound": "hbm", "kernel": "K1 of the rounds: k_pk_block<2,true> + k_pk_phaseA<2,true>", "achieved": ach,
-                                    "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": NCU_TRAFFIC_K1_FULL_ROUND,
+                                    "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic()[1],
                                     "launches": 4 * rnd.value, "ms_per_round": 1e3 * t_k1 / rnd.value, "evaluations": ev1 + ev2,
                                     "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x {ev1 + ev2} K1 evaluations of one solve (device counters) / "
                                             f"summed CUDA-event time of the block + assemble launches; peak {how}; traffic = dram read+write of the four "
-                                            "K1 launches of one round with all 4096 problems active (ncu --set full, profiles/ncu_summary_r01.md): 3.5x "
+                                            "K1 launches of one round with all 4096 problems active (ncu --set full, profiles/ncu_traffic_r01.json): about 3x "
                                             "the algorithmic bytes, because local factors, hand-over records and stage slots cross HBM between kernels"}
                 # the flat block kernel by itself: what it must move by construction, no re-reads
-                blk_bytes = 8.0 * (61 + 201) * NS
+                blk_bytes = 8.0 * (61 + 138) * NS
                 ach_b = ev1 * blk_bytes / (kms[0] * 1e-3) / 1e9
                 line["roofline_block"] = {"bound": "hbm", "kernel": "k_pk_block<2,true> (first pass)", "achieved": ach_b, "peak": hbm, "unit": "GB/s",
-                                          "frac": ach_b / hbm, "traffic": NCU_TRAFFIC_BLOCK_FULL_LAUNCH, "ms_per_launch": kms[0] / rnd.value,
-                                          "note": f"own algorithmic bytes: per problem and evaluation 8 x (61 read + 201 written doubles) x (N+1) = {int(blk_bytes)} B "
-                                                  f"(pose + block variables in; local factor 45 + hand-over record 22 per block out) x {ev1} evaluations / "
-                                                  "event time of its launches; ncu on a full launch: 0.20 GB read + 0.53 GB written in 209 us = 3.5 TB/s "
-                                                  "(53 % of the measured peak) for 0.695 GB algorithmic"}
+                                          "frac": ach_b / hbm, "traffic": ncu_traffic()[0], "ms_per_launch": kms[0] / rnd.value,
+                                          "note": f"own algorithmic bytes: per problem and evaluation 8 x (61 read + 138 written doubles) x (N+1) = {int(blk_bytes)} B "
+                                                  f"(pose + block variables in; local affine map 24 + hand-over record 22 per block out) x {ev1} evaluations / "
+                                                  "event time of its launches; traffic = ncu dram read+write of a launch with all 4096 problems active "
+                                                  "(profiles/ncu_traffic_r01.json)"}
     prof = (C.c_ulonglong * 8)()
     if lib.obca_last_profile(C.c_int(local), prof) == 0 and sum(prof[i] for i in range(6)) > 0:
         names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]
