@@ -1,10 +1,11 @@
 // obca_lib.cu -- sm_100a kernels + the C-ABI of include/obca.h.
 //
 // Kernels
-//   k_parking_solve<VM,SDV>  persistent: one CTA per resident slot, each CTA pulls problems from an atomic queue and
-//                            runs the whole interior-point solve (obca_solver.cuh) with thread k <-> stage k.
-//                            Per-CTA workspace lives in global memory (sized to stay L2 resident), scalar state in
-//                            shared memory.  No host round trip inside a solve; problems finish independently.
+//   obca_phased.cuh          the parking solver: phase-split rounds (k_pk_block, k_pk_phaseA, k_pk_sweep, k_pk_rblock,
+//                            k_pk_phaseC) over all active problems + the persistent tail kernel k_pk_tail
+//   k_parking_solve<VM,SDV>  the monolithic persistent kernel of session 1 (OBCA_MODE=3, cross-check of the above): one CTA
+//                            per resident slot pulls problems from an atomic queue and runs the whole interior-point solve
+//   k_quad_solve<SDV>        quadcopter model (config 4): persistent CTA per problem, block-cooperative 17x21 KKT sweep
 //   k_dualws<VM>             K2: one thread per (problem, stage, obstacle) micro interior-point solve.
 //   k_check                  K5: ParkingConstraints twin + strict audit, one CTA per problem.
 // There is NO CPU fallback: every compute entry point returns OBCA_ERR_NO_DEVICE without a CUDA device.

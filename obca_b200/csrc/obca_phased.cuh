@@ -3,19 +3,24 @@
 // The interior-point loop of IpmDriver<M>::solve (obca_solver.cuh) restated as a per-problem state machine so that
 // every phase of an iteration runs as its own kernel over ALL active problems of the batch, each with the launch
 // shape that suits it:
-//     k_pk_phaseA   CTA per problem, thread per stage : accept step -> K1 evaluate + assemble -> barrier update
+//     k_pk_block    flat, thread per (problem, obstacle, stage) : the OBCA constraint blocks of K1 -- evaluation, KKT-error
+//                                                        partials, condensation onto the stage pose (streaming, no barriers)
+//     k_pk_phaseA   CTA per problem, thread per stage : stage terms of K1 (dynamics, objective, bounds), assembly of the
+//                                                        stage models, reductions, convergence test, barrier update
+//     (both once more for the problems whose barrier parameter was just reduced)
 //     k_pk_sweep    HALF-WARP per problem              : K3 stage-banded KKT sweep, stage slots streamed from HBM
 //                                                        through a cp.async ring; inertia-correction bookkeeping
-//     k_pk_phaseC   CTA per problem, thread per stage : K4 step recovery, fraction-to-the-boundary, filter line search
-// The iterate, the step, the local factors and the stage slots of every problem live in HBM (layout: problem-major,
+//     k_pk_rblock   flat, thread per (problem, obstacle, stage) : K4 step of the block unknowns from the stored local map
+//     k_pk_phaseC   CTA per problem, thread per stage : K4 costates, fraction-to-the-boundary, filter line search, update
+// The iterate, the step, the local maps, the block hand-over records and the stage slots of every problem live in HBM (layout: problem-major,
 // then [array][stage], so each warp streams contiguous slices); between kernels a problem is described by its
 // ProbState record (phase, iteration, barrier parameter, filter, ...).
 // When the active set has shrunk below what one wave of resident CTAs can hold, the remaining problems are handed to
 //     k_pk_tail     persistent CTA per problem: the same three phase functions in a loop, stage slots in shared memory
 // which is also the whole solver for small batches.
 //
-// The arithmetic and its order are exactly those of IpmDriver<M>::solve: both drivers produce bit-identical iterates
-// (tests/test_gpu_parking.py::test_phased_equals_persistent).
+// The arithmetic and its order are exactly those of IpmDriver<M>::solve, and the library is built without FMA contraction:
+// all schedules produce bit-identical iterates (tests/test_gpu_parking.py::test_phased_equals_persistent).
 #pragma once
 #include "obca_check.cuh"
 #include "obca_solver.cuh"
