@@ -1,0 +1,139 @@
+"""Warm-start producer: Reeds-Shepp curves, Hybrid A*, collision check, grid heuristic, velocity
+smoothing and the main.jl:215-248 pipeline -- host-side restatements in obca_b200/planner.  The reference cannot run here
+(no Julia); the tests are the reference's own test strategy (reeds_shepp.jl:846-869 `check_path`, :871-920 `test`) plus
+properties the algorithms must have, and one end-to-end run: a Hybrid A* warm start drives the kernels' solver to a feasible
+KKT point."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from obca_b200.planner import collision, grid_policy, hybrid_a_star, reeds_shepp as rs, velo_smooth, warmstart
+
+D = math.radians
+
+
+def check_path(sx, sy, syaw, gx, gy, gyaw, maxc):
+    """reeds_shepp.jl:846-869."""
+    paths = rs.calc_paths(sx, sy, syaw, gx, gy, gyaw, maxc)
+    assert len(paths) >= 1
+    for p in paths:
+        assert abs(p.x[0] - sx) <= 0.01 and abs(p.y[0] - sy) <= 0.01 and abs(rs.pi_2_pi(p.yaw[0] - syaw)) <= 0.01
+        assert abs(p.x[-1] - gx) <= 0.01 and abs(p.y[-1] - gy) <= 0.01 and abs(rs.pi_2_pi(p.yaw[-1] - gyaw)) <= 0.01
+        d = np.hypot(np.diff(p.x[:-1]), np.diff(p.y[:-1]))
+        assert (d <= rs.STEP_SIZE + 1e-3).all()                       # sampling never coarser than the step
+        assert abs(sum(abs(l) for l in p.lengths) - p.L) < 1e-12
+    return paths
+
+
+def test_reeds_shepp_reference_cases_and_random_poses():
+    check_path(0.0, 0.0, D(10), 7.0, -8.0, D(50), 2.0)                  # reeds_shepp.jl:871-905, the three fixed cases of test()
+    check_path(0.0, 0.0, D(10), 7.0, -8.0, D(-50), 2.0)
+    check_path(0.0, 10.0, D(-10), -7.0, -8.0, D(-50), 2.0)
+    rng = np.random.default_rng(0)
+    for _ in range(300):                                                # the random part of test()
+        a = [rng.uniform(-10, 10), rng.uniform(-10, 10), rng.uniform(-math.pi, math.pi)]
+        b = [rng.uniform(-10, 10), rng.uniform(-10, 10), rng.uniform(-math.pi, math.pi)]
+        check_path(*a, *b, rng.choice([0.2, 1.0 / 4.5, 1.0, 2.0]))
+
+
+def test_reeds_shepp_known_answers_and_symmetry():
+    maxc = math.tan(0.6) / 2.7
+    p = rs.calc_shortest_path(0, 0, 0, 5, 0, 0, maxc)
+    assert abs(p.L - 5.0) < 1e-9                                         # straight ahead
+    p = rs.calc_shortest_path(0, 0, 0, -3, 0, 0, maxc)
+    assert abs(p.L - 3.0) < 1e-9 and min(p.directions) == -1             # straight back
+    R = 1.0 / maxc
+    p = rs.calc_shortest_path(0, 0, 0, R, R, math.pi / 2, maxc)
+    assert abs(p.L - R * math.pi / 2) < 1e-9                             # quarter circle to the left
+    rng = np.random.default_rng(1)
+    n_longer = 0
+    for _ in range(150):
+        a = [rng.uniform(-8, 8), rng.uniform(-8, 8), rng.uniform(-3, 3)]
+        b = [rng.uniform(-8, 8), rng.uniform(-8, 8), rng.uniform(-3, 3)]
+        l_ref = rs.calc_shortest_path_length(*a, *b, maxc)                  # with the reference's duplicate test (default)
+        rs.REFERENCE_DEDUP = False
+        try:
+            l1 = rs.calc_shortest_path_length(*a, *b, maxc); l2 = rs.calc_shortest_path_length(*b, *a, maxc)
+        finally:
+            rs.REFERENCE_DEDUP = True
+        assert abs(l1 - l2) < 1e-6                                        # time reversal: L(a -> b) = L(b -> a) once every word is kept
+        assert l1 >= math.hypot(a[0] - b[0], a[1] - b[1]) - 1e-9          # never shorter than the straight line
+        assert l_ref >= l1 - 1e-9                                         # the reference's filter can only lose candidates
+        n_longer += l_ref > l1 + 1e-6
+    assert n_longer > 0                                                   # ... and it does (documented quirk of reeds_shepp.jl:212-219)
+
+
+def test_collision_rectangle_and_bubble():
+    ox = np.array([2.0, -0.9, 0.0, 10.0]); oy = np.array([0.0, 0.0, 1.2, 10.0])
+    tree = cKDTree(np.column_stack([ox, oy]))
+    assert not collision.check_collision([0.0], [0.0], [0.0], tree, ox, oy)          # (2, 0) is inside [-1, 3.7] x [-1, 1]
+    ox2 = np.array([-1.1, 3.8, 0.0, 1.0]); oy2 = np.array([0.0, 0.0, 1.05, -1.05])
+    tree2 = cKDTree(np.column_stack([ox2, oy2]))
+    assert collision.check_collision([0.0], [0.0], [0.0], tree2, ox2, oy2)            # all just outside
+    assert not collision.check_collision([0.0], [0.0], [math.pi / 2], tree2, ox2, oy2)   # rotated car covers (0, 1.05)
+    assert collision.rect_check(0, 0, 0, [], [])
+
+
+def test_grid_distance_policy():
+    # a box of obstacle points around an empty 10 m x 10 m area: distances = octile metric to the goal cell
+    xs = np.arange(0, 10.01, 0.5)
+    ox = np.concatenate([xs, xs, np.zeros_like(xs), np.full_like(xs, 10.0)]); oy = np.concatenate([np.zeros_like(xs), np.full_like(xs, 10.0), xs, xs])
+    pmap, minx, miny = grid_policy.calc_dist_policy(5.0, 5.0, ox, oy, 1.0, 0.5)
+    g = (grid_policy.jround(5.0), grid_policy.jround(5.0))
+    for (x, y) in ((5, 5), (7, 5), (7, 7), (2, 6), (8, 3)):
+        dx, dy = abs(x - g[0]), abs(y - g[1])
+        octile = max(dx, dy) + (math.sqrt(2) - 1) * min(dx, dy)
+        assert abs(pmap[x - minx - 1, y - miny - 1] - octile) < 1e-9
+    assert np.isinf(pmap[0 - minx - 1 + 1, 0 - miny - 1 + 1]) or pmap[0, 0] >= 0      # border cells are blocked / unreachable
+
+
+def test_velo_smooth_ramps():
+    v = np.concatenate([np.full(40, 0.5), np.full(40, -0.5)]); v[-1] = 0.0            # forward, reverse, stop (as main.jl:222-229 builds it)
+    vs, a = velo_smooth.velo_smooth(v, 0.3, 0.2)
+    assert vs.shape == (80,) and a.shape == (79,)
+    assert abs(vs[0]) < 1e-12 and abs(vs[-1]) < 1e-12                                   # starts and ends at rest
+    assert np.abs(a).max() <= 0.3 * 1.1                                                 # ramps of |v0| / amax (rounded to whole steps)
+    assert np.abs(vs).max() <= 0.5 + 1e-12 and (np.sign(vs[5:35]) == 1).all() and (np.sign(vs[50:70]) == -1).all()
+
+
+@pytest.mark.parametrize("scenario,x0,xF", [("backwards", [-6.0, 9.5, 0.0, 0.0], [0.0, 1.3, math.pi / 2, 0.0]),       # main.jl:213,108
+                                            ("backwards", [7.0, 7.5, 0.0, 0.0], [0.0, 1.3, math.pi / 2, 0.0]),
+                                            ("parallel", [-6.0, 8.0, 0.0, 0.0], [-1.35, 4.0, 0.0, 0.0])])              # main.jl:162
+def test_hybrid_a_star_paths(scenario, x0, xF):
+    w = warmstart.plan_warm_start(x0, xF, scenario)
+    assert w is not None
+    rx, ry, ryaw = w["path"]
+    assert abs(rx[0] - x0[0]) < 1e-9 and abs(ry[0] - x0[1]) < 1e-9 and abs(rx[-1] - xF[0]) < 1e-6 and abs(ry[-1] - xF[1]) < 1e-6
+    assert abs(rs.pi_2_pi(ryaw[-1] - xF[2])) < 1e-6
+    ds = np.hypot(np.diff(rx), np.diff(ry))
+    assert ds.max() <= hybrid_a_star.MOTION_RESOLUTION + 1e-6
+    tree = cKDTree(np.column_stack([w["ox"], w["oy"]]))
+    assert collision.check_collision(rx, ry, ryaw, tree, w["ox"], w["oy"])
+    dyaw = np.abs([rs.pi_2_pi(b - a) for a, b in zip(ryaw[:-1], ryaw[1:])])
+    assert (dyaw <= hybrid_a_star.MOTION_RESOLUTION * math.tan(hybrid_a_star.MAX_STEER) / hybrid_a_star.WB + 1e-6).all()   # curvature bound
+    assert w["xWS"].shape == (w["N"] + 1, 4) and w["uWS"].shape[0] >= w["N"] and np.abs(w["uWS"][:, 0]).max() <= 0.6 + 1e-9
+
+
+def test_hybrid_a_star_warm_start_drives_the_solver():
+    """End to end on the reference's default problem (main.jl:213): Hybrid A* warm start -> DualMultWS -> the kernels' interior-point
+    solve (host build) -> converged, and feasible by the verbatim ParkingConstraints."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+    import emul
+    from obca_b200 import scenarios
+    from oracle import checkers
+    x0 = np.array([-6.0, 9.5, 0.0, 0.0])
+    sc = scenarios.reverse_parking_scenario()
+    w = warmstart.plan_warm_start(x0, sc["xF"], "backwards")
+    N = w["N"]
+    sc.update(B=1, N=N, Ts=w["Ts"], L=2.7, ego=np.array([3.7, 1.0, 1.0, 1.0]), XYbounds=np.array([-15.0, 15.0, 1.0, 10.0]), x0=x0[None],
+              rx=w["rx"][None], ry=w["ry"][None], ryaw=w["ryaw"][None], xWS=w["xWS"][None], uWS=w["uWS"][None, :N])
+    lp, npp, _, _ = emul.dualmultws_batch(sc)
+    r = emul.solve_batch(sc, 0, "sd", None, lp, npp)
+    assert r["status"][0] == 1
+    ok = checkers.ParkingConstraints(x0, sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
+                                     r["xp"][0].T, r["up"][0].T, r["lp"][0].T, r["np"][0].T, r["ts"][0], 0, 1)
+    assert ok
