@@ -137,3 +137,34 @@ def test_hybrid_a_star_warm_start_drives_the_solver():
     ok = checkers.ParkingConstraints(x0, sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
                                      r["xp"][0].T, r["up"][0].T, r["lp"][0].T, r["np"][0].T, r["ts"][0], 0, 1)
     assert ok
+
+
+def test_quadcopter_3d_astar_warm_start_and_solve():
+    """mainQuadcopter.jl:114-137 on its default problem: the 3-D A* path goes under the first wall and through the window of
+    the second one; the warm start built from it drives the kernels' quadcopter solver (host build) to a point that passes the
+    verbatim constrSatisfaction."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+    import emul
+    from obca_b200 import scenarios
+    from obca_b200.planner import a_star_3d
+    from oracle import checkers
+    sc = scenarios.quadcopter_scenario()
+    w = a_star_3d.plan_quadcopter_warm_start(sc["x0"], sc["xF"])
+    assert w is not None
+    rx, ry, rz = w["path"]
+    assert (rx[0], ry[0], rz[0]) == (10.0, 10.0, 30.0) and (rx[-1], ry[-1], rz[-1]) == (90.0, 30.0, 20.0)
+    step = np.sqrt(np.diff(rx) ** 2 + np.diff(ry) ** 2 + np.diff(rz) ** 2)
+    assert set(np.round(step ** 2).astype(int)) <= {1, 2, 3}                            # 26-neighbourhood moves
+    in1 = (rx >= 20) & (rx <= 25); in2 = (rx >= 70) & (rx <= 75)
+    assert in1.any() and (rz[in1] <= 6 - a_star_3d.VEHICLE_RADIUS + 1e-9).all()         # under the first wall, a vehicle radius away
+    assert in2.any() and (ry[in2] > 40).all() and (ry[in2] < 50).all() and (rz[in2] > 20).all() and (rz[in2] < 30).all()   # window
+    ox, oy, oz, lo, hi = a_star_3d.quadcopter_environment()
+    tree = cKDTree(np.column_stack([ox, oy, oz]))
+    dmin, _ = tree.query(np.column_stack([rx, ry, rz]))
+    assert dmin.min() > a_star_3d.VEHICLE_RADIUS                                        # never inside the inflated obstacles
+    assert w["N"] == rx.size - 1 and w["Ts"] == round(0.25 * 80 / w["N"] * 100) / 100 and w["xWS"].shape == (12, w["N"] + 1)
+    sc.update(B=1, N=w["N"], Ts=w["Ts"], x0=sc["x0"][None], xF=sc["xF"][None], xWS=w["xWS"][None], timeWS=w["timeWS"])
+    o = emul.default_opts(); o.max_iter = 3000
+    r = emul.quad_solve_batch(sc, "d", o)
+    assert r["status"][0] == 1
+    assert checkers.constrSatisfaction(r["xp"][0], r["up"][0], r["ts"][0], sc["x0"][0], sc["xF"][0], sc["Ts"], r["lp"][0], *sc["obs"], sc["R"])
