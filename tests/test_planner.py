@@ -40,6 +40,31 @@ def test_reeds_shepp_reference_cases_and_random_poses():
         check_path(*a, *b, rng.choice([0.2, 1.0 / 4.5, 1.0, 2.0]))
 
 
+def _drive(pose, lengths, ctypes, maxc):
+    """Independent of the module's sampling code: exact unicycle motion along each segment (arc of curvature +-maxc or straight)."""
+    x, y, th = pose
+    for l, c in zip(lengths, ctypes):
+        if c == "S":
+            x += l * math.cos(th); y += l * math.sin(th)
+        else:
+            k = maxc if c == "L" else -maxc
+            x += (math.sin(th + k * l) - math.sin(th)) / k
+            y += (-math.cos(th + k * l) + math.cos(th)) / k
+            th += k * l
+    return x, y, th
+
+
+def test_reeds_shepp_words_reach_the_goal_when_driven():
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        a = [rng.uniform(-10, 10), rng.uniform(-10, 10), rng.uniform(-math.pi, math.pi)]
+        b = [rng.uniform(-10, 10), rng.uniform(-10, 10), rng.uniform(-math.pi, math.pi)]
+        maxc = rng.choice([0.2, 1.0 / 4.5, 1.0])
+        for p in rs.calc_paths(*a, *b, maxc):
+            x, y, th = _drive(a, p.lengths, p.ctypes, maxc)             # p.lengths are metres after calc_paths
+            assert abs(x - b[0]) < 1e-6 and abs(y - b[1]) < 1e-6 and abs(rs.pi_2_pi(th - b[2])) < 1e-6, (p.ctypes, p.lengths)
+
+
 def test_reeds_shepp_known_answers_and_symmetry():
     maxc = math.tan(0.6) / 2.7
     p = rs.calc_shortest_path(0, 0, 0, 5, 0, 0, maxc)
