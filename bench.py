@@ -307,6 +307,19 @@ def gpu_arm(args):
                          "frac": achieved / hbm, "traffic": None,
                          "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x (iterations+1) per problem (SURVEY 8d, fused K1); "
                                  f"peak {how}; the solver is FP64-latency bound, see DESIGN.md and profiles/"}}
+    # ---- acceptance of the end-to-end outputs by the reference's own checker (k_check through the C-ABI) + iteration histogram ----
+    try:
+        from obca_b200 import parking as _pk
+        T_ = lambda t: np.transpose(t.numpy(), (0, 2, 1))
+        feas, _, strict = _pk.check_parking_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], nOb, sc["vOb"], sc["A"],
+                                                  sc["b"], T_(hout["xp"]), T_(hout["up"]), T_(hout["lp"]), T_(hout["np"]), hout["ts"].numpy(), 0, 1,
+                                                  T_(hout["sl"]), opts)
+        line["config"]["checker_pass_frac_rank0"] = float(np.mean(feas))        # verbatim ParkingConstraints (5e-5)
+        line["config"]["strict_audit_pass_frac_rank0"] = float(np.mean(strict))
+        line["config"]["iters_hist_by_10_rank0"] = np.bincount(np.minimum(hit.numpy() // 10, 20), minlength=21).tolist()
+    except Exception as e:                                                       # diagnostic only: never fail the bench line
+        line["config"]["checker_pass_frac_rank0"] = None
+        line["config"]["checker_note"] = repr(e)[:160]
     # ---- K1 stand-alone (fused constraint / Lagrangian-gradient evaluation) at the solution points: HBM roofline ----
     nn = C.c_longlong(); mm = C.c_longlong()
     lib.obca_parking_eval_sizes(C.c_int(N), C.c_int(nOb), NP(vOb), C.c_int(1), C.byref(nn), C.byref(mm))
