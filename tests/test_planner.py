@@ -193,3 +193,15 @@ def test_quadcopter_3d_astar_warm_start_and_solve():
     r = emul.quad_solve_batch(sc, "d", o)
     assert r["status"][0] == 1
     assert checkers.constrSatisfaction(r["xp"][0], r["up"][0], r["ts"][0], sc["x0"][0], sc["xF"][0], sc["Ts"], r["lp"][0], *sc["obs"], sc["R"])
+
+
+def test_planners_report_failure_instead_of_raising():
+    """The reference prints an error and returns `nothing` when the open set runs dry (hybrid_a_star.jl:140-143); here: None."""
+    ox, oy = warmstart.obstacle_points("backwards")
+    # goal pose buried in the left obstacle block: every analytic expansion collides and the goal cell is unreachable
+    rx, ry, ryaw = hybrid_a_star.calc_hybrid_astar_path(-6.0, 9.5, 0.0, -6.0, 4.9, math.pi / 2, ox, oy, max_expansions=300)
+    assert rx is None and ry is None and ryaw is None
+    from obca_b200.planner import a_star_3d
+    pts = np.array([(x, y, z) for x in range(4, 7) for y in range(0, 11) for z in range(0, 11)], float)      # a full wall
+    r = a_star_3d.calc_astar_path(1.0, 5.0, 5.0, 9.0, 5.0, 5.0, pts[:, 0], pts[:, 1], pts[:, 2], 0.0, 0.0, 0.0, 10.0, 10.0, 10.0, 1.0)
+    assert r == (None, None, None)
