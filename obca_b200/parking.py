@@ -160,3 +160,27 @@ def eval_batch(x0, xF, N, Ts, L, ego_, XYbounds, nOb, vOb, A, b, rx, ry, ryaw, f
         P(dlp), P(dnp), P(dsl), P(dy), C.c_int(int(fixTime)), C.c_int(int(signed_dist)), C.byref(o), P(c), P(g), P(fk),
         C.c_int(int(reps)), ptr(ms)))
     return c.cpu().numpy(), g.cpu().numpy(), fk.sum(1).cpu().numpy(), float(ms[0])
+
+
+def parking_solve_planned(x0s, xF, plans, Ts, L, ego_, XYbounds, nOb, vOb, A, b, fixTime=0, signed_dist=1, opts=None,
+                          solve=None):
+    """Solve problems whose warm starts came from the Hybrid A* producer (obca_b200.planner.warmstart.plan_batch): their horizons
+    differ, the batched entry point takes one N per call, so the problems are grouped by N, every group goes through
+    parking_solve_batch, and the results come back in the caller's order (lists of per-problem arrays in the Julia shapes
+    4 x (N_i+1), 2 x N_i, ...; None where the planner found no path).  `solve`: injection point for tests."""
+    from .planner.warmstart import group_by_horizon
+    solve = solve or parking_solve_batch
+    x0s = np.asarray(x0s, float).reshape(-1, 4)
+    out = dict(xp=[None] * len(plans), up=[None] * len(plans), ts=[None] * len(plans), lp=[None] * len(plans), np=[None] * len(plans),
+               exitflag=np.zeros(len(plans), np.int32), iters=np.zeros(len(plans), np.int32), N=np.zeros(len(plans), np.int32), time=0.0)
+    for N, idx in group_by_horizon(plans).items():
+        g = [plans[i] for i in idx]
+        r = solve(x0s[idx], xF, N, Ts, L, ego_, XYbounds, nOb, vOb, A, b, np.stack([w["rx"] for w in g]), np.stack([w["ry"] for w in g]),
+                  np.stack([w["ryaw"] for w in g]), fixTime, np.stack([w["xWS"] for w in g]), np.stack([w["uWS"][:N] for w in g]),
+                  signed_dist, None, None, opts)
+        for k, i in enumerate(idx):
+            for key in ("xp", "up", "ts", "lp", "np"):
+                out[key][i] = r[key][k]
+            out["exitflag"][i] = r["exitflag"][k]; out["iters"][i] = r["iters"][k]; out["N"][i] = N
+        out["time"] += float(r["time"])
+    return out

@@ -4,6 +4,7 @@ NLP grid.  Output = exactly what main.jl hands to ParkingDist / ParkingSignedDis
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -80,3 +81,33 @@ def plan_warm_start(x0, xF, scenario="backwards", Ts=None, L=2.7, sampleN=3):
     out = warm_start_from_path(rx, ry, ryaw, Ts, L, sampleN, hybrid_a_star.MOTION_RESOLUTION)
     out.update(path=(rx, ry, ryaw), Ts=Ts, ox=ox, oy=oy)
     return out
+
+
+def _plan_one(args):
+    x0, xF, scenario = args
+    w = plan_warm_start(x0, xF, scenario)
+    if w is not None:
+        w.pop("ox", None); w.pop("oy", None)          # the point clouds are per scenario, not per problem
+    return w
+
+
+def plan_batch(x0s, xF, scenario="backwards", workers=None):
+    """Hybrid A* warm starts for many start poses (the randomised sweeps of main.jl:165-168), one planner run per pose on a pool
+    of host processes.  Returns a list of plan_warm_start() dicts (None where no path was found); N differs from pose to pose,
+    as in the reference."""
+    import multiprocessing as mp
+    jobs = [(np.asarray(x, float), np.asarray(xF, float), scenario) for x in x0s]
+    workers = workers or min(len(jobs), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    if workers <= 1 or len(jobs) <= 1:
+        return [_plan_one(j) for j in jobs]
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_plan_one, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+
+
+def group_by_horizon(plans):
+    """The batched C-ABI takes one horizon N per call: indices of the successfully planned problems grouped by N."""
+    groups = {}
+    for i, w in enumerate(plans):
+        if w is not None:
+            groups.setdefault(int(w["N"]), []).append(i)
+    return dict(sorted(groups.items()))

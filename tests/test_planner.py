@@ -205,3 +205,32 @@ def test_planners_report_failure_instead_of_raising():
     pts = np.array([(x, y, z) for x in range(4, 7) for y in range(0, 11) for z in range(0, 11)], float)      # a full wall
     r = a_star_3d.calc_astar_path(1.0, 5.0, 5.0, 9.0, 5.0, 5.0, pts[:, 0], pts[:, 1], pts[:, 2], 0.0, 0.0, 0.0, 10.0, 10.0, 10.0, 1.0)
     assert r == (None, None, None)
+
+
+def test_planned_batches_are_grouped_by_horizon_and_scattered_back():
+    """Hybrid A* horizons differ from pose to pose; the batched entry point takes one N per call.  plan_batch + the grouping
+    wrapper of the host mirror: every problem is solved exactly once, in a batch of its own horizon, and lands at its own index
+    (the GPU solve is replaced by a recording stub -- the real one is covered by the -m gpu tests)."""
+    from obca_b200 import parking, scenarios
+    sc = scenarios.reverse_parking_scenario()
+    x0s = np.array([[-6.0, 9.5, 0, 0], [7.0, 7.5, 0, 0], [-6.0, 9.5, 0, 0], [-6.0, 4.9, 0, 0], [3.0, 8.0, 0, 0]])   # #3 starts inside an obstacle
+    plans = warmstart.plan_batch(x0s, sc["xF"], "backwards", workers=2)
+    assert plans[3] is None and all(p is not None for i, p in enumerate(plans) if i != 3)
+    assert plans[0]["N"] == plans[2]["N"] and np.array_equal(plans[0]["xWS"], plans[2]["xWS"])             # deterministic
+    groups = warmstart.group_by_horizon(plans)
+    assert sorted(i for g in groups.values() for i in g) == [0, 1, 2, 4]
+    calls = []
+
+    def stub(x0, xF, N, Ts, L, ego, XYb, nOb, vOb, A, b, rx, ry, ryaw, fixTime, xWS, uWS, sd, lWS, nWS, opts):
+        B = len(x0)
+        assert rx.shape == (B, N + 1) and xWS.shape == (B, N + 1, 4) and uWS.shape == (B, N, 2)
+        calls.append((N, B))
+        return dict(xp=np.broadcast_to(x0[:, :, None], (B, 4, N + 1)).copy(), up=np.zeros((B, 2, N)), ts=np.ones((B, N + 1)),
+                    lp=np.zeros((B, 5, N + 1)), np=np.zeros((B, 12, N + 1)), exitflag=np.ones(B, np.int32), iters=np.full(B, 7, np.int32), time=0.01)
+
+    r = parking.parking_solve_planned(x0s, sc["xF"], plans, 0.6, 2.7, np.array([3.7, 1, 1, 1.0]), np.array([-15, 15, 1, 10.0]), sc["nOb"], sc["vOb"],
+                                      sc["A"], sc["b"], solve=stub)
+    assert sorted(calls) == sorted((N, len(g)) for N, g in groups.items())
+    assert r["xp"][3] is None and r["exitflag"][3] == 0
+    for i in (0, 1, 2, 4):
+        assert r["xp"][i].shape == (4, plans[i]["N"] + 1) and np.allclose(r["xp"][i][:, 0], x0s[i]) and r["N"][i] == plans[i]["N"]
