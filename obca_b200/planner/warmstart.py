@@ -100,7 +100,7 @@ def plan_batch(x0s, xF, scenario="backwards", workers=None):
     workers = workers or min(len(jobs), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     if workers <= 1 or len(jobs) <= 1:
         return [_plan_one(j) for j in jobs]
-    with mp.get_context("fork").Pool(workers) as pool:
+    with mp.get_context("spawn").Pool(workers) as pool:      # spawn: safe next to the threads of torch / BLAS in the parent
         return pool.map(_plan_one, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
 
 
