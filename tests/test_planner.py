@@ -234,3 +234,15 @@ def test_planned_batches_are_grouped_by_horizon_and_scattered_back():
     assert r["xp"][3] is None and r["exitflag"][3] == 0
     for i in (0, 1, 2, 4):
         assert r["xp"][i].shape == (4, plans[i]["N"] + 1) and np.allclose(r["xp"][i][:, 0], x0s[i]) and r["N"][i] == plans[i]["N"]
+
+
+def test_example_main_parking_dry_run():
+    """examples/main_parking.py (the main.jl flow): without a CUDA device it must plan, build the warm start, marshal the
+    arguments of the reference-named entry points and stop with the library's no-device message -- never with a traceback."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(root, "examples", "main_parking.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert "Hybrid A*:" in p.stdout and "N = 64" in p.stdout
+    assert "Traceback" not in p.stderr
+    assert p.returncode == 2 and "solve not run" in p.stdout
