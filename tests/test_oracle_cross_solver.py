@@ -41,12 +41,12 @@ def dense(M):
     return M.toarray() if hasattr(M, "toarray") else np.asarray(M)
 
 
-@pytest.mark.parametrize("variant", ["d", "sd"])
-def test_slsqp_and_ipm_standin_and_kernel_sources_agree(variant):
+@pytest.mark.parametrize("variant,fix", [("d", 0), ("sd", 0), ("sd", 1)])
+def test_slsqp_and_ipm_standin_and_kernel_sources_agree(variant, fix):
     N = 12
     sc = straight_in(N)
     a = (sc["x0"][0], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
-         sc["rx"][0], sc["ry"][0], sc["ryaw"][0], 0, sc["xWS"][0], sc["uWS"][0])
+         sc["rx"][0], sc["ry"][0], sc["ryaw"][0], fix, sc["xWS"][0], sc["uWS"][0])
     out, res, nlp = solve_parking(*a, variant, None, None, ipm_ref.IpmOptions(tol=1e-9, max_iter=300))
     assert res.status == 1
     lay = nlp.lay
@@ -63,12 +63,12 @@ def test_slsqp_and_ipm_standin_and_kernel_sources_agree(variant):
     assert r.status == 0, r.message
     assert np.abs(nlp.cE(r.x)).max() < 1e-9
     prim = slice(0, lay.oL)                      # x, timeScale, u
-    assert np.abs(r.x[prim] - res.z[prim]).max() < 1e-6
+    assert np.abs(r.x[prim] - res.z[prim]).max() < 5e-6      # the interior-point iterate sits O(mu / z) inside weakly active bounds
     assert abs(r.fun - nlp.f(res.z)) < 1e-7
     # ---- the kernels' own per-stage source (host build) on the same problem ----
     lp, npp, _, _ = emul.dualmultws_batch(sc)
     o = emul.default_opts(); o.tol = 1e-8; o.mu_min = 1e-9
-    k = emul.solve_batch(sc, 0, variant, o, lp, npp)
+    k = emul.solve_batch(sc, fix, variant, o, lp, npp)
     assert k["status"][0] == 1
     xp, up, ts = lay.unpack(r.x)[:3]
     assert np.abs(k["xp"][0].T - xp).max() < 1e-5 and np.abs(k["up"][0].T - up).max() < 1e-5 and np.abs(k["ts"][0] - ts).max() < 1e-5
