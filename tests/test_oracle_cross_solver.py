@@ -32,7 +32,7 @@ def straight_in(N):
     xWS = np.stack([np.zeros(N + 1), ys, np.full(N + 1, np.pi / 2), np.full(N + 1, -(x0[1] - xF[1]) / (N * Ts))], 1)
     xWS[0, 3] = 0.0; xWS[-1, 3] = 0.0
     uWS = np.zeros((N, 2))
-    sc.update(B=1, N=N, Ts=Ts, L=L, ego=np.array([3.7, 1.0, 1.0, 1.0]), XYbounds=np.array([-15.0, 15.0, 1.0, 10.0]),
+    sc.update(B=1, N=N, Ts=Ts, Ts_fix=Ts, L=L, ego=np.array([3.7, 1.0, 1.0, 1.0]), XYbounds=np.array([-15.0, 15.0, 1.0, 10.0]),
               x0=x0[None], rx=xWS[None, :, 0].copy(), ry=xWS[None, :, 1].copy(), ryaw=xWS[None, :, 2].copy(), xWS=xWS[None], uWS=uWS[None])
     return sc
 
@@ -71,4 +71,5 @@ def test_slsqp_and_ipm_standin_and_kernel_sources_agree(variant, fix):
     k = emul.solve_batch(sc, fix, variant, o, lp, npp)
     assert k["status"][0] == 1
     xp, up, ts = lay.unpack(r.x)[:3]
-    assert np.abs(k["xp"][0].T - xp).max() < 1e-5 and np.abs(k["up"][0].T - up).max() < 1e-5 and np.abs(k["ts"][0] - ts).max() < 1e-5
+    tol = 5e-5       # interior point: O(mu / z) inside weakly active bounds
+    assert np.abs(k["xp"][0].T - xp).max() < tol and np.abs(k["up"][0].T - up).max() < tol and np.abs(k["ts"][0] - ts).max() < tol
