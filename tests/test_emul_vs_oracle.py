@@ -104,3 +104,24 @@ def test_warp_kkt_lane_code_matches_serial_riccati(tmp_path):
         outs.append(np.load(f))
     for key in ("xp", "up", "lp", "np", "ts"):
         assert np.abs(outs[0][key] - outs[1][key]).max() < 1e-7, key   # round-off x 1/dc (terminal penalty 1e9)
+
+
+def test_maximum_shape_on_the_host_build():
+    """Largest shape the kernels are built for: N + 1 = 128 stages, 5 obstacles, up to 4 half-spaces per obstacle (the VM = 4
+    instantiation with ragged counts 2, 2, 1, 4, 4): converges, KKT point of the reference NLP, passes the verbatim checker."""
+    N = 127
+    sc = scenarios.reverse_parking_batch(2, N, seed=4)
+
+    def box(xl, xu, yl, yu):                      # {x : A x <= b}
+        return np.array([[1.0, 0], [-1, 0], [0, 1], [0, -1]]), np.array([[xu], [-xl], [yu], [-yl]])
+    A1, b1 = box(11, 13, 6, 8); A2, b2 = box(-13, -11, 6, 8)
+    sc["A"] = np.vstack([sc["A"], A1, A2]); sc["b"] = np.vstack([np.asarray(sc["b"]).reshape(-1, 1), b1, b2])
+    sc["vOb"] = np.array(list(sc["vOb"]) + [4, 4]); sc["nOb"] = 5
+    lp, npp, _, _ = emul.dualmultws_batch(sc)
+    r = emul.solve_batch(sc, 0, "sd", None, lp, npp)
+    assert (r["status"] == 1).all() and r["lp"].shape == (2, N + 1, 13) and r["np"].shape == (2, N + 1, 20)
+    rr = dict(xp=T(r["xp"]), up=T(r["up"]), ts=r["ts"], lp=T(r["lp"]), np=T(r["np"]), sl=T(r["sl"]))
+    e = kkt_check.reference_kkt_error(sc, 0, rr)
+    assert e["E0"] < 1e-5
+    assert checkers.ParkingConstraints(sc["x0"][0], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 5, sc["vOb"], sc["A"], sc["b"],
+                                       rr["xp"][0], rr["up"][0], rr["lp"][0], rr["np"][0], rr["ts"][0], 0, 1)
