@@ -2,7 +2,8 @@
 """bench.py -- OBCA trajectories/sec on BASELINE config 2 (reverse parking, N=80, 3 obstacles, batch 4096 per GPU).
 
 A "step" = one pass of the hot path over one batch of synthetic problems: DualMultWS (K2) + the batched
-interior-point solve (K1/K3/K4 fused in the persistent kernel) of ParkingSignedDist for B randomised start poses.
+interior-point solve (rounds of k_pk_eval [K1] / k_pk_sweep [K3] / k_pk_step [K4], then the persistent tail kernel) of
+ParkingSignedDist for B randomised start poses.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
 
@@ -12,7 +13,7 @@ nothing is exchanged on the solve path, one all-reduce carries the counters.  Ra
   value      converged trajectories / s, inputs resident in HBM, device time from CUDA events on the library's
              stream (max over ranks)
   e2e        same metric through the reference-facing C-ABI call with pinned HOST buffers (H2D + D2H inside)
-  roofline   dominant kernel (k_parking_solve) against the measured HBM peak, algorithmic bytes of SURVEY 8(d)
+  roofline   dominant kernel (k_pk_eval = K1 of the rounds) against the measured HBM peak, algorithmic bytes of SURVEY 8(d)
   cpu_baseline / --impl reference : the oracle port (IPOPT stand-in, oracle/ipm_ref.py sparse path) on host cores
 """
 from __future__ import annotations
@@ -40,19 +41,14 @@ ALG_BYTES_PER_EVAL = 8 * (2 * 2185 + 2 * 1460 + 243)
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the round kernels with all 4096 problems active, from the committed ncu capture
-    (profiles/ncu_traffic_r01.json, written by tools/ncu_traffic.py from `ncu --set full`).  Returns (block kernel first pass,
-    the four K1 launches of a round) or (None, None)."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    """DRAM bytes (read + write) of one k_pk_eval launch with all 4096 problems active, from the committed ncu capture
+    (profiles/ncu_traffic_r02.json, written by tools/ncu_traffic.py from `ncu --set full`), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
     if not os.path.exists(p):
-        return None, None
+        return None
     L = json.load(open(p))["launches"]
-    tot = lambda e: e["dram_read_bytes"] + e["dram_write_bytes"]
-    blk = [e for e in L if e["kernel"].startswith("k_pk_block")]
-    pa = [e for e in L if e["kernel"].startswith("k_pk_phaseA")]
-    if len(blk) < 2 or len(pa) < 2:
-        return None, None
-    return tot(blk[0]), tot(blk[0]) + tot(blk[1]) + tot(pa[0]) + tot(pa[1])
+    ev = [e for e in L if e["kernel"].startswith("k_pk_eval")]
+    return (ev[0]["dram_read_bytes"] + ev[0]["dram_write_bytes"]) if ev else None
 
 
 def peaks():
@@ -224,6 +220,7 @@ def gpu_arm(args):
     hflag = torch.zeros(B, dtype=torch.int32).pin_memory(); hit = torch.zeros(B, dtype=torch.int32).pin_memory()
     opts = obca_b200.default_opts(device=local, retry=1)
     sec = np.zeros(1)
+    t_ws = C.c_double(0.0); t_sv = C.c_double(0.0); ws_s = [0.0]; sv_s = [0.0]
     P = lambda t: C.c_void_p(t.data_ptr())
     NP = lambda a: a.ctypes.data_as(C.c_void_p)
 
@@ -234,7 +231,11 @@ def gpu_arm(args):
                                               C.byref(opts), P(dout["xp"]), P(dout["up"]), P(dout["ts"]), P(dout["lp"]), P(dout["np"]),
                                               P(dout["sl"]), P(dflag), P(dit), P(dout["err"]), NP(sec))
         assert rc == 0, lib.obca_last_error()
-        return float(sec[0])
+        # solve_seconds is the reference's `time` (solve only, ParkingSignedDist.jl:239-241); the step of the hot path also
+        # contains DualMultWS (:219): both event-timed on the library's stream
+        lib.obca_last_times(C.c_int(local), C.byref(t_ws), C.byref(t_sv))
+        ws_s[0] += t_ws.value; sv_s[0] += t_sv.value
+        return t_ws.value + t_sv.value
 
     def step_host():
         rc = lib.obca_parking_solve_batch(C.c_int(B), C.c_int(N), C.c_int(nOb), NP(vOb), NP(A), NP(b), P(hin["x0"]), P(hin["xF"]),
@@ -245,6 +246,7 @@ def gpu_arm(args):
         assert rc == 0, lib.obca_last_error()
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # > 126 MB L2
+    torch.cuda.synchronize()      # the library runs on its own stream: the torch-side copies / fills above must have landed
 
     def barrier():
         if dist is not None:
@@ -258,7 +260,7 @@ def gpu_arm(args):
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
-    dev_s = 0.0
+    dev_s = 0.0; ws_s[0] = 0.0; sv_s[0] = 0.0
     for _ in range(args.steps):
         flush.zero_(); torch.cuda.synchronize()
         dev_s += step_dev()
@@ -299,11 +301,13 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
                        "l2": "256 MB flush between timed steps", "tol": 1e-5, "max_iter": 200,
                        "converged_frac": conv_all / (B * world), "iters_mean": it_all / (B * world), "iters_max_rank0": it_max,
-                       "wall_ms_per_step": 1e3 * wall_s / args.steps},
+                       "wall_ms_per_step": 1e3 * wall_s / args.steps,
+                       "dualws_ms_per_step_rank0": 1e3 * ws_s[0] / args.steps,
+                       "solve_only_ms_per_step_rank0": 1e3 * sv_s[0] / args.steps},
             "clocks": sampler.result(),
             "e2e": {"value": e2e_val, "unit": "traj/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "whole solve: rounds of k_pk_phaseA/k_pk_sweep/k_pk_phaseC<2,true>, then k_pk_tail<2,true>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "whole solve: rounds of k_pk_eval/k_pk_sweep/k_pk_step<2,true>, then k_pk_tail<2,true>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": None,
                          "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x (iterations+1) per problem (SURVEY 8d, fused K1); "
                                  f"peak {how}; the solver is FP64-latency bound, see DESIGN.md and profiles/"}}
@@ -348,47 +352,35 @@ def gpu_arm(args):
     rnd = C.c_int(0); hand = C.c_int(0); kms = (C.c_double * 5)()
     if lib.obca_last_schedule(C.c_int(local), C.byref(rnd), C.byref(hand), None) == 0:
         line["config"]["schedule"] = {"phase_split_rounds": rnd.value, "handed_to_tail_kernel": hand.value}
-        line["gpu_launches"] = args.steps * (2 + 7 * rnd.value + (1 if hand.value > 0 else 0)) * 2    # device arm + e2e arm
-        # one extra, untimed solve with per-kernel events: which kernel dominates the step
+        # launches of our kernels per step: DualMultWS + 3 per round + the tail kernel; device arm + e2e arm
+        line["gpu_launches"] = args.steps * (1 + 3 * rnd.value + (1 if hand.value > 0 else 0)) * 2
+        # one extra, untimed solve with CUDA events around every kernel: which kernel dominates the step, and the live K1 roofline
         os.environ["OBCA_PHASE_TIMING"] = "1"
         step_dev()
         os.environ.pop("OBCA_PHASE_TIMING", None)
-        if lib.obca_last_schedule(C.c_int(local), None, None, kms) == 0:
-            names = ["k_pk_block (K1 constraint blocks, pass 1)", "k_pk_phaseA (K1 stage terms + assemble; + pass 2)", "k_pk_sweep (K3 KKT)",
-                     "k_pk_rblock + k_pk_phaseC (K4 recovery, line search, update)", "k_pk_tail (persistent, all phases)"]
+        pr = (C.c_ulonglong * 8)()
+        if lib.obca_last_schedule(C.c_int(local), C.byref(rnd), None, kms) == 0 and lib.obca_last_profile(C.c_int(local), pr) == 0:
+            names = ["k_pk_eval (K1: constraint blocks + stage terms + assembly + decisions)", "k_pk_sweep (K3 KKT)",
+                     "k_pk_step (K4 recovery, line search, update)", "k_pk_tail (persistent, all phases)", "k_dualws (K2)"]
             tot = sum(kms) or 1.0
             line["kernel_share"] = {n: round(kms[i] / tot, 4) for i, n in enumerate(names)}
-            line["kernel_ms_serialised"] = {n: round(kms[i], 3) for i, n in enumerate(names)}
-            pr = (C.c_ulonglong * 8)()
-            if lib.obca_last_profile(C.c_int(local), pr) == 0 and pr[7] > 0 and kms[0] > 0 and rnd.value > 0:
-                ev1, ev2 = int(pr[7]), int(pr[5])            # K1 evaluations in the first / second pass of the rounds (device counters)
-                # K1 of the rounds = k_pk_block (constraint blocks) + k_pk_phaseA (stage terms, assembly, reductions): the largest
-                # group of the step.  Algorithmic bytes: SURVEY 8d, fused variant, 60 264 B per problem per evaluation.
-                t_k1 = (kms[0] + kms[1]) * 1e-3
-                ach = (ev1 + ev2) * ALG_BYTES_PER_EVAL / t_k1 / 1e9
+            line["kernel_ms_event_timed"] = {n: round(kms[i], 3) for i, n in enumerate(names)}
+            ev_r, ev_r2, me_r, ev_t, me_t = int(pr[7]), int(pr[5]), int(pr[6]), int(pr[4]), int(pr[3])
+            line["phase_counts"] = {"k1_evals_rounds": ev_r, "of_which_after_barrier_update": ev_r2, "merit_evals_rounds": me_r,
+                                    "k1_evals_tail": ev_t, "merit_evals_tail": me_t}
+            if ev_r > 0 and kms[0] > 0 and rnd.value > 0:
+                # K1 = k_pk_eval: the largest kernel of the step.  Algorithmic bytes: SURVEY 8d, fused variant (J/H never reach HBM
+                # as matrices), 60 264 B per problem per evaluation, times the evaluations the kernel did (device counter).
+                t_k1 = kms[0] * 1e-3
+                ach = ev_r * ALG_BYTES_PER_EVAL / t_k1 / 1e9
                 line["roofline_solve"] = line["roofline"]
-                line["roofline"] = {"bound": "hbm", "kernel": "K1 of the rounds: k_pk_block<2,true> + k_pk_phaseA<2,true>", "achieved": ach,
-                                    "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic()[1],
-                                    "launches": 4 * rnd.value, "ms_per_round": 1e3 * t_k1 / rnd.value, "evaluations": ev1 + ev2,
-                                    "note": f"algorithmic bytes = {ALG_BYTES_PER_EVAL} B x {ev1 + ev2} K1 evaluations of one solve (device counters) / "
-                                            f"summed CUDA-event time of the block + assemble launches; peak {how}; traffic = dram read+write of the four "
-                                            "K1 launches of one round with all 4096 problems active (ncu --set full, profiles/ncu_traffic_r01.json): about 3x "
-                                            "the algorithmic bytes, because local factors, hand-over records and stage slots cross HBM between kernels"}
-                # the flat block kernel by itself: what it must move by construction, no re-reads
-                blk_bytes = 8.0 * (61 + 138) * NS
-                ach_b = ev1 * blk_bytes / (kms[0] * 1e-3) / 1e9
-                line["roofline_block"] = {"bound": "hbm", "kernel": "k_pk_block<2,true> (first pass)", "achieved": ach_b, "peak": hbm, "unit": "GB/s",
-                                          "frac": ach_b / hbm, "traffic": ncu_traffic()[0], "ms_per_launch": kms[0] / rnd.value,
-                                          "note": f"own algorithmic bytes: per problem and evaluation 8 x (61 read + 138 written doubles) x (N+1) = {int(blk_bytes)} B "
-                                                  f"(pose + block variables in; local affine map 24 + hand-over record 22 per block out) x {ev1} evaluations / "
-                                                  "event time of its launches; traffic = ncu dram read+write of a launch with all 4096 problems active "
-                                                  "(profiles/ncu_traffic_r01.json)"}
-    prof = (C.c_ulonglong * 8)()
-    if lib.obca_last_profile(C.c_int(local), prof) == 0 and sum(prof[i] for i in range(6)) > 0:
-        names = ["eval_K1", "kkt_K3", "recover", "merit", "update", "serial"]
-        tot = float(sum(prof[i] for i in range(6))) or 1.0
-        line["phase_share"] = {n: round(prof[i] / tot, 4) for i, n in enumerate(names)}
-        line["phase_counts"] = {"merit_evals": int(prof[6]), "k1_evals": int(prof[7])}
+                line["roofline"] = {"bound": "hbm", "kernel": "k_pk_eval<2,true> (K1 of the rounds)", "achieved": ach,
+                                    "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic(),
+                                    "launches": rnd.value, "ms_per_launch": 1e3 * t_k1 / rnd.value, "evaluations": ev_r,
+                                    "note": f"achieved = {ALG_BYTES_PER_EVAL} B (SURVEY 8d, fused K1) x {ev_r} K1 evaluations of one solve (device counter) / "
+                                            f"summed CUDA-event time of the {rnd.value} k_pk_eval launches on the library's stream; peak {how}; traffic = dram "
+                                            "read + write of ONE launch with all 4096 problems active (ncu --set full, profiles/ncu_traffic_r02.json): iterate "
+                                            "in, stage slots (53 KB) + local maps (47 KB) + iterate state out; the block hand-over stays in shared memory"}
     if world == 1 and not args.no_cpu:
         cores, (v, wall, c, it, per) = cpu_arm_best(host_cores())
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": "port",

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OBCA_VERSION 100
+#define OBCA_VERSION 200
 #define OBCA_ERR_ARG (-1)
 #define OBCA_ERR_NO_DEVICE (-2)
 #define OBCA_ERR_CUDA (-3)
@@ -53,8 +53,12 @@ typedef struct obca_opts {
   int quad_dual_ws;  /* quadcopter: 1 (default) closed-form dual warm start; 0 the reference's l = 0.05 start */
   /* execution */
   int device;        /* CUDA device ordinal used by this call */
-  int retry;         /* 1: re-solve once from the last iterate when the first attempt does not converge
-                        (ParkingSignedDist.jl:256-290), 0: single attempt */
+  int retry;         /* 1: the reference's status / retry logic: ParkingSignedDist.jl:256-290 (a failed first attempt is always
+                        followed by one more solve from the last iterate, then ParkingConstraints decides) and
+                        ParkingDist.jl:245-289 (after a failed first attempt ParkingConstraints decides whether the point is
+                        accepted or solved again); 0: single attempt, exitflag = converged */
+  int q4;            /* ParkingDist only: 1 reproduces the reference's inverted test after a SECOND failure
+                        (ParkingDist.jl:278-282: Feasible == 0 -> exitflag 1); 0 (default): exitflag = Feasible */
 } obca_opts;
 
 int obca_version(void);
@@ -70,7 +74,8 @@ void obca_default_opts(obca_opts* o);
  * outputs (per problem): xp 4x(N+1), up 2xN, ts (N+1) [ones if fixTime], lp Vx(N+1), np 4nOb x(N+1)
  *                        (ParkingSignedDist.jl:302-313), sl nOb x(N+1) (may be NULL),
  *                        exitflag (1 = converged, 0 = not), iters, kkt_err (Ipopt's scaled NLP error E_0),
- *                        solve_seconds[1] = device time of the solve (the reference's `time`, :297).        */
+ *                        solve_seconds[1] = device time of the solve alone -- the reference's `time` (:239-241, :297) is
+ *                        the wall time of solve(m), which excludes DualMultWS (:219); obca_last_times() gives both.  */
 int obca_parking_solve_batch(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
                              const double* x0, const double* xF, double Ts, double L, const double* ego,
                              const double* XYbounds, const double* rx, const double* ry, const double* ryaw,
@@ -125,21 +130,24 @@ int obca_check_quadcopter(int B, int N, const double* x, const double* u, const 
                           const double* xF, double Ts, const double* lambda, const double* ob, double R,
                           const obca_opts* opts, int* feasible, double* worst);
 
-/* Per-phase device cycle counters of the last obca_parking_solve_batch[_dev] on `device`, summed over the batch
- * (thread 0 of every CTA, clock64): out8 = {eval (K1), kkt (K3), recover, merit, update, serial sections,
- * #merit evaluations, #K1 evaluations}.  The cycle counters are filled by the monolithic kernel (OBCA_MODE=3) and by the
- * quadcopter kernel; the default phase-split schedule reports only the K1 evaluation counts: out8[7] = first pass of the
- * rounds (block + assemble kernels), out8[5] = second pass (after a barrier update), out8[6] = inside the tail kernel.  Diagnostic only. */
+/* Device times of the last obca_parking_solve_batch[_dev] on `device`: DualMultWS (0 when the caller passed lWS / nWS) and the
+ * solve alone (= what solve_seconds reports; the reference's `time`, ParkingSignedDist.jl:297). */
+int obca_last_times(int device, double* dualws_seconds, double* solve_seconds);
+
+/* Counters of the last solve on `device`, summed over the batch.  Parking (phase-split schedule): out8[7] = K1 evaluations in
+ * the round kernel k_pk_eval (of which out8[5] are re-evaluations after a barrier update), out8[6] = merit-function
+ * evaluations in k_pk_step, out8[4] / out8[3] = K1 / merit evaluations inside the tail kernel.  Quadcopter kernel: per-phase
+ * device cycle counters {eval, kkt, recover, merit, update, serial, #merit evaluations, #K1 evaluations} (thread 0 of every
+ * CTA, clock64).  Diagnostic only. */
 int obca_last_profile(int device, unsigned long long* out8);
 
-/* How the last obca_parking_solve_batch[_dev] on `device` was scheduled (last chunk of the batch): number of
- * phase-split rounds ([assemble, sweep, line-search] kernel triples over all active problems) and the number of
- * problems handed to the persistent tail kernel afterwards (= the batch size when no rounds were run).  Environment
- * overrides for experiments: OBCA_MODE (0 auto, 1 tail kernel only, 2 rounds always, 3 monolithic kernel),
- * OBCA_TAIL_THRESH (hand-over point), OBCA_CHUNK (problems per chunk).  kernel_ms5 (may be NULL): with
- * OBCA_PHASE_TIMING=1 in the environment the solve records CUDA events around every kernel (this serialises the
- * host loop, so the solve itself runs slower) and reports the summed times of {block kernel (pass 1), assemble kernel
- * (+ second pass), sweep kernel, line-search kernel, tail kernel} in milliseconds.  Diagnostic only. */
+/* How the last obca_parking_solve_batch[_dev] on `device` was scheduled (last chunk of the batch): number of phase-split
+ * rounds ([k_pk_eval, k_pk_sweep, k_pk_step] kernel triples over all active problems) and the number of problems handed to
+ * the persistent tail kernel afterwards (= the batch size when no rounds were run).  Environment overrides for experiments:
+ * OBCA_MODE (0 auto, 1 tail kernel only, 2 rounds only), OBCA_TAIL_THRESH (hand-over point), OBCA_CHUNK (problems per
+ * chunk).  kernel_ms5 (may be NULL): with OBCA_PHASE_TIMING=1 in the environment the solve records CUDA events around
+ * every kernel and reports the summed times of {k_pk_eval (K1 + decisions), k_pk_sweep (K3), k_pk_step (K4), tail kernel,
+ * DualMultWS} in milliseconds.  Diagnostic only. */
 int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel_ms5);
 
 /* K1 stand-alone: fused evaluation of the parking NLP in the REFERENCE's formulation at B given points (no solve);

@@ -18,7 +18,7 @@ mutable struct ObcaOpts
     dw_min::Cdouble; dw_first::Cdouble; dw_max::Cdouble; kw_minus::Cdouble; kw_plus::Cdouble; kw_plus_first::Cdouble
     gamma_theta::Cdouble; gamma_phi::Cdouble; delta::Cdouble; s_theta::Cdouble; s_phi::Cdouble; eta_phi::Cdouble
     gamma_alpha::Cdouble; max_backtrack::Cint; dc::Cdouble; max_kick::Cint; quad_dual_ws::Cint
-    device::Cint; retry::Cint
+    device::Cint; retry::Cint; q4::Cint
     ObcaOpts() = new()
 end
 

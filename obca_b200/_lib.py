@@ -13,6 +13,7 @@ SO_PATH = os.environ.get("OBCA_SO", os.path.join(HERE, "libobca.so"))   # OBCA_S
 SYMBOLS = ["obca_version", "obca_device_count", "obca_last_error", "obca_default_opts", "obca_parking_solve_batch",
            "obca_parking_solve_batch_dev", "obca_dualmultws_batch", "obca_check_parking",
            "obca_parking_eval_batch_dev", "obca_parking_eval_sizes", "obca_last_profile", "obca_last_schedule",
+           "obca_last_times",
            "obca_quadcopter_solve_batch", "obca_check_quadcopter"]
 
 
@@ -25,7 +26,7 @@ class ObcaOpts(C.Structure):
                 ("kw_plus", C.c_double), ("kw_plus_first", C.c_double),
                 ("gamma_theta", C.c_double), ("gamma_phi", C.c_double), ("delta", C.c_double), ("s_theta", C.c_double),
                 ("s_phi", C.c_double), ("eta_phi", C.c_double), ("gamma_alpha", C.c_double),
-                ("max_backtrack", C.c_int), ("dc", C.c_double), ("max_kick", C.c_int), ("quad_dual_ws", C.c_int), ("device", C.c_int), ("retry", C.c_int)]
+                ("max_backtrack", C.c_int), ("dc", C.c_double), ("max_kick", C.c_int), ("quad_dual_ws", C.c_int), ("device", C.c_int), ("retry", C.c_int), ("q4", C.c_int)]
 
 
 class ObcaError(RuntimeError):

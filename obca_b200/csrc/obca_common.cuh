@@ -79,14 +79,10 @@ OBCA_HD IpmOpts default_opts() {
 }
 
 // Reciprocal used on the Newton-step path: computed once per gap / pivot and reused for every quotient with that
-// denominator.  (A single-precision-seeded Newton reciprocal was measured on B200 and was SLOWER than the IEEE
-// division here: the solver kernel is instruction-fetch / issue bound and the inline range checks cost more than
-// nvcc's own division fast path.)
-#if defined(__CUDA_ARCH__) && defined(OBCA_RCP_CALL)
-// one out-of-line copy of the IEEE division: the solver kernels are instruction-fetch bound (their straight-line code
-// is several hundred KB), and every inlined division is ~25 instructions plus a slow path
-__device__ __noinline__ double rcp_call(double x) { return 1.0 / x; }
-OBCA_HD double rcp(double x) { return rcp_call(x); }
+// denominator.  Device: rcp.rn.f64 (correctly rounded, so bit-identical to the host's 1.0 / x) -- about half the
+// instructions of the IEEE division subroutine, and it sits on the latency-bound chain of the KKT sweep.
+#if defined(__CUDA_ARCH__)
+OBCA_HD double rcp(double x) { return __drcp_rn(x); }
 #else
 OBCA_HD double rcp(double x) { return 1.0 / x; }
 #endif

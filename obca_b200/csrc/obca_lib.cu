@@ -1,10 +1,8 @@
 // obca_lib.cu -- sm_100a kernels + the C-ABI of include/obca.h.
 //
 // Kernels
-//   obca_phased.cuh          the parking solver: phase-split rounds (k_pk_block, k_pk_phaseA, k_pk_sweep, k_pk_rblock,
-//                            k_pk_phaseC) over all active problems + the persistent tail kernel k_pk_tail
-//   k_parking_solve<VM,SDV>  the monolithic persistent kernel of session 1 (OBCA_MODE=3, cross-check of the above): one CTA
-//                            per resident slot pulls problems from an atomic queue and runs the whole interior-point solve
+//   obca_phased.cuh          the parking solver: phase-split rounds (k_pk_eval, k_pk_sweep, k_pk_step) over all active
+//                            problems + the persistent tail kernel k_pk_tail
 //   k_quad_solve<SDV>        quadcopter model (config 4): persistent CTA per problem, block-cooperative 17x21 KKT sweep
 //   k_dualws<VM>             K2: one thread per (problem, stage, obstacle) micro interior-point solve.
 //   k_check                  K5: ParkingConstraints twin + strict audit, one CTA per problem.
@@ -29,95 +27,6 @@ using namespace obca;
 // ---------------------------------------------------------------------------------------------------------
 // device-side batch description
 // ---------------------------------------------------------------------------------------------------------
-#ifndef OBCA_MIN_BLOCKS
-#define OBCA_MIN_BLOCKS 3
-#endif
-template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, OBCA_MIN_BLOCKS)
-k_parking_solve(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L,
-                const BatchPtrs bp, double* __restrict__ Wall, int* __restrict__ counter) {
-  extern __shared__ double s_ric[];     // (N+1) x RSTRIDE stage slots of the KKT solve
-  __shared__ ProbState S;
-  __shared__ double s_tile[144];         // exchange tile of the warp-cooperative KKT sweep (obca_solver.cuh)
-  __shared__ double s_red[4 * 12];      // block_reduce scratch (4 warps x sizeof(EvalPart))
-  __shared__ int s_b;
-  __shared__ ChkPart s_chk[4];
-  __shared__ int s_feas;
-  const int N = P.N, NS = N + 1, V = P.V, nOb = P.nOb;
-  double* W = Wall + (size_t)blockIdx.x * L.total * L.NSP;
-  for (;;) {
-    if (threadIdx.x == 0) s_b = atomicAdd(counter, 1);
-    __syncthreads();
-    const int b = s_b;
-    if (b >= bp.B) break;
-    PkCtx C;
-    C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.bo = nullptr; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
-    C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
-    C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
-    C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
-    C.in.uWS = bp.uWS + (size_t)2 * N * b; C.in.ldu = N;
-    C.in.lWS = bp.lWS + (size_t)V * NS * b; C.in.nWS = bp.nWS + (size_t)4 * nOb * NS * b;
-    PkOutputs out;
-    out.xp = bp.xp + (size_t)4 * NS * b; out.up = bp.up + (size_t)2 * N * b; out.ts = bp.ts + (size_t)NS * b;
-    out.lp = bp.lp + (size_t)V * NS * b; out.np = bp.np + (size_t)4 * nOb * NS * b;
-    out.sl = bp.sl ? bp.sl + (size_t)nOb * NS * b : nullptr;
-    out.duals = bp.duals ? bp.duals + ((size_t)4 * N + (size_t)4 * nOb * NS) * b : nullptr;
-
-    // first attempt from the warm start; on failure one more solve from the last iterate
-    // (ParkingSignedDist.jl:256-263 / ParkingDist.jl:245-263).  One call site: the solver body exists once.
-    int iters = 0, status = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      IpmDriver<ParkSolver<VM, SDV> >::solve(C, attempt);
-      __syncthreads();
-      iters += S.iters;
-      status = S.status;
-      if (status == 1 || !bp.retry) break;
-      __syncthreads();
-    }
-    for (int k = threadIdx.x; k < NS; k += blockDim.x) ParkSolver<VM, SDV>::store_stage(C, k, out);
-    __syncthreads();
-    int exitflag = status == 1 ? 1 : 0;
-    if (status != 1 && bp.retry) {
-      // second failure: the reference lets ParkingConstraints decide (ParkingSignedDist.jl:276-283)
-      ChkPart c;
-      chk_init(c);
-      for (int k = threadIdx.x; k < NS; k += blockDim.x) {
-        ChkPart ck;
-        check_stage(P, k, C.in.x0, C.in.xF, out.xp, out.up, out.lp, out.np, out.ts, out.sl, SDV ? 1 : 0, 0, ck);
-        chk_merge(c, ck);
-      }
-      // block reduction through shared memory (4 warps max)
-      for (int off = 16; off > 0; off >>= 1) {
-        ChkPart o;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) o.c0[i] = __shfl_down_sync(0xffffffffu, c.c0[i], off);
-        o.c1 = __shfl_down_sync(0xffffffffu, c.c1, off); o.c2 = __shfl_down_sync(0xffffffffu, c.c2, off);
-        o.c3 = __shfl_down_sync(0xffffffffu, c.c3, off); o.c4 = __shfl_down_sync(0xffffffffu, c.c4, off);
-        o.c5 = __shfl_down_sync(0xffffffffu, c.c5, off); o.c6 = __shfl_down_sync(0xffffffffu, c.c6, off);
-        o.sbox = __shfl_down_sync(0xffffffffu, c.sbox, off);
-        chk_merge(c, o);
-      }
-      if ((threadIdx.x & 31) == 0) s_chk[threadIdx.x >> 5] = c;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) chk_merge(c, s_chk[w]);
-        int e[7];
-        s_feas = check_finish(P, c, out.ts, 0, 5e-5, e);
-      }
-      __syncthreads();
-      exitflag = s_feas ? 1 : 0;
-    }
-    if (threadIdx.x == 0) {
-      bp.exitflag[b] = exitflag;
-      bp.iters[b] = iters;
-      bp.kkt_err[b] = S.e0;
-      if (bp.prof)
-        for (int i = 0; i < 8; ++i) atomicAdd(bp.prof + i, (unsigned long long)S.prof[i]);
-    }
-    __syncthreads();
-  }
-}
-
 template <int VM>
 __global__ void k_dualws(const __grid_constant__ ParkProblem P, int B, const double* __restrict__ rx,
                          const double* __restrict__ ry, const double* __restrict__ ryaw, double tol, int max_iter,
@@ -323,26 +232,29 @@ static void set_err(const std::string& s) { g_err = s; }
 struct DevCtx {
   bool init = false;
   cudaStream_t st = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, evm = nullptr, ev1 = nullptr;
   int sms = 0;
   double* W = nullptr; size_t Wbytes = 0;
   int* counter = nullptr;
   unsigned long long* prof = nullptr;
   unsigned long long prof_host[8] = {0};
   char* stage = nullptr; size_t stage_bytes = 0;   // device staging for the host-pointer API
+  double* wsd = nullptr; size_t wsd_bytes = 0;     // warm-start duals of DualMultWS when the caller passes lWS = nWS = NULL
   // phase-split driver (obca_phased.cuh)
-  double* slots = nullptr; size_t slots_bytes = 0;  // stage slots of every problem, B x (N+1) x GSTRIDE
+  double* slots = nullptr; size_t slots_bytes = 0;  // stage slots of every problem, B x (N+1) x RSTRIDE
   char* pstate = nullptr; size_t pstate_bytes = 0;  // ProbState per problem
   int* act = nullptr; size_t act_bytes = 0;         // two active lists
-  double* bo = nullptr; size_t bo_bytes = 0;        // block hand-over records, B x nOb x BO_N x NSP
-  int* ncnt = nullptr;                              // device: n[0], n[1] (active counts), [2] tail work counter
+  int* ncnt = nullptr;                              // device: three rotating active counts, [3] tail work counter
   int* h_n = nullptr;                               // pinned ring of active counts read back per round
   cudaEvent_t evr[16] = {nullptr};
+  std::vector<cudaEvent_t> tev;                     // OBCA_PHASE_TIMING=1: pool of timing events
   int last_rounds = 0, last_tail = 0;
-  double phase_ms[5] = {0, 0, 0, 0, 0};                // OBCA_PHASE_TIMING=1: summed event times of K_A, K_B, K_C, tail
-  std::mutex mu;
+  double phase_ms[5] = {0, 0, 0, 0, 0};             // OBCA_PHASE_TIMING=1: summed event times of eval, sweep, step, tail; [4] DualMultWS
+  double last_dualws_s = 0.0, last_solve_s = 0.0;
+  std::recursive_mutex mu;
 };
 static DevCtx g_dev[64];
+static std::mutex g_init_mu;
 
 static int get_ctx(int dev, DevCtx** out) {
   int n = 0;
@@ -350,9 +262,10 @@ static int get_ctx(int dev, DevCtx** out) {
   if (dev < 0 || dev >= n || dev >= 64) { set_err("bad device ordinal"); return OBCA_ERR_ARG; }
   DevCtx& c = g_dev[dev];
   CK(cudaSetDevice(dev));
+  std::lock_guard<std::mutex> lk(g_init_mu);
   if (!c.init) {
     CK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1));
+    CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.evm)); CK(cudaEventCreate(&c.ev1));
     cudaDeviceProp pr;
     CK(cudaGetDeviceProperties(&pr, dev));
     c.sms = pr.multiProcessorCount;
@@ -406,26 +319,6 @@ static int run_dualws(DevCtx& c, const ParkProblem& P, int B, const double* rx, 
                          : launch_dualws<4>(c, P, B, rx, ry, ryaw, lp, np, dd);
 }
 
-template <int VM, bool SDV>
-static int launch_solve(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const BatchPtrs& bp) {
-  PkLay L = make_layout(P, LocalDims<VM, SDV>::NFAC);
-  if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
-  const size_t smem = (size_t)(P.N + 1) * RSTRIDE * sizeof(double);
-  CK(cudaFuncSetAttribute(k_parking_solve<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parking_solve<VM, SDV>, L.NSP, smem));
-  if (occ < 1) occ = 1;
-  int grid = c.sms * occ;
-  if (grid > bp.B) grid = bp.B;
-  const size_t need = (size_t)grid * L.total * L.NSP * sizeof(double);
-  int rc = ensure((void**)&c.W, &c.Wbytes, need);
-  if (rc) return rc;
-  CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
-  k_parking_solve<VM, SDV><<<grid, L.NSP, smem, c.st>>>(P, O, L, bp, c.W, c.counter);
-  CK(cudaGetLastError());
-  return 0;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // phase-split driver (obca_phased.cuh): rounds of [K_A, K_B, K_C] over the active problems, then the tail kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -437,76 +330,75 @@ static int env_int(const char* name, int dflt) {
 template <int VM, bool SDV>
 static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, const BatchPtrs& bp, int mode) {
   PkLay L = make_layout(P, LocalDims<VM, SDV>::NFAC);
-  if (L.NSP > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
   const int B = bp.B, NS = P.N + 1;
-  const size_t smem = (size_t)NS * RSTRIDE * sizeof(double);
-  CK(cudaFuncSetAttribute(k_pk_phaseA<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_pk_tail<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pk_tail<VM, SDV>, L.NSP, smem));
-  if (occ < 1) occ = 1;
-  const int tail_cap = c.sms * occ;
+  if (NS > 128) { set_err("horizon too long for this build (N+1 <= 128)"); return OBCA_ERR_UNSUPPORTED; }
+  const size_t smem_slots = (size_t)NS * RSTRIDE * sizeof(double);
+  const size_t smem_step = (size_t)(L.dRS + 1 - L.dLAM) * L.NSP * sizeof(double);
+  CK(cudaFuncSetAttribute(k_pk_eval<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slots));
+  CK(cudaFuncSetAttribute(k_pk_tail<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slots));
+  CK(cudaFuncSetAttribute(k_pk_step<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_step));
+  const size_t smem_sweep = (size_t)SWEEP_WARPS * SWEEP_WARP_DOUBLES * sizeof(double);
+  CK(cudaFuncSetAttribute(k_pk_sweep<VM, SDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sweep));
+  int occ_t = 0, occ_e = 0, occ_s = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_pk_tail<VM, SDV>, PK_THREADS, smem_slots));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_pk_eval<VM, SDV>, PK_THREADS, smem_slots));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_pk_step<VM, SDV>, PK_THREADS, smem_step));
+  if (occ_t < 1) occ_t = 1;
+  if (occ_e < 1) occ_e = 1;
+  if (occ_s < 1) occ_s = 1;
+  const int tail_cap = c.sms * occ_t, eval_cap = c.sms * occ_e, step_cap = c.sms * occ_s;
   int rc = ensure((void**)&c.W, &c.Wbytes, (size_t)B * L.total * L.NSP * sizeof(double));
   if (rc) return rc;
   rc = ensure((void**)&c.pstate, &c.pstate_bytes, (size_t)B * sizeof(ProbState));
   if (rc) return rc;
   ProbState* Sg = (ProbState*)c.pstate;
   cudaStream_t st = c.st;
-  // mode 1: tail kernel only; mode 2: rounds until the active set fits one wave of the tail kernel; auto: by batch size
-  // hand-over point: measured on B200 (config 2, B = 4096) the solve time is flat for thresholds between B/4 and 3B/4
-  // and ~8 % higher for rounds-only or tail-only, so: half the batch, but never less than one wave of the tail kernel
-  const int thresh = env_int("OBCA_TAIL_THRESH", B / 2 > tail_cap ? B / 2 : tail_cap);
+  // mode 1: tail kernel only; mode 2: rounds only (until the active set is empty, or OBCA_TAIL_THRESH if set); auto: rounds for
+  // large batches until the active set has shrunk to the hand-over point, then the tail kernel.  Hand-over point: measured on
+  // B200 (config 2, B = 4096, this build) the solve time is flat (113-116 ms) between 1200 and 2500 remaining problems and
+  // 4-15 % higher outside (rounds only 133 ms, tail kernel only 133 ms): lock-step rounds do 1.65x the evaluations per second
+  // while all SMs are busy, the persistent kernel finishes the stragglers without a launch-bound round per iteration.
+  const int thresh = env_int("OBCA_TAIL_THRESH", mode == 2 ? 0 : (B / 2 > tail_cap ? B / 2 : tail_cap));
   const bool rounds = mode == 2 || (mode == 0 && B > 2 * tail_cap);
   c.last_rounds = 0; c.last_tail = B;
   int h_init[4] = {B, 0, 0, 0};
   CK(cudaMemcpyAsync(c.ncnt, h_init, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
   if (!rounds) {
     const int grid = B < tail_cap ? B : tail_cap;
-    k_pk_tail<VM, SDV><<<grid, L.NSP, smem, st>>>(P, O, L, bp, c.W, Sg, nullptr, c.ncnt, c.ncnt + 2, 1);
+    k_pk_tail<VM, SDV><<<grid, PK_THREADS, smem_slots, st>>>(P, O, L, bp, c.W, Sg, nullptr, c.ncnt, c.ncnt + 3, 1);
     CK(cudaGetLastError());
     return 0;
   }
-  rc = ensure((void**)&c.slots, &c.slots_bytes, (size_t)B * NS * GSTRIDE * sizeof(double));
+  rc = ensure((void**)&c.slots, &c.slots_bytes, (size_t)B * NS * RSTRIDE * sizeof(double));
   if (rc) return rc;
   rc = ensure((void**)&c.act, &c.act_bytes, 2 * (size_t)B * sizeof(int));
   if (rc) return rc;
   int* act[2] = {c.act, c.act + B};
-  rc = ensure((void**)&c.bo, &c.bo_bytes, (size_t)B * P.nOb * BO_N * L.NSP * sizeof(double));
-  if (rc) return rc;
-  int cur = 0, n_bound = B, done_r = 0, r = 0;
+  int n_bound = B, done_r = 0, r = 0;
   const int max_rounds = 8 * (O.max_iter + 8);
-  const bool timing = env_int("OBCA_PHASE_TIMING", 0) != 0;      // development: per-kernel event times, summed per solve
-  std::vector<cudaEvent_t> tev;
-  auto mark = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
-  const int per = P.nOb * NS;
-  auto blk_grid = [&](int n) { return (int)(((long long)n * per + 127) / 128); };
-  // initial points: the assemble kernel in "fresh" mode only runs the initialisation and leaves every problem in PH_EVAL
-  CK(cudaMemsetAsync(c.ncnt + 1, 0, sizeof(int), st));
-  k_pk_phaseA<VM, SDV><<<B, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, nullptr, c.ncnt, act[1], c.ncnt + 1, 1, 1);
-  CK(cudaGetLastError());
-  cur = 1;
+  const bool timing = env_int("OBCA_PHASE_TIMING", 0) != 0;      // development / bench: per-kernel event times, summed per solve
+  size_t n_ev = 0;
+  auto mark = [&]() {
+    if (!timing) return;
+    if (n_ev == c.tev.size()) { cudaEvent_t e; cudaEventCreate(&e); c.tev.push_back(e); }
+    cudaEventRecord(c.tev[n_ev++], st);
+  };
+  auto cap = [](int n, int m) { return n < m ? (n > 0 ? n : 1) : m; };
   for (; r < max_rounds; ++r) {
-    CK(cudaMemsetAsync(c.ncnt + (1 - cur), 0, sizeof(int), st));
+    const int* a_in = act[r & 1]; int* a_out = act[(r + 1) & 1];
+    int* n_in = c.ncnt + (r % 3); int* n_out = c.ncnt + ((r + 1) % 3); int* n_zero = c.ncnt + ((r + 2) % 3);
     mark();
-    k_pk_block<VM, SDV><<<blk_grid(n_bound), 128, 0, st>>>(P, L, c.W, c.bo, Sg, act[cur], c.ncnt + cur, 1);
+    k_pk_eval<VM, SDV><<<cap(n_bound, eval_cap), PK_THREADS, smem_slots, st>>>(P, O, L, bp, c.W, c.slots, Sg, a_in, n_in, a_out, n_out,
+                                                                            r == 0 ? 1 : 0);
     mark();
-    k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[cur], c.ncnt + cur, act[1 - cur],
-                                                      c.ncnt + (1 - cur), 0, 1);
-    // second pass for the problems whose barrier parameter was reduced by the first one
-    k_pk_block<VM, SDV><<<blk_grid(n_bound), 128, 0, st>>>(P, L, c.W, c.bo, Sg, act[1 - cur], c.ncnt + (1 - cur), 2);
-    k_pk_phaseA<VM, SDV><<<n_bound, L.NSP, smem, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[1 - cur], c.ncnt + (1 - cur), nullptr,
-                                                      nullptr, 0, 2);
+    k_pk_sweep<VM, SDV><<<(n_bound + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, smem_sweep, st>>>(P, O, L, c.W, c.slots, Sg, a_out,
+                                                                                              n_out, n_zero);
     mark();
-    k_pk_sweep<VM, SDV><<<(n_bound + 2 * SWEEP_WARPS - 1) / (2 * SWEEP_WARPS), 32 * SWEEP_WARPS, 0, st>>>(P, O, L, c.W, c.slots, Sg, act[1 - cur],
-                                                                                              c.ncnt + (1 - cur));
-    mark();
-    k_pk_rblock<VM, SDV><<<blk_grid(n_bound), 128, 0, st>>>(P, L, c.W, c.bo, Sg, act[1 - cur], c.ncnt + (1 - cur));
-    k_pk_phaseC<VM, SDV><<<n_bound, L.NSP, 0, st>>>(P, O, L, bp, c.W, c.slots, Sg, c.bo, act[1 - cur], c.ncnt + (1 - cur));
+    k_pk_step<VM, SDV><<<cap(n_bound, step_cap), PK_THREADS, smem_step, st>>>(P, O, L, bp, c.W, c.slots, Sg, a_out, n_out);
     mark();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c.h_n + (r & 15), c.ncnt + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c.h_n + (r & 15), n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c.evr[r & 15], st));
-    cur = 1 - cur;
     // the active set only shrinks: the count of any completed round bounds every later round
     if (r - done_r >= 8) CK(cudaEventSynchronize(c.evr[done_r & 15]));
     while (done_r <= r && cudaEventQuery(c.evr[done_r & 15]) == cudaSuccess) { n_bound = c.h_n[done_r & 15]; ++done_r; }
@@ -520,22 +412,21 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
   c.last_rounds = r; c.last_tail = n_bound;
   if (timing) {
     CK(cudaStreamSynchronize(st));
-    double t[4] = {0, 0, 0, 0};      // five marks per round: | block | assemble (+ second pass) | sweep | line search |
-    for (size_t i = 0; i + 4 < tev.size(); i += 5)
-      for (int j = 0; j < 4; ++j) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[i + j], tev[i + j + 1]); t[j] += ms; }
-    for (cudaEvent_t e : tev) cudaEventDestroy(e);
-    for (int j = 0; j < 4; ++j) c.phase_ms[j] = t[j];
-    c.phase_ms[4] = 0.0;
+    double t[3] = {0, 0, 0};      // four marks per round: | eval | sweep | step |
+    for (size_t i = 0; i + 3 < n_ev; i += 4)
+      for (int j = 0; j < 3; ++j) { float ms = 0.f; cudaEventElapsedTime(&ms, c.tev[i + j], c.tev[i + j + 1]); t[j] += ms; }
+    for (int j = 0; j < 3; ++j) c.phase_ms[j] += t[j];
   }
   if (n_bound > 0) {
+    // after r rounds the active list is act[r & 1] with count ncnt[r % 3]
     const int grid = n_bound < tail_cap ? n_bound : tail_cap;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-    k_pk_tail<VM, SDV><<<grid, L.NSP, smem, st>>>(P, O, L, bp, c.W, Sg, act[cur], c.ncnt + cur, c.ncnt + 2, 0);
+    k_pk_tail<VM, SDV><<<grid, PK_THREADS, smem_slots, st>>>(P, O, L, bp, c.W, Sg, act[r & 1], c.ncnt + (r % 3), c.ncnt + 3, 0);
     CK(cudaGetLastError());
     if (timing) {
       cudaEventRecord(e1, st); cudaEventSynchronize(e1);
-      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); c.phase_ms[4] = ms;
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); c.phase_ms[3] += ms;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
   }
@@ -552,6 +443,7 @@ static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, Bat
   }
   CK(cudaMemsetAsync(c.prof, 0, 8 * sizeof(unsigned long long), c.st));
   bp.prof = c.prof;
+  for (int i = 0; i < 4; ++i) c.phase_ms[i] = 0.0;
   int rc;
   const int mode = env_int("OBCA_MODE", 0);
   // large batches are solved in chunks so that the per-problem workspace (~0.25 MB) stays within a few GB
@@ -570,25 +462,24 @@ static int solve_dev_impl(DevCtx& c, const ParkProblem& P, const IpmOpts& O, Bat
     q.exitflag += o; q.iters += o; q.kkt_err += o;
 #ifdef OBCA_FAST_BUILD   // development builds: only the config-2 instantiation
     if (!(P.signed_dist && vm == 2)) { set_err("fast build: only <2,true>"); return OBCA_ERR_UNSUPPORTED; }
-    rc = mode == 3 ? launch_solve<2, true>(c, P, O, q) : launch_phased<2, true>(c, P, O, q, mode);
+    rc = launch_phased<2, true>(c, P, O, q, mode);
 #else
-    // OBCA_MODE: 0 auto (phase-split rounds for large batches, persistent tail kernel for small ones), 1 tail kernel only,
-    // 2 rounds always, 3 the monolithic persistent kernel k_parking_solve (kept as the cross-check of the phase split)
-    if (mode == 3) {
-      if (P.signed_dist) rc = vm == 2 ? launch_solve<2, true>(c, P, O, q) : launch_solve<4, true>(c, P, O, q);
-      else rc = vm == 2 ? launch_solve<2, false>(c, P, O, q) : launch_solve<4, false>(c, P, O, q);
-    } else {
-      if (P.signed_dist) rc = vm == 2 ? launch_phased<2, true>(c, P, O, q, mode) : launch_phased<4, true>(c, P, O, q, mode);
-      else rc = vm == 2 ? launch_phased<2, false>(c, P, O, q, mode) : launch_phased<4, false>(c, P, O, q, mode);
-    }
+    // OBCA_MODE: 0 auto (phase-split rounds for large batches + tail kernel for the stragglers, tail kernel alone for small
+    // batches), 1 tail kernel only, 2 rounds only
+    if (P.signed_dist) rc = vm == 2 ? launch_phased<2, true>(c, P, O, q, mode) : launch_phased<4, true>(c, P, O, q, mode);
+    else rc = vm == 2 ? launch_phased<2, false>(c, P, O, q, mode) : launch_phased<4, false>(c, P, O, q, mode);
 #endif
   }
   if (rc) return rc;
   CK(cudaEventRecord(c.ev1, c.st));
   CK(cudaMemcpyAsync(c.prof_host, c.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st));
   CK(cudaStreamSynchronize(c.st));
-  float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  // the reference's `time` is the wall time of solve(m) alone (ParkingSignedDist.jl:239-241,297): DualMultWS (:219) and
+  // the model build are outside it.  ev0 .. evm = DualMultWS (when the library runs it), evm .. ev1 = the solve.
+  float ms = 0.f, ms_ws = 0.f;
+  CK(cudaEventElapsedTime(&ms, c.evm, c.ev1));
+  CK(cudaEventElapsedTime(&ms_ws, c.ev0, c.evm));
+  c.last_solve_s = ms * 1e-3; c.last_dualws_s = ms_ws * 1e-3; c.phase_ms[4] = ms_ws;
   if (seconds) *seconds = ms * 1e-3;
   return 0;
 }
@@ -645,7 +536,7 @@ void obca_default_opts(obca_opts* o) {
   o->gamma_theta = d.gamma_theta; o->gamma_phi = d.gamma_phi; o->delta = d.delta; o->s_theta = d.s_theta;
   o->s_phi = d.s_phi; o->eta_phi = d.eta_phi; o->gamma_alpha = d.gamma_alpha; o->max_backtrack = d.max_backtrack;
   o->dc = d.dc; o->max_kick = d.max_kick; o->quad_dual_ws = d.quad_dual_ws;
-  o->device = 0; o->retry = 1;
+  o->device = 0; o->retry = 1; o->q4 = 0;
 }
 
 int obca_parking_solve_batch_dev(int B, int N, int nOb, const int* vOb, const double* A, const double* b,
@@ -664,23 +555,26 @@ int obca_parking_solve_batch_dev(int B, int N, int nOb, const int* vOb, const do
   DevCtx* c;
   int rc = get_ctx(opts ? opts->device : 0, &c);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
   IpmOpts O = to_ipm(opts);
   BatchPtrs bp;
   bp.x0 = x0; bp.xF = xF; bp.rx = rx; bp.ry = ry; bp.ryaw = ryaw; bp.xWS = xWS; bp.uWS = uWS;
   bp.xp = xp; bp.up = up; bp.ts = ts; bp.lp = lp; bp.np = np; bp.sl = sl; bp.duals = nullptr;
   bp.exitflag = exitflag; bp.iters = iters; bp.kkt_err = kkt_err; bp.B = B; bp.retry = opts ? opts->retry : 1;
-  CK(cudaEventRecord(c->ev0, c->st));      // the timed region covers DualMultWS (K2) + the solve
+  bp.q4 = opts ? opts->q4 : 0;
+  CK(cudaEventRecord(c->ev0, c->st));
   if (lWS && nWS) { bp.lWS = lWS; bp.nWS = nWS; }
   else {
-    // the reference runs DualMultWS inside the NLP driver (ParkingSignedDist.jl:219): use the output arrays
-    // lp / np as scratch for the warm-start duals (they have exactly the transposed size)
-    rc = run_dualws(*c, P, B, rx, ry, ryaw, lp, np, nullptr);
+    // the reference runs DualMultWS inside the NLP driver (ParkingSignedDist.jl:219); its result goes to a scratch of
+    // the library (never to the caller's output arrays, which stay untouched until a problem has finished)
+    const size_t NS = (size_t)N + 1, nl = (size_t)P.V * NS * B, nn = 4 * (size_t)nOb * NS * B;
+    rc = ensure((void**)&c->wsd, &c->wsd_bytes, (nl + nn) * sizeof(double));
     if (rc) return rc;
-    // lp/np now hold (N+1)xV column-major == what the solver expects for lWS/nWS; the solver overwrites them
-    // at store time only after the solve of that problem has finished reading its own slice.
-    bp.lWS = lp; bp.nWS = np;
+    rc = run_dualws(*c, P, B, rx, ry, ryaw, c->wsd, c->wsd + nl, nullptr);
+    if (rc) return rc;
+    bp.lWS = c->wsd; bp.nWS = c->wsd + nl;
   }
+  CK(cudaEventRecord(c->evm, c->st));      // `time` = the solve alone, as in the reference (:239-241); see obca_last_times
   return solve_dev_impl(*c, P, O, bp, solve_seconds);
 }
 
@@ -711,11 +605,10 @@ int obca_parking_solve_batch(int B, int N, int nOb, const int* vOb, const double
   const size_t o_err = take(1);
   const size_t dbytes = off * sizeof(double);
   const size_t ibytes = 2 * (size_t)B * sizeof(int);
-  {
-    std::lock_guard<std::mutex> lk(c->mu);
-    rc = ensure((void**)&c->stage, &c->stage_bytes, dbytes + ibytes);
-    if (rc) return rc;
-  }
+  // one staging buffer per device: the whole call (copies in, solve, copies out) runs under the device lock
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  rc = ensure((void**)&c->stage, &c->stage_bytes, dbytes + ibytes);
+  if (rc) return rc;
   double* d = (double*)c->stage;
   int* di = (int*)(c->stage + dbytes);
   cudaStream_t st = c->st;
@@ -752,7 +645,7 @@ int obca_dualmultws_batch(int B, int N, int nOb, const int* vOb, const double* A
   DevCtx* c;
   int rc = get_ctx(opts ? opts->device : 0, &c);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
   const size_t NS = N + 1, nr = NS * B, nl = (size_t)P.V * NS * B, nn = 4 * (size_t)nOb * NS * B, ndd = (size_t)nOb * NS * B;
   rc = ensure((void**)&c->stage, &c->stage_bytes, (3 * nr + nl + nn + ndd) * sizeof(double));
   if (rc) return rc;
@@ -783,7 +676,7 @@ int obca_check_parking(int B, int N, int nOb, const int* vOb, const double* A, c
   DevCtx* c;
   int rc = get_ctx(opts ? opts->device : 0, &c);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
   const size_t NS = N + 1;
   const size_t nx = 4 * NS * B, nu = 2 * (size_t)N * B, nl = (size_t)P.V * NS * B, nn = 4 * (size_t)nOb * NS * B, nt = NS * B,
                ns = (size_t)nOb * NS * B, n0 = 4 * (size_t)B;
@@ -821,7 +714,7 @@ int obca_quadcopter_solve_batch(int B, int N, const double* x0, const double* xF
   DevCtx* c;
   int rc = get_ctx(opts ? opts->device : 0, &c);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
   IpmOpts O = to_ipm(opts);
   if (!opts) O.max_iter = 3000;                        // the reference sets no max_iter here (Ipopt default)
   const size_t NS = N + 1;
@@ -868,7 +761,7 @@ int obca_check_quadcopter(int B, int N, const double* x, const double* u, const 
   DevCtx* c;
   int rc = get_ctx(opts ? opts->device : 0, &c);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
   const size_t NS = N + 1;
   const size_t n0 = 12 * (size_t)B, nx = 12 * NS * B, nu = 4 * (size_t)N * B, nt = NS * B, nl = 30 * NS * B;
   const size_t dbytes = (2 * n0 + nx + nu + nt + nl + B) * sizeof(double);
@@ -904,6 +797,13 @@ int obca_last_schedule(int device, int* rounds, int* handed_over, double* kernel
   return 0;
 }
 
+int obca_last_times(int device, double* dualws_seconds, double* solve_seconds) {
+  if (device < 0 || device >= 64 || !g_dev[device].init) { set_err("no solve yet"); return OBCA_ERR_ARG; }
+  if (dualws_seconds) *dualws_seconds = g_dev[device].last_dualws_s;
+  if (solve_seconds) *solve_seconds = g_dev[device].last_solve_s;
+  return 0;
+}
+
 int obca_parking_eval_sizes(int N, int nOb, const int* vOb, int signed_dist, long long* n_out, long long* m_out) {
   ParkProblem P;
   double A[2 * OBCA_MAX_ROWS] = {0}, b[OBCA_MAX_ROWS] = {0}, ego[4] = {1, 1, 1, 1}, xy[4] = {0, 1, 0, 1};
@@ -927,7 +827,7 @@ int obca_parking_eval_batch_dev(int B, int N, int nOb, const int* vOb, const dou
   DevCtx* c;
   int rc = get_ctx(opts ? opts->device : 0, &c);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
   EvalIn in; in.x0 = x0; in.xF = xF; in.rx = rx; in.ry = ry; in.ryaw = ryaw; in.xp = xp; in.up = up; in.ts = ts; in.lp = lp;
   in.np = np; in.sl = sl; in.y = y;
   EvalOut out; out.c = c_out; out.gradL = gradL_out; out.fk = fk_out;

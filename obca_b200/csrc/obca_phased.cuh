@@ -1,26 +1,30 @@
 // obca_phased.cuh -- phase-split ("lock-step") driver of the batched parking solve.
 //
-// The interior-point loop of IpmDriver<M>::solve (obca_solver.cuh) restated as a per-problem state machine so that
-// every phase of an iteration runs as its own kernel over ALL active problems of the batch, each with the launch
-// shape that suits it:
-//     k_pk_block    flat, thread per (problem, obstacle, stage) : the OBCA constraint blocks of K1 -- evaluation, KKT-error
-//                                                        partials, condensation onto the stage pose (streaming, no barriers)
-//     k_pk_phaseA   CTA per problem, thread per stage : stage terms of K1 (dynamics, objective, bounds), assembly of the
-//                                                        stage models, reductions, convergence test, barrier update
-//     (both once more for the problems whose barrier parameter was just reduced)
-//     k_pk_sweep    HALF-WARP per problem              : K3 stage-banded KKT sweep, stage slots streamed from HBM
-//                                                        through a cp.async ring; inertia-correction bookkeeping
-//     k_pk_rblock   flat, thread per (problem, obstacle, stage) : K4 step of the block unknowns from the stored local map
-//     k_pk_phaseC   CTA per problem, thread per stage : K4 costates, fraction-to-the-boundary, filter line search, update
-// The iterate, the step, the local maps, the block hand-over records and the stage slots of every problem live in HBM (layout: problem-major,
-// then [array][stage], so each warp streams contiguous slices); between kernels a problem is described by its
-// ProbState record (phase, iteration, barrier parameter, filter, ...).
-// When the active set has shrunk below what one wave of resident CTAs can hold, the remaining problems are handed to
-//     k_pk_tail     persistent CTA per problem: the same three phase functions in a loop, stage slots in shared memory
+// The interior-point loop of IpmDriver<M>::solve (obca_solver.cuh) restated as a per-problem state machine so that the
+// parallel phases and the serial-in-time KKT sweep of an iteration run as separate kernels over ALL active problems of
+// the batch, each with the launch shape that suits it.  One round = three launches:
+//     k_pk_eval    persistent CTAs, one problem at a time: K1 -- item pass (one thread per (obstacle, stage) block:
+//                  evaluation, KKT-error partials, condensation onto the stage pose; hand-over of the 12 doubles per block
+//                  the assembly needs IN THE STAGE SLOT, shared memory), stage pass (dynamics, objective, bounds, assembly
+//                  of the stage models), reductions, convergence test, barrier update -- and, when the barrier parameter
+//                  was reduced, the re-evaluation, in the same launch.  The finished stage models leave shared memory in
+//                  ONE bulk copy (cp.async.bulk.global.shared::cta, 53 KB per problem).  Also: initial point, end of
+//                  attempt (status / retry / checker), compaction of the active list.
+//     k_pk_sweep   HALF-WARP per problem: K3 stage-banded KKT sweep; the 656-byte stage slots are streamed from HBM through
+//                  a 4-deep ring of bulk copies (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), gains and
+//                  costate rows written back in place; inertia-correction bookkeeping.
+//     k_pk_step    persistent CTAs, one problem at a time: K4 -- item pass (steps of the block unknowns from the stored
+//                  local maps) + stage pass (costates, bounds), fraction-to-the-boundary, filter line search (merit
+//                  function: item + stage pass), iterate update.  The step of the block unknowns lives in shared memory.
+// The iterate, the local maps and the stage slots of every problem live in HBM (layout: problem-major, then [array][stage],
+// so each warp streams contiguous slices); between kernels a problem is described by its ProbState record (phase,
+// iteration, barrier parameter, filter, ...).  When the active set has shrunk far enough the remaining problems are handed to
+//     k_pk_tail    persistent CTA per problem: the same phase functions in a loop, stage slots in shared memory
 // which is also the whole solver for small batches.
 //
-// The arithmetic and its order are exactly those of IpmDriver<M>::solve, and the library is built without FMA contraction:
-// all schedules produce bit-identical iterates (tests/test_gpu_parking.py::test_phased_equals_persistent).
+// Every floating-point operation of a phase lives in ONE out-of-line device function per template instance
+// (PhasedDriver::phase_A / phase_C and the per-item / per-stage functions of ParkSolver) that all kernels call: the
+// schedules produce bit-identical iterates by construction (tests/test_gpu_parking.py::test_phased_equals_persistent).
 #pragma once
 #include "obca_check.cuh"
 #include "obca_solver.cuh"
@@ -28,7 +32,6 @@
 namespace obca {
 
 enum { PH_INIT = 0, PH_EVAL = 1, PH_EVAL2 = 2, PH_REASM = 3, PH_KKT = 4, PH_RECOVER = 5, PH_END = 6, PH_DONE = 7 };
-constexpr int GSTRIDE = 80;   // doubles per stage slot in global memory: RSTRIDE rounded up to a 16-byte multiple
 
 struct BatchPtrs {
   const double *x0, *xF, *rx, *ry, *ryaw, *xWS, *uWS, *lWS, *nWS;
@@ -37,13 +40,52 @@ struct BatchPtrs {
   double* kkt_err;
   int B;
   int retry;
-  unsigned long long* prof;   // optional: 8 cycle counters summed over the batch (device pointer)
+  int q4;                     // 1: reproduce the inverted test of ParkingDist.jl:278-282 after a second failure
+  unsigned long long* prof;   // optional: 8 counters summed over the batch (device pointer)
 };
 
 #if defined(__CUDACC__)
 
 // ------------------------------------------------------------------------------------------------------------
-// the three phase functions (all threads of a CTA call them with the same context; ProbState in shared memory)
+// Blackwell bulk-copy (TMA) and mbarrier primitives used by the round kernels
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes: multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// writes of the generic proxy (st.shared) become visible to the async proxy (the bulk copy engine)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// same for writes to global memory that a later bulk copy of this thread's warp reads back
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// the phase functions (all threads of a CTA call them with the same context; ProbState in shared memory)
 // ------------------------------------------------------------------------------------------------------------
 template <class M>
 struct PhasedDriver {
@@ -52,29 +94,16 @@ struct PhasedDriver {
 
   // A: [init] -> evaluate at the current iterate, convergence test, barrier update (+ re-evaluation), or re-assembly
   //    with a larger delta_w.  Leaves phase = PH_KKT (stage models ready) or PH_END (attempt over).
-  //    BLK (phase-split rounds): the obstacle blocks come from the flat block kernel through C.bo, so an evaluation can only
-  //    run when that kernel has seen the current iterate / barrier parameter: after the initial point the function returns
-  //    with PH_EVAL, after a barrier update with PH_EVAL2, and is called again once the blocks have been refreshed.
-  template <bool BLK>
-  __device__ static void eval_all(const Ctx& C, bool do_err, EvalPart& ep) {
-    const int NS = M::n_stages(C);
-    part_init(ep);
-    OBCA_FOR_STAGES(k, NS) {
-      EvalPart e1;
-      if (BLK) M::stage_eval_blk(C, k, do_err, true, e1); else M::stage_eval(C, k, do_err, true, e1);
-      part_merge(ep, e1);
-    }
-    OBCA_REDUCE(ep);
-  }
-  template <bool BLK>
-  __device__ static void phase_A(const Ctx& C) {
+  __device__ __noinline__ static void phase_A(const Ctx& C) {
     const IpmOpts& O = CTX_O(C);
     ProbState& S = *C.S;
     const int NS = M::n_stages(C);
     const int ph = S.phase;
     EvalPart ep;
     if (ph == PH_REASM) {
-      eval_all<BLK>(C, false, ep);
+      part_init(ep);
+      M::eval_phase(C, false, ep);
+      OBCA_REDUCE(ep);
       OBCA_SERIAL { S.ok = ep.ok; S.phase = PH_KKT; S.prof[7]++; }
       OBCA_SYNC();
       return;
@@ -94,46 +123,47 @@ struct PhasedDriver {
       // (S.phase may only change behind a barrier: every thread read it on entry)
       OBCA_SERIAL { S.phase = PH_EVAL; }
       OBCA_SYNC();
-      if (BLK) return;
     }
-    if (ph != PH_EVAL2) {
-      // (PH_EVAL: new iterate -- or a barrier kick: new direction from the same iterate)
-      OBCA_SERIAL { S.dw = 0.0; }
-      OBCA_SYNC();
-      eval_all<BLK>(C, true, ep);
-      OBCA_SERIAL {
-        S.prof[7]++;
-        D::apply_errors(C, ep);
-        S.ok = ep.ok;
-        if (S.first) {
-          S.theta_max = 1e4 * dmax(1.0, S.th_k);
-          S.theta_min = 1e-4 * dmax(1.0, S.th_k);
-          S.first = 0;
-        }
-        S.e0 = D::err_mu(C, 0.0);
-        S.iters = S.it;
-        S.flag = 0;
-        if (S.e0 <= O.tol && S.e_dual <= O.dual_inf_tol && S.e_pr <= O.constr_viol_tol && S.e_cmax <= O.compl_inf_tol) {
-          S.status = 1; S.flag = 1;
-        } else if (S.it >= O.max_iter) {
-          S.status = 0; S.flag = 1;
-        } else {
-          bool changed = false;
-          while (S.mu > O.mu_min && D::err_mu(C, S.mu) <= O.kappa_eps * S.mu) {
-            S.mu = dmax(O.mu_min, dmin_(O.kappa_mu * S.mu, pow(S.mu, O.theta_mu)));
-            S.tau = dmax(O.tau_min, 1.0 - S.mu);
-            changed = true;
-          }
-          if (changed) { S.nfilt = 0; S.flag = 2; }
-        }
-        S.phase = (S.flag == 1) ? PH_END : (S.flag == 2 ? PH_EVAL2 : PH_KKT);
+    // (PH_EVAL: new iterate -- or a barrier kick: new direction from the same iterate)
+    OBCA_SERIAL { S.dw = 0.0; }
+    OBCA_SYNC();
+    part_init(ep);
+    M::eval_phase(C, true, ep);
+    OBCA_REDUCE(ep);
+    OBCA_SERIAL {
+      S.prof[7]++;
+      D::apply_errors(C, ep);
+      S.ok = ep.ok;
+      if (S.first) {
+        S.theta_max = 1e4 * dmax(1.0, S.th_k);
+        S.theta_min = 1e-4 * dmax(1.0, S.th_k);
+        S.first = 0;
       }
-      OBCA_SYNC();
-      if (S.flag != 2 || BLK) return;
+      S.e0 = D::err_mu(C, 0.0);
+      S.iters = S.it;
+      S.flag = 0;
+      if (S.e0 <= O.tol && S.e_dual <= O.dual_inf_tol && S.e_pr <= O.constr_viol_tol && S.e_cmax <= O.compl_inf_tol) {
+        S.status = 1; S.flag = 1;
+      } else if (S.it >= O.max_iter) {
+        S.status = 0; S.flag = 1;
+      } else {
+        bool changed = false;
+        while (S.mu > O.mu_min && D::err_mu(C, S.mu) <= O.kappa_eps * S.mu) {
+          S.mu = dmax(O.mu_min, dmin_(O.kappa_mu * S.mu, pow(S.mu, O.theta_mu)));
+          S.tau = dmax(O.tau_min, 1.0 - S.mu);
+          changed = true;
+        }
+        if (changed) { S.nfilt = 0; S.flag = 2; }
+      }
+      S.phase = (S.flag == 1) ? PH_END : PH_KKT;
     }
+    OBCA_SYNC();
+    if (S.flag != 2) return;
     // mu changed: the barrier terms of the stage models (and phi) are stale
-    eval_all<BLK>(C, true, ep);
-    OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; S.phase = PH_KKT; }
+    part_init(ep);
+    M::eval_phase(C, true, ep);
+    OBCA_REDUCE(ep);
+    OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; S.prof[5]++; }
     OBCA_SYNC();
   }
 
@@ -154,18 +184,12 @@ struct PhasedDriver {
 
   // C: recover the full step, step lengths, filter line search, and -- when a step is accepted -- the iterate update.
   //    Leaves PH_EVAL (new iterate, or barrier kick: same iterate, new barrier parameter) or PH_END (line-search failure).
-  template <bool BLK>
-  __device__ static void phase_C(const Ctx& C) {
+  __device__ __noinline__ static void phase_C(const Ctx& C) {
     const IpmOpts& O = CTX_O(C);
     ProbState& S = *C.S;
-    const int NS = M::n_stages(C);
     StepPart sp;
     part_init(sp);
-    OBCA_FOR_STAGES(k, NS) {
-      StepPart s1;
-      if (BLK) M::recover_stage_blk(C, k, s1); else M::recover_stage(C, k, s1);
-      part_merge(sp, s1);
-    }
+    M::recover_phase(C, sp);
     OBCA_REDUCE(sp);
     OBCA_SERIAL {
       const double apr = sp.apr, adu = sp.adu, dphi = sp.dphi;
@@ -185,9 +209,10 @@ struct PhasedDriver {
       const double alpha = S.alpha;
       MeritPart mp;
       part_init(mp);
-      OBCA_FOR_STAGES(k, NS) { MeritPart m1; M::merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
+      M::merit_phase(C, alpha, mp);
       OBCA_REDUCE(mp);
       OBCA_SERIAL {
+        S.prof[6]++;
         const double th = mp.th, ph = mp.phi;
         S.th_t = th; S.ph_t = ph;
         bool in_filter = th >= S.theta_max || !(ph < 1e299);
@@ -230,7 +255,7 @@ struct PhasedDriver {
       if (S.flag != 0) break;
     }
     if (S.flag == 1) {      // accept
-      OBCA_FOR_STAGES(k, NS) M::update_stage(C, k);
+      M::update_phase(C);
       OBCA_SERIAL { M::update_scalars(C); S.it++; }
       OBCA_SYNC();
     }
@@ -257,7 +282,7 @@ template <int VM, bool SDV>
 __device__ __forceinline__ void pk_make_ctx(PkCtx& C, PkOutputs& out, const ParkProblem& P, const IpmOpts& O, const PkLay& L,
                                             const BatchPtrs& bp, int b, double* W) {
   const int N = P.N, NS = N + 1, V = P.V, nOb = P.nOb;
-  C.P = &P; C.O = &O; C.L = L; C.W = W; C.bo = nullptr;
+  C.P = &P; C.O = &O; C.L = L; C.W = W; C.Wd = W + (size_t)L.dLAM * L.NSP;
   C.in.x0 = bp.x0 + 4 * (size_t)b; C.in.xF = bp.xF + 4 * (size_t)b;
   C.in.rx = bp.rx + (size_t)NS * b; C.in.ry = bp.ry + (size_t)NS * b; C.in.ryaw = bp.ryaw + (size_t)NS * b;
   C.in.xWS = bp.xWS + (size_t)4 * NS * b; C.in.ldx = NS;
@@ -270,22 +295,27 @@ __device__ __forceinline__ void pk_make_ctx(PkCtx& C, PkOutputs& out, const Park
 }
 
 struct PkFinalScratch {
-  ChkPart chk[4];
+  ChkPart chk[8];
   int feas;
 };
 
-// End of an attempt (phase PH_END): the reference's status / retry logic around solve(m)
-// (ParkingSignedDist.jl:256-283): a failed first attempt is followed by one more solve from the last iterate; after a
-// second failure ParkingConstraints decides.  Leaves PH_INIT (second attempt) or PH_DONE (outputs written).
+// End of an attempt (phase PH_END): the reference's status / retry logic around solve(m).
+//   ParkingSignedDist.jl:256-283: status Optimal -> exitflag 1; Error / UserLimit -> one more solve from the last iterate;
+//     after a second failure ParkingConstraints decides (exitflag = Feasible).
+//   ParkingDist.jl:245-289: the first failure is followed by ParkingConstraints; only an INFEASIBLE point is solved again
+//     (a feasible one is accepted: exitflag 1, :259-262); after a second failure the reference's test is inverted
+//     (:278-282, Feasible == 0 -> exitflag 1: SURVEY Q4) -- reproduced with opts.q4 = 1, fixed (exitflag = Feasible) otherwise.
+// Leaves PH_INIT (second attempt) or PH_DONE (outputs written).
 template <int VM, bool SDV>
-__device__ void pk_end_of_attempt(const PkCtx& C, const PkOutputs& out, const BatchPtrs& bp, int b, PkFinalScratch& F) {
+__device__ __noinline__ void pk_end_of_attempt(const PkCtx& C, const PkOutputs& out, const BatchPtrs& bp, int b, PkFinalScratch& F) {
   ProbState& S = *C.S;
   const ParkProblem& P = CTX_P(C);
   const int NS = P.N + 1;
   const int status = S.status;
-  const bool again = !(status == 1 || !bp.retry || S.attempt == 1);
+  const int attempt = S.attempt;
   __syncthreads();      // everybody has read the state before thread 0 changes it
-  if (again) {
+  const bool failed = status != 1 && bp.retry;
+  if (failed && attempt == 0 && SDV) {      // SignedDist: always solve again
     if (threadIdx.x == 0) { S.iters_total += S.iters; S.attempt = 1; S.phase = PH_INIT; }
     __syncthreads();
     return;
@@ -293,7 +323,7 @@ __device__ void pk_end_of_attempt(const PkCtx& C, const PkOutputs& out, const Ba
   for (int k = threadIdx.x; k < NS; k += blockDim.x) ParkSolver<VM, SDV>::store_stage(C, k, out);
   __syncthreads();
   int exitflag = status == 1 ? 1 : 0;
-  if (status != 1 && bp.retry) {
+  if (failed) {
     ChkPart c;
     chk_init(c);
     for (int k = threadIdx.x; k < NS; k += blockDim.x) {
@@ -319,7 +349,20 @@ __device__ void pk_end_of_attempt(const PkCtx& C, const PkOutputs& out, const Ba
       F.feas = check_finish(P, c, out.ts, 0, 5e-5, e);
     }
     __syncthreads();
-    exitflag = F.feas ? 1 : 0;
+    const int feas = F.feas;
+    if (!SDV && attempt == 0) {
+      // ParkingDist.jl:256-263: only an infeasible point is solved again
+      if (!feas) {
+        if (threadIdx.x == 0) { S.iters_total += S.iters; S.attempt = 1; S.phase = PH_INIT; }
+        __syncthreads();
+        return;
+      }
+      exitflag = 1;
+    } else if (!SDV && bp.q4) {
+      exitflag = feas ? 0 : 1;          // ParkingDist.jl:278-282 as written (inverted)
+    } else {
+      exitflag = feas ? 1 : 0;          // ParkingSignedDist.jl:278-283
+    }
   }
   if (threadIdx.x == 0) {
     bp.exitflag[b] = exitflag;
@@ -330,15 +373,14 @@ __device__ void pk_end_of_attempt(const PkCtx& C, const PkOutputs& out, const Ba
   __syncthreads();
 }
 
-// phase A of one problem including the attempt bookkeeping; returns with phase in {PH_KKT, PH_DONE} (BLK: also PH_EVAL /
-// PH_EVAL2 when the block kernel has to run first)
-template <int VM, bool SDV, bool BLK>
+// phase A of one problem including the attempt bookkeeping; returns with phase in {PH_KKT, PH_DONE}
+template <int VM, bool SDV>
 __device__ __forceinline__ void pk_step_A(const PkCtx& C, const PkOutputs& out, const BatchPtrs& bp, int b, PkFinalScratch& F) {
   ProbState& S = *C.S;
   for (;;) {
     if (S.phase == PH_END) pk_end_of_attempt<VM, SDV>(C, out, bp, b, F);
     if (S.phase == PH_DONE) return;
-    PhasedDriver<ParkSolver<VM, SDV> >::template phase_A<BLK>(C);
+    PhasedDriver<ParkSolver<VM, SDV> >::phase_A(C);
     if (S.phase != PH_END) return;
   }
 }
@@ -347,207 +389,143 @@ __device__ __forceinline__ void state_fresh(ProbState& S) {
   if (threadIdx.x == 0) {
     S.phase = PH_INIT; S.attempt = 0; S.iters_total = 0; S.it = 0; S.first = 1; S.status = 0; S.iters = 0;
     S.t = 1.0; S.e0 = 0.0; S.ok = 0; S.flag = 0;
+    for (int i = 0; i < 8; ++i) S.prof[i] = 0;
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K_blk: the OBCA constraint blocks of K1 as a flat streaming kernel -- one thread per (active problem, obstacle, stage),
-// consecutive threads = consecutive stages, so every warp reads contiguous slices of the stacked (x, lambda, mu, sl, duals)
-// arrays; no shared memory, no barriers.  Each thread evaluates the signed-distance rows of its block, their
-// Lagrangian-gradient / KKT-error pieces, condenses the block onto the stage pose and writes the local factor
-// (workspace) and the 22-double hand-over record read by k_pk_phaseA.  pass 1: new iterates (PH_EVAL) and
-// inertia-correction re-assemblies (PH_REASM); pass 2: problems whose barrier parameter was just reduced (PH_EVAL2).
-// ------------------------------------------------------------------------------------------------------------
-#ifndef OBCA_MINB_BLK
-#define OBCA_MINB_BLK 3
+#ifndef OBCA_PK_THREADS
+#define OBCA_PK_THREADS 128
 #endif
-template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, OBCA_MINB_BLK)
-k_pk_block(const __grid_constant__ ParkProblem P, const PkLay L, double* __restrict__ Wall, double* __restrict__ BOall,
-           const ProbState* __restrict__ Sg, const int* __restrict__ act, const int* __restrict__ n_act, int pass) {
-  const int NS = P.N + 1, per = P.nOb * NS;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int a = (int)(idx / per);
-  if (a >= *n_act) return;
-  const int rem = (int)(idx - (long long)a * per);
-  const int j = rem / NS, k = rem - j * NS;
-  const int b = act[a];
-  const ProbState* S = Sg + b;
-  const int ph = S->phase;
-  bool do_err;
-  double dw;
-  if (pass == 1) {
-    if (ph == PH_EVAL) { do_err = true; dw = 0.0; }
-    else if (ph == PH_REASM) { do_err = false; dw = S->dw; }
-    else return;
-  } else {
-    if (ph != PH_EVAL2) return;
-    do_err = true; dw = 0.0;
-  }
-  const double mu_b = S->mu;
-  PkCtx C;
-  C.W = Wall + (size_t)b * L.total * L.NSP;
-  C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
-  const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
-  double sn_, cs_;
-  sincos(ps, &sn_, &cs_);
-  BlockOut B;
-  ParkSolver<VM, SDV>::block_eval(C, k, j, X, Y, cs_, sn_, mu_b, dw, do_err, true, B);
-  ParkSolver<VM, SDV>::block_store(C, k, j, B);
-}
+// CTA size of the per-problem kernels (item passes: nOb (N+1) work items, stage passes: N+1).  The same for all of them: the
+// per-thread partial sums of a reduction depend on it, and the schedules must round identically.
+constexpr int PK_THREADS = OBCA_PK_THREADS;
 
 // ------------------------------------------------------------------------------------------------------------
-// K_A: one CTA per active problem
+// K_eval: persistent CTAs, one problem at a time (see the file header).  fresh: first launch of a solve -- every problem
+// of the batch starts from its warm start (no active list yet).
 // ------------------------------------------------------------------------------------------------------------
 #ifndef OBCA_MINB_A
 #define OBCA_MINB_A 3
 #endif
 template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, OBCA_MINB_A)
-k_pk_phaseA(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
-            double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
-            double* __restrict__ BOall, const int* __restrict__ act_in, const int* __restrict__ n_in, int* __restrict__ act_out,
-            int* __restrict__ n_out, int fresh, int pass) {
-  extern __shared__ double s_ric[];     // (N+1) x RSTRIDE stage slots, assembled here, streamed out for the sweep kernel
+__global__ void __launch_bounds__(PK_THREADS, OBCA_MINB_A)
+k_pk_eval(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
+          double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
+          const int* __restrict__ act_in, const int* __restrict__ n_in, int* __restrict__ act_out, int* __restrict__ n_out,
+          int fresh) {
+  extern __shared__ __align__(16) double s_ric[];     // (N+1) x RSTRIDE stage slots: hand-over area of the item pass, then
+                                                     // the assembled stage models, bulk-copied out for the sweep kernel
   __shared__ ProbState S;
   __shared__ double s_red[4 * 12];
   __shared__ PkFinalScratch s_fin;
-  if ((int)blockIdx.x >= *n_in) return;
-  const int b = fresh ? (int)blockIdx.x : act_in[blockIdx.x];
-  const int NS = P.N + 1;
-  if (pass == 2 && Sg[b].phase != PH_EVAL2) return;      // second pass of a round: only problems whose barrier parameter changed
-  if (fresh) state_fresh(S); else state_load(S, Sg + b);
-  __syncthreads();
-  if (threadIdx.x == 0) S.prof[7] = 0;      // K1 evaluations of this launch (diagnostic counter, see obca_last_profile)
-  // the context is identical for every thread: one copy in shared memory (not one per thread in local memory)
   __shared__ PkCtx C; __shared__ PkOutputs out;
-  if (threadIdx.x == 0) {
-    pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
-    C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
-    C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
-  }
-  __syncthreads();
-  pk_step_A<VM, SDV, true>(C, out, bp, b, s_fin);
-  if (S.phase == PH_KKT) {
-    double* g = slots + (size_t)b * NS * GSTRIDE;
-    for (int i = threadIdx.x; i < NS * RSTRIDE; i += blockDim.x) {
-      const int k = i / RSTRIDE, o = i - k * RSTRIDE;
-      g[(size_t)k * GSTRIDE + o] = s_ric[i];
+  const int NS = P.N + 1;
+  const int n = fresh ? bp.B : *n_in;
+  unsigned long long n_eval = 0, n_eval2 = 0;
+  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+    const int b = fresh ? a : act_in[a];
+    if (fresh) state_fresh(S); else state_load(S, Sg + b);
+    if (threadIdx.x == 0) {
+      bulk_wait_read0();      // the bulk copy of the previous problem has finished reading the slots
+      pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
+      C.ric = s_ric; C.pp = s_ric; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { S.prof[7] = 0; S.prof[5] = 0; }
+    __syncthreads();
+    pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
+    if (S.phase == PH_KKT) {
+      fence_proxy_async();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        bulk_s2g(slots + (size_t)b * NS * RSTRIDE, s_ric, (unsigned)(NS * RSTRIDE * sizeof(double)));
+        bulk_commit();
+      }
+    }
+    state_store(Sg + b, S);
+    if (threadIdx.x == 0) {
+      n_eval += (unsigned long long)S.prof[7]; n_eval2 += (unsigned long long)S.prof[5];
+      if (S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
+    }
+    __syncthreads();
   }
-  state_store(Sg + b, S);
   if (threadIdx.x == 0) {
-    if (bp.prof) atomicAdd(bp.prof + (pass == 1 ? 7 : 5), (unsigned long long)S.prof[7]);
-    if (pass == 1 && S.phase != PH_DONE) act_out[atomicAdd(n_out, 1)] = b;
+    bulk_wait_read0();
+    if (bp.prof) { atomicAdd(bp.prof + 7, n_eval); atomicAdd(bp.prof + 5, n_eval2); }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K_B: half-warp per problem.  Backward Riccati sweep + forward roll-out with the stage slots streamed from global memory
-// (each slot = 640 contiguous bytes) through a 4-deep cp.async ring; gains and the P_{k+1} rows needed by the
-// multiplier recovery are written back in place (consumed Q/q space of the slots).
+// K_sweep: one WARP per problem (wide lane program of ParkSolver: <= 2 scalar tasks per lane and step).  Backward Riccati
+// sweep + forward roll-out with the stage slots streamed from global memory (each slot = 656 contiguous bytes) through a
+// ring of asynchronous copies, SWEEP_DEPTH - 1 stages ahead: the recursion is a serial chain, so the look-ahead has to
+// cover the memory latency at a fraction of a microsecond per stage.  Gains and the P_k rows needed by the multiplier
+// recovery are written back in place (consumed Q/q space of the slots).
+// The ring uses LDGSTS (cp.async, 41 x 16 bytes per slot spread over the lanes), not bulk copies: measured on B200 the same
+// ring with cp.async.bulk + mbarrier per slot (one elected lane, SWEEP_DEPTH 4 / 8 / 16) took 26.3 / 23.1 / 20.7 ms per
+// config-2 solve against 15.9 ms with LDGSTS -- the issue sequence of a bulk copy (expect-tx, uniform-register moves,
+// try-wait) sits on the latency-bound chain of every stage, the LDGSTS of a lane does not.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SWEEP_DEPTH = 4;
+#ifndef OBCA_SWEEP_DEPTH
+#define OBCA_SWEEP_DEPTH 8
+#endif
+constexpr int SWEEP_DEPTH = OBCA_SWEEP_DEPTH;      // ring slots per warp (power of two)
+constexpr int SWEEP_WARP_DOUBLES = SWEEP_DEPTH * RSTRIDE + 240;   // ring + tile (ParkSolver::WIDE_TILE)
+static_assert((RSTRIDE * 8) % 16 == 0 && (SWEEP_WARP_DOUBLES % 2) == 0, "16-byte alignment of the ring slots");
 
-// ------------------------------------------------------------------------------------------------------------
-// Two problems per warp: the lane code of the sweep uses 9 of 32 lanes, so each HALF-warp runs one problem (lanes 0..15 /
-// 16..31, same instruction stream, own ring / exchange tile / pointers).  Halves the instruction and shared-memory traffic
-// per sweep; the kernel is issue / MIO bound (profiles/ncu_summary_r01.md).  A half without work (odd count, problem not
-// waiting for a sweep, local pivots already failed) executes along on valid memory with every global write redirected
-// to a shared-memory dump area.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int SWEEP_HALF_DOUBLES = SWEEP_DEPTH * GSTRIDE + 144 + 48 + 4;   // ring + tile + dump + 4 (bank offset between the halves)
-
-__device__ __forceinline__ void sweep_prefetch16(double* ring, const double* gslots, int k, int hl, int n) {
+__device__ __forceinline__ void sweep_prefetch(double* ring, const double* gslots, int k, int lane, int n) {
   if (k >= 0 && k < n) {
-    double* dst = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
-    const double* src = gslots + (size_t)k * GSTRIDE;
-    cp_async16(dst + 2 * hl, src + 2 * hl);
-    cp_async16(dst + 32 + 2 * hl, src + 32 + 2 * hl);
-    if (hl < 8) cp_async16(dst + 64 + 2 * hl, src + 64 + 2 * hl);
+    double* dst = ring + (k & (SWEEP_DEPTH - 1)) * RSTRIDE;
+    const double* src = gslots + (size_t)k * RSTRIDE;
+    cp_async16(dst + 2 * lane, src + 2 * lane);                          // 41 x 16 bytes: 32 + 9
+    if (lane < RSTRIDE / 2 - 32) cp_async16(dst + 64 + 2 * lane, src + 64 + 2 * lane);
   }
   cp_async_commit();
 }
 
-// run: this half has a sweep to do (uniform within the half).  Returns 1 if the half's sweep found inertia (n, m, 0).
+// one warp, one problem.  Returns 1 if the sweep found inertia (n, m, 0).
 template <int VM, bool SDV>
-__device__ int pk_sweep_pair(const ParkProblem& Pp, const IpmOpts& O, const PkLay& Lay, double* W, double* gslots,
-                             ProbState* Sgl, bool run, double* ring, double* tile, double* dump) {
+__device__ int pk_sweep_warp(const ParkProblem& Pp, const IpmOpts& O, const PkLay& Lay, double* W, double* gslots,
+                             ProbState* Sgl, double* ring, double* tile) {
   typedef ParkSolver<VM, SDV> PS;
   const int N = Pp.N;
-  const int lane = threadIdx.x & 31, hl = lane & 15, base = lane & 16;
-  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   PkCtx C;
   C.P = &Pp; C.O = &O; C.L = Lay; C.W = W;
-  typename PS::KktLane L;
-  // kl_init zeroes tile[70 .. 90] with 21 lanes; a half has 16
-  PS::kl_init(L, hl, tile, C);
-  if (hl < 5) tile[86 + hl] = 0.0;
-  sweep_prefetch16(ring, gslots, N - 1, hl, N);
-  sweep_prefetch16(ring, gslots, N - 2, hl, N);
-  sweep_prefetch16(ring, gslots, N - 3, hl, N);
+  typename PS::WideLane L;
+#pragma unroll
+  for (int a = 1; a < SWEEP_DEPTH; ++a) sweep_prefetch(ring, gslots, N - a, lane, N);
+  PS::wl_init(L, lane);
+  PS::wl_zero(lane, tile, gslots + (size_t)N * RSTRIDE);
+  __syncwarp();
+  PS::wl_terminal(lane, tile, gslots + (size_t)N * RSTRIDE, C);
   __syncwarp();
   for (int k = N - 1; k >= 0; --k) {
-    sweep_prefetch16(ring, gslots, k - 3, hl, N);
-    cp_async_wait<3>();
+    sweep_prefetch(ring, gslots, k - (SWEEP_DEPTH - 1), lane, N);
+    cp_async_wait<SWEEP_DEPTH - 1>();
     __syncwarp();
-    const double* slot = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
-    double* gk = gslots + (size_t)k * GSTRIDE;
-    const bool wr = run && L.ok;
-    PS::kl_step1(L, hl, slot, tile, wr ? gk + GSTRIDE : dump);
+    const double* slot = ring + (k & (SWEEP_DEPTH - 1)) * RSTRIDE;
+    PS::wl_step1(L, slot, tile);
     __syncwarp();
-    PS::kl_step2(L, hl, slot, tile);
+    PS::wl_step2(L, slot, tile);
     __syncwarp();
-    PS::kl_step3(L, hl, wr ? gk : dump, tile);
+    PS::wl_step3(L, gslots + (size_t)k * RSTRIDE, tile);
     __syncwarp();
-    if (!__any_sync(FULL, run && L.ok)) break;      // both halves have nothing (left) to do
+    if (!L.ok) break;
   }
   cp_async_wait<0>();
-  const bool good = run && L.ok;
-  if (!__any_sync(FULL, good)) return 0;
-  int ok = good ? 1 : 0;
-  if (hl == IT) { tile[63] = L.Prow[IT]; tile[64] = L.pl; }
-  __threadfence();
+  if (!L.ok) return 0;
+  __threadfence();      // the gains written above are read back through the ring below
   __syncwarp();
-  double dt = 0.0;
-  if (!Pp.fix_time) {
-    double ptt = tile[63];
-    if (!(ptt > 0.0)) { ok = 0; ptt = 1e300; }
-    dt = -tile[64] / ptt;
-  }
-  if (hl == 0 && good) Sgl->dt = dt;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
-  const int ur = hl & 1, xr = hl & 3;
-  const double selx = (xr == 0) ? 1.0 : 0.0, sely = (xr == 1) ? 1.0 : 0.0;
-  double* const dxw = W + (size_t)(Lay.dX + xr) * Lay.NSP;
-  double* const duw = W + (size_t)(Lay.dDE + ur) * Lay.NSP;
-  __syncwarp();
-  sweep_prefetch16(ring, gslots, 0, hl, N); sweep_prefetch16(ring, gslots, 1, hl, N); sweep_prefetch16(ring, gslots, 2, hl, N);
-  for (int k = 0; k < N; ++k) {
-    sweep_prefetch16(ring, gslots, k + 3, hl, N);
-    cp_async_wait<3>();
+#pragma unroll
+  for (int a = 0; a < SWEEP_DEPTH - 1; ++a) sweep_prefetch(ring, gslots, a, lane, N);
+  const int ok = PS::kkt_forward_warp(C, tile, Sgl, true, [&](int k) {
+    sweep_prefetch(ring, gslots, k + (SWEEP_DEPTH - 1), lane, N);
+    cp_async_wait<SWEEP_DEPTH - 1>();
     __syncwarp();
-    const double* const slot = ring + (k & (SWEEP_DEPTH - 1)) * GSTRIDE;
-    const double* const kr = slot + RK + ur * NSV;
-    double u = slot[RK + 14 + ur] + kr[0] * s0 + kr[1] * s1 + kr[2] * s2 + kr[3] * s3 + kr[4] * s4 + kr[5] * s5 + kr[6] * dt;
-    const double u0 = __shfl_sync(FULL, u, base + 0), u1 = __shfl_sync(FULL, u, base + 1);
-    const double* const dr = slot + RDYN + 5 * xr;
-    double sn = slot[RR4 + xr] + selx * s0 + sely * s1 + dr[0] * s2 + dr[1] * s3 + dr[2] * dt + dr[3] * u0 + dr[4] * u1;
-    if (hl < 2 && good) duw[k] = u;
-    s0 = __shfl_sync(FULL, sn, base + 0); s1 = __shfl_sync(FULL, sn, base + 1); s2 = __shfl_sync(FULL, sn, base + 2);
-    s3 = __shfl_sync(FULL, sn, base + 3);
-    s4 = u0; s5 = u1;
-    if (hl < 4 && good) {
-      if (k + 1 < N) dxw[k + 1] = sn;
-      else Sgl->eN[xr] = sn;
-    }
-    __syncwarp();
-  }
+    return (const double*)(ring + (k & (SWEEP_DEPTH - 1)) * RSTRIDE);
+  });
   cp_async_wait<0>();
-  if (good) {
-    if (hl < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
-    if (hl < 2) duw[N] = 0.0;
-  }
   return ok;
 }
 
@@ -556,111 +534,87 @@ template <int VM, bool SDV>
 __global__ void __launch_bounds__(32 * SWEEP_WARPS)
 k_pk_sweep(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L,
            double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
-           const int* __restrict__ act, const int* __restrict__ n_act) {
-  __shared__ __align__(16) double s_w[SWEEP_WARPS][2 * SWEEP_HALF_DOUBLES];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+           const int* __restrict__ act, const int* __restrict__ n_act, int* __restrict__ n_zero) {
+  extern __shared__ __align__(16) double s_w[];      // SWEEP_WARPS x SWEEP_WARP_DOUBLES
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n_zero) *n_zero = 0;      // the active count that the next round's K_eval fills
   const int n = *n_act;
-  const int first = (blockIdx.x * SWEEP_WARPS + warp) * 2;
-  if (first >= n) return;
-  const int idx = first + half;
-  const bool valid = idx < n;
-  const int b = act[valid ? idx : first];              // a half without a problem reads its partner's (valid) memory
+  const int idx = blockIdx.x * SWEEP_WARPS + warp;
+  if (idx >= n) return;
+  const int b = act[idx];
   ProbState* S = Sg + b;
-  const bool active = valid && S->phase == PH_KKT;
-  if (!__any_sync(0xffffffffu, active)) return;
+  if (S->phase != PH_KKT) return;
   const int NS = P.N + 1;
-  const bool run = active && S->ok != 0;
-  double* hw = s_w[warp] + half * SWEEP_HALF_DOUBLES;
+  double* hw = s_w + (size_t)warp * SWEEP_WARP_DOUBLES;
   int ok = 0;
-  if (__any_sync(0xffffffffu, run))
-    ok = pk_sweep_pair<VM, SDV>(P, O, L, Wall + (size_t)b * L.total * L.NSP, slots + (size_t)b * NS * GSTRIDE, S, run, hw,
-                                hw + SWEEP_DEPTH * GSTRIDE, hw + SWEEP_DEPTH * GSTRIDE + 144);
+  if (S->ok != 0)
+    ok = pk_sweep_warp<VM, SDV>(P, O, L, Wall + (size_t)b * L.total * L.NSP, slots + (size_t)b * NS * RSTRIDE, S, hw,
+                                hw + SWEEP_DEPTH * RSTRIDE);
   __syncwarp();
-  if (hl == 0 && active) PhasedDriver<ParkSolver<VM, SDV> >::phase_B_serial(*S, O, run ? ok : 0);
+  if (lane == 0) PhasedDriver<ParkSolver<VM, SDV> >::phase_B_serial(*S, O, ok);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K_rblk: step recovery of the OBCA blocks as a flat streaming kernel (same thread mapping as k_pk_block): reads the local
-// factor written by k_pk_block and the pose step of the sweep, writes the steps of (lambda, mu, sl) and the new multipliers
-// of the block's rows into the workspace, and a 5-double record (tightest primal / dual fractions to the boundary, barrier
-// directional derivative) for k_pk_phaseC.
-// ------------------------------------------------------------------------------------------------------------
-template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, OBCA_MINB_BLK)
-k_pk_rblock(const __grid_constant__ ParkProblem P, const PkLay L, double* __restrict__ Wall, double* __restrict__ BOall,
-            const ProbState* __restrict__ Sg, const int* __restrict__ act, const int* __restrict__ n_act) {
-  const int NS = P.N + 1, per = P.nOb * NS;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int a = (int)(idx / per);
-  if (a >= *n_act) return;
-  const int rem = (int)(idx - (long long)a * per);
-  const int j = rem / NS, k = rem - j * NS;
-  const int b = act[a];
-  const ProbState* S = Sg + b;
-  if (S->phase != PH_RECOVER) return;
-  const double mu_b = S->mu, dw = S->dw;
-  PkCtx C;
-  C.W = Wall + (size_t)b * L.total * L.NSP;
-  C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
-  const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
-  const double dX = WA(dX, k), dY = WA(dY, k), dP = WA(dPS, k);
-  double sn_, cs_;
-  sincos(ps, &sn_, &cs_);
-  typename ParkSolver<VM, SDV>::RBlockOut rb;
-  ParkSolver<VM, SDV>::block_recover(C, k, j, X, Y, cs_, sn_, dX, dY, dP, mu_b, dw, rb);
-  ParkSolver<VM, SDV>::rblock_store(C, k, j, rb);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K_C: one CTA per active problem
+// K_step: persistent CTAs, one problem at a time.  The rows of the step that the sweep does not produce (block unknowns,
+// new multipliers, slack steps: 40 of 46 rows for config 2) never leave shared memory.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef OBCA_MINB_C
-#define OBCA_MINB_C 4
+#define OBCA_MINB_C 5
 #endif
 template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, OBCA_MINB_C)
-k_pk_phaseC(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
-            double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg, double* __restrict__ BOall,
-            const int* __restrict__ act, const int* __restrict__ n_act) {
+__global__ void __launch_bounds__(PK_THREADS, OBCA_MINB_C)
+k_pk_step(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
+          double* __restrict__ Wall, double* __restrict__ slots, ProbState* __restrict__ Sg,
+          const int* __restrict__ act, const int* __restrict__ n_act) {
+  extern __shared__ __align__(16) double s_step[];      // (dRS + 1 - dLAM) x NSP
   __shared__ ProbState S;
   __shared__ double s_red[4 * 12];
-  if ((int)blockIdx.x >= *n_act) return;
-  const int b = act[blockIdx.x];
-  if (Sg[b].phase != PH_RECOVER) return;
-  const int NS = P.N + 1;
-  state_load(S, Sg + b);
   __shared__ PkCtx C; __shared__ PkOutputs out;
-  if (threadIdx.x == 0) {
-    pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
-    C.ric = nullptr; C.pp = slots + (size_t)b * NS * GSTRIDE; C.pps = GSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
-    C.bo = BOall + (size_t)b * P.nOb * BO_N * L.NSP;
+  const int NS = P.N + 1;
+  const int n = *n_act;
+  unsigned long long n_merit = 0;
+  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+    const int b = act[a];
+    if (Sg[b].phase != PH_RECOVER) continue;      // (uniform: every thread reads the same word)
+    state_load(S, Sg + b);
+    if (threadIdx.x == 0) {
+      pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
+      C.Wd = s_step;
+      C.ric = nullptr; C.pp = slots + (size_t)b * NS * RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) S.prof[6] = 0;
+    __syncthreads();
+    PhasedDriver<ParkSolver<VM, SDV> >::phase_C(C);
+    state_store(Sg + b, S);
+    if (threadIdx.x == 0) n_merit += (unsigned long long)S.prof[6];
+    __syncthreads();
   }
-  __syncthreads();
-  PhasedDriver<ParkSolver<VM, SDV> >::template phase_C<true>(C);
-  state_store(Sg + b, S);
+  if (threadIdx.x == 0 && bp.prof) atomicAdd(bp.prof + 6, n_merit);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// tail / small-batch kernel: persistent CTAs pull problems (fresh, or handed over by the phase kernels at a round
-// boundary) and run the three phases in a loop with the stage slots in shared memory.
+// tail / small-batch kernel: persistent CTAs pull problems (fresh, or handed over by the round kernels at a round
+// boundary) and run the phases in a loop with the stage slots in shared memory.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef OBCA_MIN_BLOCKS
 #define OBCA_MIN_BLOCKS 3
 #endif
 template <int VM, bool SDV>
-__global__ void __launch_bounds__(128, OBCA_MIN_BLOCKS)
+__global__ void __launch_bounds__(PK_THREADS, OBCA_MIN_BLOCKS)
 k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts O, const PkLay L, const BatchPtrs bp,
           double* __restrict__ Wall, ProbState* __restrict__ Sg, const int* __restrict__ act, const int* __restrict__ n_act,
           int* __restrict__ counter, int fresh) {
-  extern __shared__ double s_ric[];
+  extern __shared__ __align__(16) double s_ric[];
   __shared__ ProbState S;
-  __shared__ double s_tile[144];
+  __shared__ double s_tile[ParkSolver<VM, SDV>::WIDE_TILE];
   __shared__ double s_red[4 * 12];
   __shared__ PkFinalScratch s_fin;
   __shared__ int s_i;
   __shared__ PkCtx C; __shared__ PkOutputs out;
   typedef ParkSolver<VM, SDV> PS;
-  const int n = *n_act;
+  const int n = fresh ? bp.B : *n_act;
+  unsigned long long n_eval = 0, n_merit = 0;
   for (;;) {
     if (threadIdx.x == 0) s_i = atomicAdd(counter, 1);
     __syncthreads();
@@ -669,13 +623,14 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
     const int b = fresh ? i : act[i];
     if (fresh) state_fresh(S); else state_load(S, Sg + b);
     if (threadIdx.x == 0) {
-      S.prof[7] = 0;
       pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
-      C.ric = s_ric; C.pp = s_ric; C.pps = RSTRIDE; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
+      C.ric = s_ric; C.pp = s_ric; C.red_scratch = s_red; C.tile = s_tile; C.S = &S;
     }
     __syncthreads();
+    if (threadIdx.x == 0) { S.prof[7] = 0; S.prof[6] = 0; }
+    __syncthreads();
     for (;;) {
-      pk_step_A<VM, SDV, false>(C, out, bp, b, s_fin);
+      pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
       if (S.phase == PH_DONE) break;
       if (threadIdx.x < 32) {
         int ok = S.ok;
@@ -684,11 +639,12 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
         if (threadIdx.x == 0) PhasedDriver<PS>::phase_B_serial(S, O, ok);
       }
       __syncthreads();
-      if (S.phase == PH_RECOVER) PhasedDriver<PS>::template phase_C<false>(C);
+      if (S.phase == PH_RECOVER) PhasedDriver<PS>::phase_C(C);
     }
-    if (threadIdx.x == 0 && bp.prof) atomicAdd(bp.prof + 6, (unsigned long long)S.prof[7]);
+    if (threadIdx.x == 0) { n_eval += (unsigned long long)S.prof[7]; n_merit += (unsigned long long)S.prof[6]; }
     __syncthreads();
   }
+  if (threadIdx.x == 0 && bp.prof) { atomicAdd(bp.prof + 4, n_eval); atomicAdd(bp.prof + 3, n_merit); }
 }
 
 #endif  // __CUDACC__

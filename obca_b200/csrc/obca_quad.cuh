@@ -934,6 +934,25 @@ struct QuadSolver {
     }
   }
 
+  // phase wrappers of the generic driver (the quadcopter model has no separate item pass: its 5 box blocks are evaluated
+  // inside the stage functions)
+  OBCA_HD static void eval_phase(const QCtx& C, bool do_err, EvalPart& ep) {
+    const int NS = C.P->N + 1;
+    OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, do_err, true, e1); part_merge(ep, e1); }
+  }
+  OBCA_HD static void recover_phase(const QCtx& C, StepPart& sp) {
+    const int NS = C.P->N + 1;
+    OBCA_FOR_STAGES(k, NS) { StepPart s1; recover_stage(C, k, s1); part_merge(sp, s1); }
+  }
+  OBCA_HD static void merit_phase(const QCtx& C, double alpha, MeritPart& mp) {
+    const int NS = C.P->N + 1;
+    OBCA_FOR_STAGES(k, NS) { MeritPart m1; merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
+  }
+  OBCA_HD static void update_phase(const QCtx& C) {
+    const int NS = C.P->N + 1;
+    OBCA_FOR_STAGES(k, NS) update_stage(C, k);
+  }
+
   OBCA_HD static void store_stage(const QCtx& C, int k, const QOutputs& o) {
     const int N = C.P->N;
     for (int i = 0; i < QNX; ++i) o.xp[(size_t)QNX * k + i] = QA(X, i, k);

@@ -19,6 +19,7 @@
 
 #if defined(__CUDA_ARCH__)
 #define OBCA_FOR_STAGES(k, ns) for (int k = threadIdx.x; k < (ns); k += blockDim.x)
+#define OBCA_FOR_ITEMS(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define OBCA_SYNC() __syncthreads()
 #define OBCA_SERIAL if (threadIdx.x == 0)
 // phase profiling: thread 0 charges the cycles since the last mark to counter i (call right after a barrier)
@@ -28,6 +29,7 @@
 #define OBCA_PROF(i)
 #define OBCA_PROF_COUNT(i)
 #define OBCA_FOR_STAGES(k, ns) for (int k = 0; k < (ns); ++k)
+#define OBCA_FOR_ITEMS(i, n) for (int i = 0; i < (n); ++i)
 #define OBCA_SYNC()
 #define OBCA_SERIAL
 #endif
@@ -103,15 +105,17 @@ __device__ __forceinline__ void block_reduce(T& v, void* scratch) {
 #define OBCA_REDUCE(v)
 #endif
 
-// ---- what one (stage, obstacle) OBCA block contributes to its stage (K1): computed in line by the persistent kernels,
-//      or by the flat block kernel of the phase-split driver, which hands it over through global memory ----
+// ---- what one (stage, obstacle) OBCA block contributes to its stage (K1).  The blocks are evaluated by the "item" pass of
+//      an evaluation (one thread per (obstacle, stage) pair); the 12 doubles the stage assembly needs (Schur complement,
+//      gradient, Lagrangian-gradient rows of the pose) are handed over through the stage's own slot in shared memory, the
+//      KKT-error / merit partials are merged into the thread's running EvalPart ----
 struct BlockOut {
   double Sxx[6], rx3[3];   // Schur complement and gradient on the pose (X, Y, psi)      (assembly)
   double gx[3];            // the block's rows of the Lagrangian gradient on the pose    (errors)
   double e_dual, e_pr, cmax, cmin, sum_y, sum_z, th, lsum, fobj;   // KKT-error / merit partials; lsum = sum of log(gap)
   int ok;                  // 1: every local pivot had the sign required for inertia (n, m, 0)
 };
-constexpr int BO_N = 22;   // doubles per block in the global hand-over array (ok stored as a double)
+constexpr int HO_N = 12;   // doubles per block handed over in the stage slot: Sxx 6 | rx3 3 | gx 3 (slot offset HO_N * j)
 
 // ---- workspace layout: every entry is an array of NSP doubles indexed by stage ----
 struct PkLay {
@@ -139,7 +143,7 @@ __constant__ PkLay c_pkL;
 inline PkLay make_layout(const ParkProblem& P, int nfac) {
   PkLay L;
   const int NS = P.N + 1;
-  L.NSP = ((NS + 31) / 32) * 32;
+  L.NSP = (NS + 1) & ~1;      // row stride: even, so that every row starts on a 16-byte boundary (bulk copies)
   int c = 0;
   auto take = [&](int n) { int o = c; c += n; return o; };
   L.X = take(1); L.Y = take(1); L.PS = take(1); L.VL = take(1); L.DE = take(1); L.AC = take(1);
@@ -164,7 +168,10 @@ inline PkLay make_layout(const ParkProblem& P, int nfac) {
 //   after stage_eval(k):   [RQ..] Q (45, packed 9x9) | [Rq..] q (9) | [RDYN..] dynamics Jacobian (20) | [RR4..] residual (4)
 //   after the backward sweep passed stage k:  [RK..] gain K (2x7) + feed-forward (2)  and, in slot k+1,
 //                                             [RPP..] rows 0..3 of P_{k+1} (4x7) + p_{k+1}[0..3]  (consumed Q/q space)
-constexpr int RSTRIDE = 79;   // odd -> conflict-free column accesses
+// 82 doubles = 656 bytes: a multiple of 16, so that the whole slot array of a problem leaves shared memory in ONE bulk
+// copy (cp.async.bulk) and the sweep kernel streams single slots back with bulk copies; 82 = 2 mod 4 costs a 2-way bank
+// conflict on the thread-per-stage accesses (an odd stride would be conflict-free but misaligns every second slot).
+constexpr int RSTRIDE = 82;
 constexpr int RQ = 0, Rq = 45, RDYN = 54, RR4 = 74;
 constexpr int RK = 0, RPP = 16, Rpp = 44;   // RPP: rows 0..3 of P_{k+1}, row-major 4x7;  Rpp: p_{k+1}[0..3]
 
@@ -228,11 +235,10 @@ struct PkCtx {
   const IpmOpts* O;
   PkLay L;
   double* W;
+  double* Wd;      // rows dLAM .. dRS of the step (those the sweep does not write): W + dLAM * NSP, or shared memory
   double* ric;     // (N+1) x RSTRIDE slots
-  double* bo;        // phase-split driver: per-problem block hand-over array, [obstacle][BO_N][NSP]; nullptr otherwise
-  const double* pp;  // where recover_stage finds rows 0..3 of P_{k+1} / p_{k+1}: slot base + stride (doubles).  The
-  int pps;           // persistent kernel and the emulation keep them in the stage slots (pp = ric, pps = RSTRIDE);
-                     // the phase-split driver reads them from the global slot array written by the sweep kernel.
+  const double* pp;  // where recover_stage finds rows 0..3 of P_{k+1} / p_{k+1}: the stage slots (shared memory in the
+                     // persistent kernel and the emulation; the global slot array written by the sweep kernel in the rounds)
   void* red_scratch;   // device: shared-memory scratch of block_reduce
   double* tile;        // device: 7*9+7 doubles of shared memory for the warp-cooperative KKT sweep
   ProbState* S;
@@ -241,8 +247,11 @@ struct PkCtx {
 
 #define WA(name, k) (C.W[(size_t)(CTX_L(C).name) * CTX_L(C).NSP + (k)])
 #define WV(name, i, k) (C.W[(size_t)(CTX_L(C).name + (i)) * CTX_L(C).NSP + (k)])
+// step rows that live in the step buffer (dLAM, dMU, dSL, PIn, YNn, YRn, dSD, dSN, dRS: contiguous in the layout)
+#define WD(name, k) (C.Wd[(size_t)(CTX_L(C).name - CTX_L(C).dLAM) * CTX_L(C).NSP + (k)])
+#define WDV(name, i, k) (C.Wd[(size_t)(CTX_L(C).name - CTX_L(C).dLAM + (i)) * CTX_L(C).NSP + (k)])
 #define RIC(off, k) (C.ric[(k) * RSTRIDE + (off)])
-#define PPV(off, k) (C.pp[(size_t)(k) * C.pps + (off)])
+#define PPV(off, k) (C.pp[(size_t)(k) * RSTRIDE + (off)])
 
 OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
   const double pl = dmin_(k1 * dmax(1.0, dabs(lo)), k2 * (hi - lo));
@@ -436,49 +445,45 @@ struct ParkSolver {
     B.e_dual = e_dual; B.e_pr = e_pr; B.cmax = cmax; B.cmin = cmin; B.sum_y = sum_y; B.sum_z = sum_z; B.th = th;
     B.lsum = do_err ? lacc.total() : 0.0; B.fobj = fobj;
   }
-  // hand-over of a block through global memory (phase-split driver): [obstacle][field][stage]
-  OBCA_HD static void block_store(const PkCtx& C, int k, int j, const BlockOut& B) {
-    double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
-    const size_t st = CTX_L(C).NSP;
+  // ---------------------------------------------------------------------------------------------------
+  // K1, item pass: item i = (obstacle j, stage k), i = j * (N+1) + k, so that consecutive threads work on consecutive
+  // stages (contiguous slices of every stacked array).  Evaluates the block (block_eval), hands the 12 doubles the stage
+  // assembly needs over in the stage's own slot (offset HO_N * j; the stage pass reads them before it zeroes its Q / q
+  // area) and merges the block's KKT-error / merit partials into the thread's running EvalPart.
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD_NI static void block_item_eval(const PkCtx& C, int i, bool do_err, EvalPart& acc) {
+    const ParkProblem& P = CTX_P(C);
+    const ProbState& S = *C.S;
+    const int NS = P.N + 1;
+    const int j = i / NS, k = i - j * NS;
+    const double mu_b = S.mu;
+    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+    BlockOut B;
+    block_eval(C, k, j, X, Y, cs_, sn_, mu_b, S.dw, do_err, true, B);
+    double* const h = &RIC(HO_N * j, k);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) o[i * st] = B.Sxx[i];
+    for (int e = 0; e < 6; ++e) h[e] = B.Sxx[e];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { o[(6 + i) * st] = B.rx3[i]; o[(9 + i) * st] = B.gx[i]; }
-    o[12 * st] = B.e_dual; o[13 * st] = B.e_pr; o[14 * st] = B.cmax; o[15 * st] = B.cmin; o[16 * st] = B.sum_y;
-    o[17 * st] = B.sum_z; o[18 * st] = B.th; o[19 * st] = B.lsum; o[20 * st] = B.fobj; o[21 * st] = (double)B.ok;
-  }
-  OBCA_HD static void block_load(const PkCtx& C, int k, int j, bool do_err, bool do_asm, BlockOut& B) {
-    const double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
-    const size_t st = CTX_L(C).NSP;
-    if (do_asm) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) B.Sxx[i] = o[i * st];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) B.rx3[i] = o[(6 + i) * st];
-      B.ok = o[21 * st] != 0.0;
-    }
+    for (int e = 0; e < 3; ++e) { h[6 + e] = B.rx3[e]; h[9 + e] = B.gx[e]; }
+    acc.ok &= B.ok;
+    acc.f += B.fobj;
     if (do_err) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) B.gx[i] = o[(9 + i) * st];
-      B.e_dual = o[12 * st]; B.e_pr = o[13 * st]; B.cmax = o[14 * st]; B.cmin = o[15 * st]; B.sum_y = o[16 * st];
-      B.sum_z = o[17 * st]; B.th = o[18 * st]; B.lsum = o[19 * st];
+      acc.e_dual = dmax(acc.e_dual, B.e_dual); acc.e_pr = dmax(acc.e_pr, B.e_pr);
+      acc.cmax = dmax(acc.cmax, B.cmax); acc.cmin = dmin_(acc.cmin, B.cmin);
+      acc.sy += B.sum_y; acc.sz += B.sum_z; acc.th += B.th;
+      acc.phi += B.fobj - mu_b * B.lsum;
     }
-    B.fobj = o[20 * st];
   }
 
   // ---------------------------------------------------------------------------------------------------
   // P1 (K1): fused evaluation at the current iterate.
   //   do_err: KKT-error / merit partials into RED;   do_asm: stage model Q, q, dynamics, local factors.
   // ---------------------------------------------------------------------------------------------------
+  // stage pass of an evaluation: everything of stage k that is not an obstacle block (state objective and bounds, controls,
+  // input-rate terms, steering-rate row, dynamics with second derivatives, time scale) + the sums of the block hand-overs
   OBCA_HD_NI static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
-    stage_eval_t<false>(C, k, do_err, do_asm, out);
-  }
-  OBCA_HD_NI static void stage_eval_blk(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
-    stage_eval_t<true>(C, k, do_err, do_asm, out);
-  }
-  // BLK: the obstacle blocks were evaluated by the flat block kernel and are read from the hand-over array C.bo
-  template <bool BLK>
-  OBCA_HD static void stage_eval_t(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -488,9 +493,15 @@ struct ParkSolver {
     const bool has_u = k < N;
     const double t = fix ? 1.0 : S.t;
     const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k), v = WA(VL, k);
-    double sn_, cs_;
-    sincos(ps, &sn_, &cs_);
 
+    // hand-overs of the item pass (sum over the obstacles in index order), read before the slot is reused for Q / q
+    double hs[HO_N];
+#pragma unroll
+    for (int e = 0; e < HO_N; ++e) hs[e] = 0.0;
+    for (int j = 0; j < P.nOb; ++j) {
+#pragma unroll
+      for (int e = 0; e < HO_N; ++e) hs[e] += RIC(HO_N * j + e, k);
+    }
     // the stage model (packed 9x9 Q, q) is accumulated directly in the stage slot (shared memory on the device)
 #pragma unroll
     for (int i = 0; i < NQ + NYV; ++i) RIC(RQ + i, k) = 0.0;
@@ -498,33 +509,13 @@ struct ParkSolver {
     double rz_t = 0.0;
     int ok = 1;
     LogAcc lacc;   // barrier terms: phi -= mu * sum(log gap)
-    double lsum_blocks = 0.0;
-    // Lagrangian gradient rows of the pose
-    double rzX = 0.0, rzY = 0.0, rzP = 0.0, rzV = 0.0;
 
-    // Order of the sections: obstacle blocks first, then the state terms, the controls / dynamics last -- the local
-    // elimination of a block needs ~60 doubles in registers, so nothing else big (dynamics Jacobian, residuals) may be
-    // live across it; the dynamics outputs go straight into the stage slot.
-    // ---- (C) obstacle blocks ----
-    for (int j = 0; j < P.nOb; ++j) {
-      BlockOut bo;
-      if (BLK) block_load(C, k, j, do_err, do_asm, bo);
-      else block_eval(C, k, j, X, Y, cs_, sn_, mu_b, dw, do_err, do_asm, bo);
-      if (do_err) {
-        rzX += bo.gx[0]; rzY += bo.gx[1]; rzP += bo.gx[2];
-        e_dual = dmax(e_dual, bo.e_dual); e_pr = dmax(e_pr, bo.e_pr);
-        cmax = dmax(cmax, bo.cmax); cmin = dmin_(cmin, bo.cmin);
-        sum_y += bo.sum_y; sum_z += bo.sum_z; th += bo.th; lsum_blocks += bo.lsum;
-      }
-      fobj += bo.fobj;
-      if (do_asm) {
-        ok &= bo.ok;
-        if (pose_free) {
-          RIC(RQ + sym_idx<NYV>(IX, IX), k) += bo.Sxx[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) += bo.Sxx[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) += bo.Sxx[2];
-          RIC(RQ + sym_idx<NYV>(IY, IY), k) += bo.Sxx[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) += bo.Sxx[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) += bo.Sxx[5];
-          RIC(Rq + IX, k) += bo.rx3[0]; RIC(Rq + IY, k) += bo.rx3[1]; RIC(Rq + IP, k) += bo.rx3[2];
-        }
-      }
+    // ---- (C) obstacle blocks: Schur complements / gradients on the pose, Lagrangian-gradient rows ----
+    double rzX = hs[9], rzY = hs[10], rzP = hs[11], rzV = 0.0;
+    if (do_asm && pose_free) {
+      RIC(RQ + sym_idx<NYV>(IX, IX), k) = hs[0]; RIC(RQ + sym_idx<NYV>(IX, IY), k) = hs[1]; RIC(RQ + sym_idx<NYV>(IX, IP), k) = hs[2];
+      RIC(RQ + sym_idx<NYV>(IY, IY), k) = hs[3]; RIC(RQ + sym_idx<NYV>(IY, IP), k) = hs[4]; RIC(RQ + sym_idx<NYV>(IP, IP), k) = hs[5];
+      RIC(Rq + IX, k) = hs[6]; RIC(Rq + IY, k) = hs[7]; RIC(Rq + IP, k) = hs[8];
     }
     // ---- (A) state objective + bounds ----
     {
@@ -677,7 +668,7 @@ struct ParkSolver {
         phi -= m * mu_b * (log(gl) + log(gu));
       }
     }
-    if (do_err) phi -= mu_b * (lacc.total() + lsum_blocks);
+    if (do_err) phi -= mu_b * lacc.total();
     if (do_err && pose_free) e_dual = dmax(e_dual, dmax(dmax(dabs(rzX), dabs(rzY)), dmax(dabs(rzP), dabs(rzV))));
     out.e_dual = e_dual; out.e_pr = e_pr; out.cmax = cmax; out.cmin = cmin; out.sy = sum_y; out.sz = sum_z;
     out.th = th; out.phi = phi + fobj; out.rt = rz_t; out.f = fobj; out.ok = ok;
@@ -774,144 +765,180 @@ struct ParkSolver {
     return ok;
   }
 
+  // a0 b0 + a1 b1 + a2 b2 + a3 b3 as two fused chains
+  OBCA_HD static double dot4(double a0, double b0, double a1, double b1, double a2, double b2, double a3, double b3) {
+    return fma(a1, b1, a0 * b0) + fma(a3, b3, a2 * b2);
+  }
+  // forward roll-out of the step: control row `kr` of the gain, state row `dr` of the dynamics Jacobian
+  OBCA_HD static double roll_u(double kf, const double* kr, double s0, double s1, double s2, double s3, double s4, double s5,
+                               double dt) {
+    return (fma(kr[1], s1, kr[0] * s0) + fma(kr[3], s3, kr[2] * s2)) + (fma(kr[5], s5, kr[4] * s4) + fma(kr[6], dt, kf));
+  }
+  OBCA_HD static double roll_x(double r, double selx, double sely, const double* dr, double s0, double s1, double s2, double s3,
+                               double dt, double u0, double u1) {
+    return (fma(sely, s1, selx * s0) + fma(dr[1], s3, dr[0] * s2)) + (fma(dr[4], u1, dr[3] * u0) + fma(dr[2], dt, r));
+  }
   // -------------------------------------------------------------------------------------------------
-  // Warp-cooperative KKT sweep (the device path; the host emulation runs the same lane code for 32 lanes in turn).
-  // Nothing is replicated, no branches / selects / index arithmetic inside the stage loop (the loop is
-  // issue-latency bound: every instruction counts).
-  //   lane l (< 7) owns ROW l of the value function P (7 doubles) and p_l
-  //   step 1: lane l: row l of T = P Phi (9 values, Phi sparse), g_l = p_l + P(l,:) r~        -> shared tile
-  //   step 2: lane j (< 9): column j of H = Q + Phi' T and hv_j; the (de, a) columns          -> shared tile
-  //   step 3: 2x2 pivot on (de, a) with ONE reciprocal; lane j (< 7) ends with column j of the new P, which by
-  //           symmetry is the row it owns at the next stage.
-  // Lanes outside the active range park their (meaningless) results in the dump area of the tile.
-  // Tile (doubles): T 7x9 [0,63) | g [63,70) | 0 [70] | zero column [71,91) | H(:,de) [91,100) | H(:,a) [100,109) |
-  //                 hv_de, hv_a [109,111) | dump [112,144)
+  // Wide (full-warp) KKT sweep: the device path of the sweep kernel and of the persistent kernel.
+  // The stage recursion is a serial chain of 2 N steps per problem and nothing else of an iteration is, so its latency --
+  // not its operation count -- bounds the solve time of the slowest problems of a batch.  Each of the three matrix steps
+  // of a stage is cut into scalar TASKS (one entry of T, H or P each: a 4-term inner product or a rank-2 update), at most
+  // two per lane, described by offsets that a lane computes once per sweep; the steps exchange through a 2 KB tile:
+  //   step 1 (42 tasks): T = P Phi (the 5 dense columns) and g = p + P r~                         reads P, slot   writes T
+  //   step 2 (54 tasks): H = Q + Phi' T (45 entries, both triangles stored), hv = q + Phi' g      reads T, slot   writes H
+  //   step 3 (35 tasks): 2x2 pivot on (de, a) (every lane: one reciprocal), gain column, new P entry / p entry
+  //                                                                                               reads H         writes P, T(:, X|Y)
+  // Tile (doubles): P 7x7 full [0,49) | p [49,56) | T 7x10 (columns of the stage vector + g) [56,126) |
+  //                 H 9x10 (column 9 = hv) [126,216) | zeros [216,224) | dump [224,240)
+  // Gains go to the stage's slot (RK..), rows 0..3 of P_k / p_k too (RPP.., Rpp..: consumed Q/q space) for recover_stage.
   // -------------------------------------------------------------------------------------------------
-  static constexpr int TILE_DOUBLES = 144;
-  struct KktLane {
-    double Prow[NSV], pl;   // row of P / entry of p owned by the lane
-    double H[NYV], hv;      // column of H owned by the lane
-    int qoff[NYV];          // slot offsets of Q(i, j), i = 0..8
-    int dcol;               // offset of the lane's dynamics-Jacobian column in the slot, or -1
-    int gext;               // tile index of the identity entry of Phi' g for this column
-    int tr, gs, hcol, hvst; // tile offsets where the lane writes
+  static constexpr int WP = 0, Wp = 49, WT = 56, WH = 126, WZ = 216, WDUMP = 224, WIDE_TILE = 240;
+  struct WideLane {
+    int s1_p[2], s1_j[2], s1_js[2], s1_x[2], s1_o[2];
+    int s2_q[2], s2_j[2], s2_js[2], s2_t[2], s2_x[2], s2_o1[2], s2_o2[2];
+    int s3_h[2], s3_hid[2], s3_hia[2], s3_hdj[2], s3_haj[2], s3_o1[2], s3_o2[2], s3_t1[2], s3_t2[2], s3_g1[2], s3_g2[2], s3_k[2], s3_ks[2];
     int ok;
   };
-  OBCA_HD static void kl_init(KktLane& L, int lane, double* tile, const PkCtx& C) {
-    const int N = CTX_P(C).N;
-    const int j = lane < NYV ? lane : NYV - 1;
-#pragma unroll
-    for (int i = 0; i < NYV; ++i) L.qoff[i] = RQ + (i <= j ? sym_idx<NYV>(i, j) : sym_idx<NYV>(j, i));
-    L.dcol = (j == IP) ? RDYN + 0 : (j == IV) ? RDYN + 1 : (j == IT) ? RDYN + 2 : (j == IDE) ? RDYN + 3 : (j == IAC) ? RDYN + 4 : -1;
-    L.gext = (j == IX) ? 63 + 0 : (j == IY) ? 63 + 1 : (j == IT) ? 63 + 6 : (j == IDE) ? 63 + 4 : (j == IAC) ? 63 + 5 : 70;
-    L.tr = (lane < NSV) ? lane * NYV : 112;
-    L.gs = (lane < NSV) ? 63 + lane : 124;
-    L.hcol = (lane == IDE) ? 91 : (lane == IAC) ? 100 : 112;
-    L.hvst = (lane == IDE) ? 109 : (lane == IAC) ? 110 : 124;
-    if (lane < 21) tile[70 + lane] = 0.0;
-#pragma unroll
-    for (int b = 0; b < NSV; ++b) L.Prow[b] = 0.0;
-    L.pl = 0.0;
-    if (lane < 4) {                      // terminal value: rho |x_N - xF|^2 with multiplier estimate pi_{N-1}
-      L.Prow[lane] = 1.0 / CTX_O(C).dc;
-      L.pl = -WV(PI, lane, N - 1);
+  OBCA_HD static constexpr int col5(int c) { return c == 0 ? IP : c == 1 ? IV : c == 2 ? IT : c == 3 ? IDE : IAC; }
+  OBCA_HD static constexpr int idx5(int y) { return y == IP ? 0 : y == IV ? 1 : y == IT ? 2 : y == IDE ? 3 : y == IAC ? 4 : -1; }
+  // packed pair index -> (i, j), i <= j < n
+  OBCA_HD static void unpack_pair(int t, int n, int& i, int& j) {
+    i = 0;
+    while (t >= n - i) { t -= n - i; ++i; }
+    j = i + t;
+  }
+  OBCA_HD static void wl_init(WideLane& L, int lane) {
+    for (int u = 0; u < 2; ++u) {
+      const int t = lane + 32 * u;
+      // ---- step 1: task t = 6 a + c6 ----
+      if (t < 42) {
+        const int a = t / 6, c6 = t - 6 * a;
+        L.s1_p[u] = WP + 7 * a;
+        L.s1_j[u] = c6 < 5 ? RDYN + c6 : RR4;
+        L.s1_js[u] = c6 < 5 ? 5 : 1;
+        L.s1_x[u] = c6 == 2 ? WP + 7 * a + 6 : c6 == 3 ? WP + 7 * a + 4 : c6 == 4 ? WP + 7 * a + 5 : c6 == 5 ? Wp + a : WZ;
+        L.s1_o[u] = WT + 10 * a + (c6 < 5 ? col5(c6) : 9);
+      } else {
+        L.s1_p[u] = WP; L.s1_j[u] = RDYN; L.s1_js[u] = 5; L.s1_x[u] = WZ; L.s1_o[u] = WDUMP + u;
+      }
+      // ---- step 2: t < 45: H(i, j), i <= j;  45 <= t < 54: hv(i) ----
+      if (t < 54) {
+        int i, j;
+        if (t < 45) unpack_pair(t, NYV, i, j); else { i = t - 45; j = 9; }
+        // representation with the row index in the dense set {psi, v, t, de, a} when there is one
+        int r = i, c = j;
+        if (idx5(i) < 0 && j < 9 && idx5(j) >= 0) { r = j; c = i; }
+        const int r5 = idx5(r);
+        L.s2_q[u] = j < 9 ? RQ + sym_idx<NYV>(i, j) : Rq + i;
+        L.s2_j[u] = r5 >= 0 ? RDYN + r5 : -1;
+        L.s2_js[u] = r5 >= 0 ? 5 : 1;
+        L.s2_t[u] = WT + c;
+        L.s2_x[u] = r == IT ? WT + 60 + c : r == IDE ? WT + 40 + c : r == IAC ? WT + 50 + c : r == IX ? WT + c : r == IY ? WT + 10 + c : WZ;
+        L.s2_o1[u] = WH + 10 * i + j;
+        L.s2_o2[u] = (j < 9 && i != j) ? WH + 10 * j + i : WDUMP + 2 + u;
+      } else {
+        L.s2_q[u] = RQ; L.s2_j[u] = -1; L.s2_js[u] = 1; L.s2_t[u] = WT; L.s2_x[u] = WZ; L.s2_o1[u] = WDUMP + 4 + u; L.s2_o2[u] = WDUMP + 6 + u;
+      }
+      // ---- step 3: t < 28: P(i, j), i <= j < 7;  28 <= t < 35: p(i) ----
+      if (t < 35) {
+        int i, j;
+        if (t < 28) unpack_pair(t, NSV, i, j); else { i = t - 28; j = 9; }
+        L.s3_h[u] = WH + 10 * i + j; L.s3_hid[u] = WH + 10 * i + IDE; L.s3_hia[u] = WH + 10 * i + IAC;
+        L.s3_hdj[u] = WH + 10 * IDE + j; L.s3_haj[u] = WH + 10 * IAC + j;
+        if (j < 7) {
+          L.s3_o1[u] = WP + 7 * i + j; L.s3_o2[u] = WP + 7 * j + i;
+          L.s3_t1[u] = j < 2 ? WT + 10 * i + j : WDUMP + 8 + u;              // T(:, X | Y) = P(:, 0 | 1)
+          L.s3_t2[u] = (i < 2 && i != j) ? WT + 10 * j + i : WDUMP + 10 + u;
+          L.s3_g1[u] = i < 4 ? RPP + NSV * i + j : -1;
+          L.s3_g2[u] = (j < 4 && i != j) ? RPP + NSV * j + i : -1;
+          L.s3_k[u] = i == 0 ? RK + j : -1; L.s3_ks[u] = NSV;
+        } else {
+          L.s3_o1[u] = Wp + i; L.s3_o2[u] = WDUMP + 12 + u; L.s3_t1[u] = WDUMP + 8 + u; L.s3_t2[u] = WDUMP + 10 + u;
+          L.s3_g1[u] = i < 4 ? Rpp + i : -1; L.s3_g2[u] = -1;
+          L.s3_k[u] = i == 0 ? RK + 14 : -1; L.s3_ks[u] = 1;
+        }
+      } else {
+        L.s3_h[u] = WZ; L.s3_hid[u] = WZ; L.s3_hia[u] = WZ; L.s3_hdj[u] = WZ; L.s3_haj[u] = WZ;
+        L.s3_o1[u] = WDUMP + 12 + u; L.s3_o2[u] = WDUMP + 12 + u; L.s3_t1[u] = WDUMP + 8 + u; L.s3_t2[u] = WDUMP + 10 + u;
+        L.s3_g1[u] = -1; L.s3_g2[u] = -1; L.s3_k[u] = -1; L.s3_ks[u] = 1;
+      }
     }
     L.ok = 1;
   }
-  // `slot`: stage model of stage k (read);  `next`: slot k+1, where P_{k+1} rows are parked for the multiplier recovery
-  OBCA_HD static void kl_step1(KktLane& L, int lane, const double* slot, double* tile, double* next) {
-    {  // rows 0..3 of P_{k+1} / p_{k+1} -> slot k+1 (consumed Q/q space) for the multiplier recovery
-      double* const prs = (lane < 4) ? (next + RPP + lane * NSV) : (tile + 125);
-      double* const pps = (lane < 4) ? (next + Rpp + lane) : (tile + 132);
-#pragma unroll
-      for (int b = 0; b < NSV; ++b) prs[b] = L.Prow[b];
-      *pps = L.pl;
-    }
-    double tp = 0.0, tv = 0.0, tt = L.Prow[6], td = L.Prow[4], ta = L.Prow[5], gl = L.pl;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const double pm = L.Prow[m];
-      tp += pm * slot[RDYN + 5 * m + 0]; tv += pm * slot[RDYN + 5 * m + 1]; tt += pm * slot[RDYN + 5 * m + 2];
-      td += pm * slot[RDYN + 5 * m + 3]; ta += pm * slot[RDYN + 5 * m + 4];
-      gl += pm * slot[RR4 + m];
-    }
-    double* const tr = tile + L.tr;
-    tr[IX] = L.Prow[0]; tr[IY] = L.Prow[1]; tr[IP] = tp; tr[IV] = tv; tr[IWD] = 0.0; tr[IWA] = 0.0;
-    tr[IT] = tt; tr[IDE] = td; tr[IAC] = ta;
-    tile[L.gs] = gl;
+  // terminal value (regularised end-point rows x_N == xF, multiplier estimate pi_{N-1}) into the tile; its rows 0..3 into
+  // slot N.  Two lane passes (zero, then set) with a warp barrier in between.
+  OBCA_HD static void wl_zero(int lane, double* tile, double* slotN) {
+    for (int e = lane; e < WIDE_TILE; e += 32) tile[e] = 0.0;
+    if (lane < 28) slotN[RPP + lane] = 0.0;
   }
-  OBCA_HD static void kl_step2(KktLane& L, int lane, const double* slot, double* tile) {
-    const int j = lane < NYV ? lane : NYV - 1;
-    double T[NSV];
-#pragma unroll
-    for (int a = 0; a < NSV; ++a) T[a] = tile[a * NYV + j];
-    double hp = slot[L.qoff[IP]], hvv = slot[L.qoff[IV]], ht = slot[L.qoff[IT]] + T[6], hd = slot[L.qoff[IDE]] + T[4],
-           ha = slot[L.qoff[IAC]] + T[5];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const double tm = T[m];
-      hp += slot[RDYN + 5 * m + 0] * tm; hvv += slot[RDYN + 5 * m + 1] * tm; ht += slot[RDYN + 5 * m + 2] * tm;
-      hd += slot[RDYN + 5 * m + 3] * tm; ha += slot[RDYN + 5 * m + 4] * tm;
+  OBCA_HD static void wl_terminal(int lane, double* tile, double* slotN, const PkCtx& C) {
+    const int N = CTX_P(C).N;
+    if (lane < 4) {
+      const double rho = 1.0 / CTX_O(C).dc, pl = -WV(PI, lane, N - 1);
+      tile[WP + 8 * lane] = rho; tile[Wp + lane] = pl;
+      if (lane < 2) tile[WT + 10 * lane + lane] = rho;
+      slotN[RPP + NSV * lane + lane] = rho; slotN[Rpp + lane] = pl;
     }
-    L.H[IX] = slot[L.qoff[IX]] + T[0]; L.H[IY] = slot[L.qoff[IY]] + T[1]; L.H[IP] = hp; L.H[IV] = hvv;
-    L.H[IWD] = slot[L.qoff[IWD]]; L.H[IWA] = slot[L.qoff[IWA]]; L.H[IT] = ht; L.H[IDE] = hd; L.H[IAC] = ha;
-    const double* const dc_ = (L.dcol >= 0) ? (slot + L.dcol) : (tile + 71);
-    L.hv = slot[Rq + j] + tile[L.gext] + dc_[0] * tile[63] + dc_[5] * tile[64] + dc_[10] * tile[65] + dc_[15] * tile[66];
-    double* const hc = tile + L.hcol;
-#pragma unroll
-    for (int i = 0; i < NYV; ++i) hc[i] = L.H[i];
-    tile[L.hvst] = L.hv;
   }
-  // `kout`: slot that receives the gains of stage k (the stage's own slot; a different address space in the sweep kernel)
-  OBCA_HD static void kl_step3(KktLane& L, int lane, double* kout, double* tile) {
-    const double h77 = tile[91 + IDE], h78 = tile[91 + IAC], h88 = tile[100 + IAC];
-    double det = h77 * h88 - h78 * h78;
+  OBCA_HD static void wl_step1(const WideLane& L, const double* slot, double* tile) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const double* const pr = tile + L.s1_p[u];
+      const double* const jc = slot + L.s1_j[u];
+      const int js = L.s1_js[u];
+      const double acc = dot4(pr[0], jc[0], pr[1], jc[js], pr[2], jc[2 * js], pr[3], jc[3 * js]);
+      tile[L.s1_o[u]] = tile[L.s1_x[u]] + acc;
+    }
+  }
+  OBCA_HD static void wl_step2(const WideLane& L, const double* slot, double* tile) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const double* const jc = L.s2_j[u] >= 0 ? slot + L.s2_j[u] : tile + WZ;
+      const double* const tc = tile + L.s2_t[u];
+      const int js = L.s2_js[u];
+      const double acc = dot4(jc[0], tc[0], jc[js], tc[10], jc[2 * js], tc[20], jc[3 * js], tc[30]);
+      const double v = (slot[L.s2_q[u]] + tile[L.s2_x[u]]) + acc;
+      tile[L.s2_o1[u]] = v; tile[L.s2_o2[u]] = v;
+    }
+  }
+  // `out`: the stage's slot (gains, rows 0..3 of P_k / p_k)
+  OBCA_HD static void wl_step3(WideLane& L, double* out, double* tile) {
+    const double h77 = tile[WH + 10 * IDE + IDE], h78 = tile[WH + 10 * IDE + IAC], h88 = tile[WH + 10 * IAC + IAC];
+    double det = fma(h77, h88, -(h78 * h78));
     if (!(h77 > 0.0) || !(det > 0.0)) { L.ok = 0; det = 1e300; }
     const double idet = rcp(det);
     const double n00 = h88 * idet, n01 = -h78 * idet, n11 = h77 * idet;
-    const double K0 = -(n00 * L.H[IDE] + n01 * L.H[IAC]), K1 = -(n01 * L.H[IDE] + n11 * L.H[IAC]);   // column j of the gain
-    const double hv7 = tile[109], hv8 = tile[110];
-    const double kf0 = -(n00 * hv7 + n01 * hv8), kf1 = -(n01 * hv7 + n11 * hv8);
 #pragma unroll
-    for (int i = 0; i < NSV; ++i) L.Prow[i] = L.H[i] + tile[91 + i] * K0 + tile[100 + i] * K1;   // new P(:, j) == row j
-    L.pl = L.hv + L.H[IDE] * kf0 + L.H[IAC] * kf1;
-    double* const ks = (lane < NSV) ? (kout + RK + lane) : (tile + 133);
-    ks[0] = K0; ks[NSV] = K1;
-    if (lane == 0) { kout[RK + 14] = kf0; kout[RK + 15] = kf1; }
+    for (int u = 0; u < 2; ++u) {
+      const double hdj = tile[L.s3_hdj[u]], haj = tile[L.s3_haj[u]];
+      const double K0 = -fma(n00, hdj, n01 * haj), K1 = -fma(n01, hdj, n11 * haj);
+      const double v = fma(tile[L.s3_hia[u]], K1, fma(tile[L.s3_hid[u]], K0, tile[L.s3_h[u]]));
+      double* const g1 = L.s3_g1[u] >= 0 ? out + L.s3_g1[u] : tile + WDUMP + 14;
+      double* const g2 = L.s3_g2[u] >= 0 ? out + L.s3_g2[u] : tile + WDUMP + 14;
+      double* const kp = L.s3_k[u] >= 0 ? out + L.s3_k[u] : tile + WDUMP + 14;
+      const int ks = L.s3_k[u] >= 0 ? L.s3_ks[u] : 1;
+      *g1 = v; *g2 = v;
+      kp[0] = K0; kp[ks] = K1;
+      tile[L.s3_o1[u]] = v; tile[L.s3_o2[u]] = v; tile[L.s3_t1[u]] = v; tile[L.s3_t2[u]] = v;
+    }
   }
 
 #if defined(__CUDA_ARCH__)
-  __device__ static int kkt_solve_warp(const PkCtx& C, double* tile) {
+  // root (x_0, w_0 fixed; dt free) + forward roll-out of the primal step, lane-parallel: lanes 0,1 -> controls, lanes 0..3 ->
+  // next state rows.  SRC(k): pointer to the slot of stage k (gains, dynamics Jacobian, residual).
+  template <class SlotOf>
+  __device__ static __forceinline__ int kkt_forward_warp(const PkCtx& C, const double* tile, ProbState* Sout, bool write, SlotOf slot_of) {
     const ParkProblem& Pp = CTX_P(C);
     const int N = Pp.N;
     const int lane = threadIdx.x & 31;
-    KktLane L;
-    kl_init(L, lane, tile, C);
-    __syncwarp();
-    for (int k = N - 1; k >= 0; --k) {
-      double* const slot = C.ric + k * RSTRIDE;
-      kl_step1(L, lane, slot, tile, slot + RSTRIDE);
-      __syncwarp();
-      kl_step2(L, lane, slot, tile);
-      __syncwarp();
-      kl_step3(L, lane, slot, tile);
-      __syncwarp();
-      if (!L.ok) break;      // wrong inertia: the sweep result is discarded anyway (all lanes see the same pivot)
-    }
-    int ok = L.ok;
-    if (!ok) return 0;
-    // ---- root (x_0, w_0 fixed; dt free) ----
-    if (lane == IT) { tile[63] = L.Prow[IT]; tile[64] = L.pl; }           // P(t, t), p_t
-    __syncwarp();
-    ProbState& S = *C.S;
+    int ok = 1;
     double dt = 0.0;
     if (!Pp.fix_time) {
-      double ptt = tile[63];
+      double ptt = tile[WP + 7 * IT + IT];
       if (!(ptt > 0.0)) { ok = 0; ptt = 1e300; }
-      dt = -tile[64] / ptt;
+      dt = -tile[Wp + IT] / ptt;
     }
-    if (lane == 0) S.dt = dt;
-    // ---- forward roll-out, lane-parallel: lanes 0,1 -> controls, lanes 0..3 -> next state rows ----
+    if (lane == 0 && write) Sout->dt = dt;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
     const int ur = lane & 1, xr = lane & 3;
     const unsigned FULL = 0xffffffffu;
@@ -919,41 +946,67 @@ struct ParkSolver {
     double* const dxw = C.W + (size_t)(CTX_L(C).dX + xr) * CTX_L(C).NSP;      // dX, dY, dPS, dVL are consecutive arrays
     double* const duw = C.W + (size_t)(CTX_L(C).dDE + ur) * CTX_L(C).NSP;     // dDE, dAC are consecutive arrays
     for (int k = 0; k < N; ++k) {
-      const double* const slot = C.ric + k * RSTRIDE;
+      const double* const slot = slot_of(k);
       const double* const kr = slot + RK + ur * NSV;
-      double u = slot[RK + 14 + ur] + kr[0] * s0 + kr[1] * s1 + kr[2] * s2 + kr[3] * s3 + kr[4] * s4 + kr[5] * s5 + kr[6] * dt;
+      const double u = roll_u(slot[RK + 14 + ur], kr, s0, s1, s2, s3, s4, s5, dt);
       const double u0 = __shfl_sync(FULL, u, 0), u1 = __shfl_sync(FULL, u, 1);
       const double* const dr = slot + RDYN + 5 * xr;
-      double sn = slot[RR4 + xr] + selx * s0 + sely * s1 + dr[0] * s2 + dr[1] * s3 + dr[2] * dt + dr[3] * u0 + dr[4] * u1;
-      if (lane < 2) duw[k] = u;
+      const double sn = roll_x(slot[RR4 + xr], selx, sely, dr, s0, s1, s2, s3, dt, u0, u1);
+      if (lane < 2 && write) duw[k] = u;
       s0 = __shfl_sync(FULL, sn, 0); s1 = __shfl_sync(FULL, sn, 1); s2 = __shfl_sync(FULL, sn, 2); s3 = __shfl_sync(FULL, sn, 3);
       s4 = u0; s5 = u1;
-      if (lane < 4) {
+      if (lane < 4 && write) {
         if (k + 1 < N) dxw[k + 1] = sn;
-        else S.eN[xr] = sn;
+        else Sout->eN[xr] = sn;
       }
     }
-    if (lane < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
-    if (lane < 2) duw[N] = 0.0;
+    if (write) {
+      if (lane < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
+      if (lane < 2) duw[N] = 0.0;
+    }
     return ok;
+  }
+  // the whole sweep with the stage slots in shared memory (persistent kernel): one warp
+  __device__ static int kkt_solve_warp(const PkCtx& C, double* tile) {
+    const int N = CTX_P(C).N;
+    const int lane = threadIdx.x & 31;
+    WideLane L;
+    wl_init(L, lane);
+    wl_zero(lane, tile, C.ric + N * RSTRIDE);
+    __syncwarp();
+    wl_terminal(lane, tile, C.ric + N * RSTRIDE, C);
+    __syncwarp();
+    for (int k = N - 1; k >= 0; --k) {
+      double* const slot = C.ric + k * RSTRIDE;
+      wl_step1(L, slot, tile);
+      __syncwarp();
+      wl_step2(L, slot, tile);
+      __syncwarp();
+      wl_step3(L, slot, tile);
+      __syncwarp();
+      if (!L.ok) return 0;      // wrong inertia: the sweep result is discarded anyway (all lanes see the same pivot)
+    }
+    double* const ric = C.ric;
+    return kkt_forward_warp(C, tile, C.S, true, [ric](int k) { return (const double*)(ric + k * RSTRIDE); });
   }
 #else
   // host emulation of the warp: the 32 lanes run each step one after the other (a step only reads what earlier
   // steps wrote, exactly what __syncwarp() guarantees on the device)
   static int kkt_solve_warp_emul(const PkCtx& C, double* tile) {
     const int N = CTX_P(C).N;
-    KktLane L[32];
-    for (int l = 0; l < 32; ++l) kl_init(L[l], l, tile, C);
+    WideLane L[32];
+    double* const slotN = C.ric + N * RSTRIDE;
+    for (int l = 0; l < 32; ++l) wl_init(L[l], l);
+    for (int l = 0; l < 32; ++l) wl_zero(l, tile, slotN);
+    for (int l = 0; l < 32; ++l) wl_terminal(l, tile, slotN, C);
     for (int k = N - 1; k >= 0; --k) {
       double* const slot = C.ric + k * RSTRIDE;
-      for (int l = 0; l < 32; ++l) kl_step1(L[l], l, slot, tile, slot + RSTRIDE);
-      for (int l = 0; l < 32; ++l) kl_step2(L[l], l, slot, tile);
-      for (int l = 0; l < 32; ++l) kl_step3(L[l], l, slot, tile);
+      for (int l = 0; l < 32; ++l) wl_step1(L[l], slot, tile);
+      for (int l = 0; l < 32; ++l) wl_step2(L[l], slot, tile);
+      for (int l = 0; l < 32; ++l) wl_step3(L[l], slot, tile);
       if (!L[0].ok) return 0;
     }
-    int ok = 1;
-    for (int l = 0; l < 32; ++l) ok &= L[l].ok;
-    return ok & kkt_root_forward(C, L[IT].Prow[IT], L[IT].pl);
+    return kkt_root_forward(C, tile[WP + 7 * IT + IT], tile[Wp + IT]);
   }
 #endif
 
@@ -1010,7 +1063,7 @@ struct ParkSolver {
 #pragma unroll
       for (int i = 0; i < VM; ++i) {
         if (i < R.v) {
-          WV(dLAM, P.voff[j] + i, k) = St.dlam[i];
+          WDV(dLAM, P.voff[j] + i, k) = St.dlam[i];
           ftb(Qv.lam[i], St.dlam[i], tau, apr);
           ftb(Qv.zlam[i], dzb(Qv.zlam[i], Qv.lam[i], St.dlam[i], mu_b), tau, adu);
           dphi += -mu_b * rcp(Qv.lam[i]) * St.dlam[i];
@@ -1018,17 +1071,17 @@ struct ParkSolver {
       }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        WV(dMU, 4 * j + m, k) = St.dmu[m];
+        WDV(dMU, 4 * j + m, k) = St.dmu[m];
         ftb(Qv.mu[m], St.dmu[m], tau, apr);
         ftb(Qv.zmu[m], dzb(Qv.zmu[m], Qv.mu[m], St.dmu[m], mu_b), tau, adu);
         dphi += -mu_b * rcp(Qv.mu[m]) * St.dmu[m];
       }
       if (SDV) {
-        WV(dSL, j, k) = St.dsl; WV(YNn, j, k) = St.yn_new;
+        WDV(dSL, j, k) = St.dsl; WDV(YNn, j, k) = St.yn_new;
         dphi += (1e2 + 2e4 * Qv.sl) * St.dsl;
       }
-      WV(YRn, 2 * j, k) = St.yr1_new; WV(YRn, 2 * j + 1, k) = St.yr2_new;
-      WV(dSD, j, k) = St.dsd;
+      WDV(YRn, 2 * j, k) = St.yr1_new; WDV(YRn, 2 * j + 1, k) = St.yr2_new;
+      WDV(dSD, j, k) = St.dsd;
       {
         const double gap = Qv.sd - P.dmin;
         ftb(gap, St.dsd, tau, apr);
@@ -1036,7 +1089,7 @@ struct ParkSolver {
         dphi += -mu_b * rcp(gap) * St.dsd;
       }
       if (!SDV) {
-        WV(dSN, j, k) = St.dsn;
+        WDV(dSN, j, k) = St.dsn;
         const double gap = 1.0 - Qv.sn;
         ftb(gap, -St.dsn, tau, apr);
         ftb(Qv.vn, dzb(Qv.vn, gap, -St.dsn, mu_b), tau, adu);
@@ -1045,22 +1098,27 @@ struct ParkSolver {
     }
     rbo.apr_g = apr.g; rbo.apr_d = apr.d; rbo.adu_g = adu.g; rbo.adu_d = adu.d; rbo.dphi = dphi;
   }
-  OBCA_HD static void rblock_store(const PkCtx& C, int k, int j, const RBlockOut& r) {
-    double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
-    const size_t st = CTX_L(C).NSP;
-    o[0] = r.apr_g; o[st] = r.apr_d; o[2 * st] = r.adu_g; o[3 * st] = r.adu_d; o[4 * st] = r.dphi;
-  }
-  OBCA_HD static void rblock_load(const PkCtx& C, int k, int j, RBlockOut& r) {
-    const double* o = C.bo + ((size_t)j * BO_N) * CTX_L(C).NSP + k;
-    const size_t st = CTX_L(C).NSP;
-    r.apr_g = o[0]; r.apr_d = o[st]; r.adu_g = o[2 * st]; r.adu_d = o[3 * st]; r.dphi = o[4 * st];
+  // K4a, item pass: step of the unknowns of block i = (obstacle j, stage k); its tightest fractions to the boundary and its
+  // part of the barrier directional derivative go straight into the thread's running StepPart (min / min / sum)
+  OBCA_HD_NI static void block_item_recover(const PkCtx& C, int i, StepPart& acc) {
+    const ParkProblem& P = CTX_P(C);
+    const ProbState& S = *C.S;
+    const int NS = P.N + 1;
+    const int j = i / NS, k = i - j * NS;
+    const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k);
+    const double dX = WA(dX, k), dY = WA(dY, k), dP = WA(dPS, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+    RBlockOut rb;
+    block_recover(C, k, j, X, Y, cs_, sn_, dX, dY, dP, S.mu, S.dw, rb);
+    Ftb apr, adu;
+    apr.g = rb.apr_g; apr.d = rb.apr_d; adu.g = rb.adu_g; adu.d = rb.adu_d;
+    acc.apr = dmin_(acc.apr, apr.alpha(S.tau)); acc.adu = dmin_(acc.adu, adu.alpha(S.tau));
+    acc.dphi += rb.dphi;
   }
 
-  OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) { recover_stage_t<false>(C, k, out); }
-  OBCA_HD_NI static void recover_stage_blk(const PkCtx& C, int k, StepPart& out) { recover_stage_t<true>(C, k, out); }
-  // BLK: the obstacle blocks were recovered by the flat kernel k_pk_rblock; their step-length / merit partials are read from C.bo
-  template <bool BLK>
-  OBCA_HD static void recover_stage_t(const PkCtx& C, int k, StepPart& out) {
+  // K4a, stage pass (everything of stage k that is not an obstacle block)
+  OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) {
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1070,8 +1128,6 @@ struct ParkSolver {
     const double t = fix ? 1.0 : S.t;
     const double X = WA(X, k), Y = WA(Y, k), ps = WA(PS, k), v = WA(VL, k);
     const double dX = WA(dX, k), dY = WA(dY, k), dP = WA(dPS, k), dV = WA(dVL, k);
-    double sn_, cs_;
-    sincos(ps, &sn_, &cs_);
     Ftb apr, adu;
     double dphi = 0.0;
     if (k < N) {
@@ -1085,7 +1141,7 @@ struct ParkSolver {
         double acc = PPV(Rpp + i, k + 1);
 #pragma unroll
         for (int l = 0; l < NSV; ++l) acc += PPV(RPP + i * NSV + l, k + 1) * sn[l];
-        WV(PIn, i, k) = -acc;
+        WDV(PIn, i, k) = -acc;
       }
     }
     if (pose_free) {
@@ -1122,21 +1178,13 @@ struct ParkSolver {
       const double rs = WA(RS, k);
       const double gl = rs + 0.6, gu = 0.6 - rs;
       const double drs = (dwd - dD) * ih - (fix ? 0.0 : gr * it * S.dt) + (gr - rs);
-      WA(dRS, k) = drs;
+      WD(dRS, k) = drs;
       ftb(gl, drs, tau, apr); ftb(gu, -drs, tau, apr);
       z = WA(RVL, k); ftb(z, dzb(z, gl, drs, mu_b), tau, adu);
       z = WA(RVU, k); ftb(z, dzb(z, gu, -drs, mu_b), tau, adu);
       dphi += (0.02 * de + 0.2 * ed * ih2 - mu_b * rcp(aDl) + mu_b * rcp(aDu)) * dD + (2.0 * P.w_a * ac + 0.2 * ea * ih2 - mu_b * rcp(aAl) + mu_b * rcp(aAu)) * dA +
               (-0.2 * ed * ih2) * dwd + (-0.2 * ea * ih2) * dwa + (fix ? 0.0 : -2.0 * T * it * S.dt) +
               (-mu_b * rcp(gl) + mu_b * rcp(gu)) * drs;
-    }
-    for (int j = 0; j < P.nOb; ++j) {
-      RBlockOut rb;
-      if (BLK) rblock_load(C, k, j, rb);
-      else block_recover(C, k, j, X, Y, cs_, sn_, dX, dY, dP, mu_b, dw, rb);
-      ftb(rb.apr_g, -rb.apr_d, tau, apr);      // merge the block's tightest fractions (d = 0: no shrinking gap in the block)
-      ftb(rb.adu_g, -rb.adu_d, tau, adu);
-      dphi += rb.dphi;
     }
     if (k == 0 && !fix) {
       const double m = (double)(N + 1);
@@ -1152,6 +1200,50 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // K4b: merit-function partials at the trial point z + alpha dz  (theta = ||c||_1, phi = barrier objective)
   // ---------------------------------------------------------------------------------------------------
+  // item pass: block i = (obstacle j, stage k) at the trial point
+  OBCA_HD_NI static void block_item_merit(const PkCtx& C, int i, double alpha, MeritPart& acc) {
+    const ParkProblem& P = CTX_P(C);
+    const ProbState& S = *C.S;
+    const int NS = P.N + 1;
+    const int j = i / NS, k = i - j * NS;
+    const double mu_b = S.mu;
+    const double X = WA(X, k) + alpha * WA(dX, k), Y = WA(Y, k) + alpha * WA(dY, k);
+    const double ps = WA(PS, k) + alpha * WA(dPS, k);
+    double sn_, cs_;
+    sincos(ps, &sn_, &cs_);
+    double th = 0.0, phi = 0.0;
+    bool bad = false;
+    LogAcc lacc;
+    ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
+    load_rows(C, j, R);
+#pragma unroll
+    for (int r = 0; r < VM; ++r) {
+      const bool on = r < R.v;
+      Qv.lam[r] = on ? WV(LAM, P.voff[j] + r, k) + alpha * WDV(dLAM, P.voff[j] + r, k) : 1.0;
+      Qv.zlam[r] = 0.0;
+      if (on) { bad |= !(Qv.lam[r] > 0.0); lacc.add(Qv.lam[r]); }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      Qv.mu[m] = WV(MU, 4 * j + m, k) + alpha * WDV(dMU, 4 * j + m, k);
+      Qv.zmu[m] = 0.0;
+      bad |= !(Qv.mu[m] > 0.0); lacc.add(Qv.mu[m]);
+    }
+    Qv.sl = SDV ? WV(SL, j, k) + alpha * WDV(dSL, j, k) : 0.0;
+    Qv.sd = WV(SD, j, k) + alpha * WDV(dSD, j, k);
+    Qv.sn = SDV ? 0.0 : WV(SN, j, k) + alpha * WDV(dSN, j, k);
+    Qv.yn = Qv.yr1 = Qv.yr2 = Qv.vd = Qv.vn = 0.0;
+    obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
+    th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
+    if (SDV) phi += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
+    { const double gap = Qv.sd - P.dmin; bad |= !(gap > 0.0); lacc.add(gap); }
+    if (!SDV) { const double gap = 1.0 - Qv.sn; bad |= !(gap > 0.0); lacc.add(gap); }
+    phi -= mu_b * lacc.total();
+    acc.th += th;
+    acc.phi += bad ? 1e300 : phi;
+  }
+
+  // stage pass: everything of stage k that is not an obstacle block
   OBCA_HD_NI static void merit_stage(const PkCtx& C, int k, double alpha, MeritPart& out) {
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
@@ -1162,8 +1254,6 @@ struct ParkSolver {
     const double t = fix ? 1.0 : S.t + alpha * S.dt;
     const double X = WA(X, k) + alpha * WA(dX, k), Y = WA(Y, k) + alpha * WA(dY, k);
     const double ps = WA(PS, k) + alpha * WA(dPS, k), v = WA(VL, k) + alpha * WA(dVL, k);
-    double sn_, cs_;
-    sincos(ps, &sn_, &cs_);
     double th = 0.0, phi = 0.0;
     bool bad = false;
     LogAcc lacc;
@@ -1183,7 +1273,7 @@ struct ParkSolver {
       const double h = t * P.Ts, ih = 1.0 / h;
       const double ed = de - wd, ea = ac - wa;
       phi += 0.01 * de * de + P.w_a * ac * ac + 0.1 * (ed * ed + ea * ea) * ih * ih;
-      const double rs = WA(RS, k) + alpha * WA(dRS, k);
+      const double rs = WA(RS, k) + alpha * WD(dRS, k);
       const double g6[6] = {de + 0.6, 0.6 - de, ac + 0.4, 0.4 - ac, rs + 0.6, 0.6 - rs};
 #pragma unroll
       for (int i = 0; i < 6; ++i) { bad |= !(g6[i] > 0.0); lacc.add(g6[i]); }
@@ -1198,32 +1288,6 @@ struct ParkSolver {
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) th += dabs(dyn.f[i] - xn[i]);
-    }
-    for (int j = 0; j < P.nOb; ++j) {
-      ObsRows<VM> R; ObsVars<VM> Qv; ObsGeom<VM> G;
-      load_rows(C, j, R);
-#pragma unroll
-      for (int i = 0; i < VM; ++i) {
-        const bool on = i < R.v;
-        Qv.lam[i] = on ? WV(LAM, P.voff[j] + i, k) + alpha * WV(dLAM, P.voff[j] + i, k) : 1.0;
-        Qv.zlam[i] = 0.0;
-        if (on) { bad |= !(Qv.lam[i] > 0.0); lacc.add(Qv.lam[i]); }
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        Qv.mu[m] = WV(MU, 4 * j + m, k) + alpha * WV(dMU, 4 * j + m, k);
-        Qv.zmu[m] = 0.0;
-        bad |= !(Qv.mu[m] > 0.0); lacc.add(Qv.mu[m]);
-      }
-      Qv.sl = SDV ? WV(SL, j, k) + alpha * WV(dSL, j, k) : 0.0;
-      Qv.sd = WV(SD, j, k) + alpha * WV(dSD, j, k);
-      Qv.sn = SDV ? 0.0 : WV(SN, j, k) + alpha * WV(dSN, j, k);
-      Qv.yn = Qv.yr1 = Qv.yr2 = Qv.vd = Qv.vn = 0.0;
-      obs_geom<VM, SDV>(P, X, Y, cs_, sn_, R, Qv, G);
-      th += dabs(G.cn) + dabs(G.cd) + dabs(G.cr1) + dabs(G.cr2);
-      if (SDV) phi += 1e2 * Qv.sl + 1e4 * Qv.sl * Qv.sl;
-      { const double gap = Qv.sd - P.dmin; bad |= !(gap > 0.0); lacc.add(gap); }
-      if (!SDV) { const double gap = 1.0 - Qv.sn; bad |= !(gap > 0.0); lacc.add(gap); }
     }
     if (k == 0 && !fix) {
       const double m = (double)(N + 1);
@@ -1250,6 +1314,53 @@ struct ParkSolver {
     q += alpha * dq; zl += adu * dzl; zu += adu * dzu;
     zl = clipz(zl, q - lo, mu_b, ks); zu = clipz(zu, hi - q, mu_b, ks);
   }
+  // item pass: the variables of block i = (obstacle j, stage k)
+  OBCA_HD_NI static void block_item_update(const PkCtx& C, int i) {
+    const ParkProblem& P = CTX_P(C);
+    const ProbState& S = *C.S;
+    const int NS = P.N + 1;
+    const int j = i / NS, k = i - j * NS;
+    const double mu_b = S.mu, ks = CTX_O(C).kappa_sigma;
+    const double alpha = S.alpha, adu = S.a_du, ay = dmin_(S.alpha, S.a_du);   // alpha_for_y = min (:41)
+    for (int r = P.voff[j]; r < P.voff[j + 1]; ++r) {
+      double q = WV(LAM, r, k), z = WV(ZLAM, r, k);
+      const double dq = WDV(dLAM, r, k);
+      const double dz = dzb(z, q, dq, mu_b);
+      q += alpha * dq; z += adu * dz;
+      WV(LAM, r, k) = q; WV(ZLAM, r, k) = clipz(z, q, mu_b, ks);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int r = 4 * j + m;
+      double q = WV(MU, r, k), z = WV(ZMU, r, k);
+      const double dq = WDV(dMU, r, k);
+      const double dz = dzb(z, q, dq, mu_b);
+      q += alpha * dq; z += adu * dz;
+      WV(MU, r, k) = q; WV(ZMU, r, k) = clipz(z, q, mu_b, ks);
+    }
+    if (SDV) {
+      WV(SL, j, k) += alpha * WDV(dSL, j, k);
+      WV(YN, j, k) += ay * (WDV(YNn, j, k) - WV(YN, j, k));
+    }
+    WV(YR, 2 * j, k) += ay * (WDV(YRn, 2 * j, k) - WV(YR, 2 * j, k));
+    WV(YR, 2 * j + 1, k) += ay * (WDV(YRn, 2 * j + 1, k) - WV(YR, 2 * j + 1, k));
+    {
+      double s = WV(SD, j, k), z = WV(VD, j, k);
+      const double ds = WDV(dSD, j, k);
+      const double dz = dzb(z, s - P.dmin, ds, mu_b);
+      s += alpha * ds; z += adu * dz;
+      WV(SD, j, k) = s; WV(VD, j, k) = clipz(z, s - P.dmin, mu_b, ks);
+    }
+    if (!SDV) {
+      double s = WV(SN, j, k), z = WV(VN, j, k);
+      const double ds = WDV(dSN, j, k);
+      const double dz = dzb(z, 1.0 - s, -ds, mu_b);
+      s += alpha * ds; z += adu * dz;
+      WV(SN, j, k) = s; WV(VN, j, k) = clipz(z, 1.0 - s, mu_b, ks);
+    }
+  }
+
+  // stage pass: pose, speed, controls, rate slack, multipliers of the dynamics rows
   OBCA_HD_NI static void update_stage(const PkCtx& C, int k) {
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
@@ -1279,47 +1390,38 @@ struct ParkSolver {
       upd_pair(q, WA(dAC, k), zl, zu, -0.4, 0.4, alpha, adu, mu_b, ks);
       WA(AC, k) = q; WA(ZAL, k) = zl; WA(ZAU, k) = zu;
       q = WA(RS, k); zl = WA(RVL, k); zu = WA(RVU, k);
-      upd_pair(q, WA(dRS, k), zl, zu, -0.6, 0.6, alpha, adu, mu_b, ks);
+      upd_pair(q, WD(dRS, k), zl, zu, -0.6, 0.6, alpha, adu, mu_b, ks);
       WA(RS, k) = q; WA(RVL, k) = zl; WA(RVU, k) = zu;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) WV(PI, i, k) += ay * (WV(PIn, i, k) - WV(PI, i, k));
+      for (int i = 0; i < 4; ++i) WV(PI, i, k) += ay * (WDV(PIn, i, k) - WV(PI, i, k));
     }
-    for (int r = 0; r < P.V; ++r) {
-      double q = WV(LAM, r, k), z = WV(ZLAM, r, k);
-      const double dq = WV(dLAM, r, k);
-      const double dz = dzb(z, q, dq, mu_b);
-      q += alpha * dq; z += adu * dz;
-      WV(LAM, r, k) = q; WV(ZLAM, r, k) = clipz(z, q, mu_b, ks);
-    }
-    for (int r = 0; r < 4 * P.nOb; ++r) {
-      double q = WV(MU, r, k), z = WV(ZMU, r, k);
-      const double dq = WV(dMU, r, k);
-      const double dz = dzb(z, q, dq, mu_b);
-      q += alpha * dq; z += adu * dz;
-      WV(MU, r, k) = q; WV(ZMU, r, k) = clipz(z, q, mu_b, ks);
-    }
-    for (int j = 0; j < P.nOb; ++j) {
-      if (SDV) {
-        WV(SL, j, k) += alpha * WV(dSL, j, k);
-        WV(YN, j, k) += ay * (WV(YNn, j, k) - WV(YN, j, k));
-      }
-      WV(YR, 2 * j, k) += ay * (WV(YRn, 2 * j, k) - WV(YR, 2 * j, k));
-      WV(YR, 2 * j + 1, k) += ay * (WV(YRn, 2 * j + 1, k) - WV(YR, 2 * j + 1, k));
-      {
-        double s = WV(SD, j, k), z = WV(VD, j, k);
-        const double ds = WV(dSD, j, k);
-        const double dz = dzb(z, s - P.dmin, ds, mu_b);
-        s += alpha * ds; z += adu * dz;
-        WV(SD, j, k) = s; WV(VD, j, k) = clipz(z, s - P.dmin, mu_b, ks);
-      }
-      if (!SDV) {
-        double s = WV(SN, j, k), z = WV(VN, j, k);
-        const double ds = WV(dSN, j, k);
-        const double dz = dzb(z, 1.0 - s, -ds, mu_b);
-        s += alpha * ds; z += adu * dz;
-        WV(SN, j, k) = s; WV(VN, j, k) = clipz(z, 1.0 - s, mu_b, ks);
-      }
-    }
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // The four stage-parallel phases of an iteration as the driver sees them: an item pass over the (obstacle, stage) blocks
+  // and a stage pass.  Only the evaluation needs a barrier between the two (the hand-over in the stage slots); the partial
+  // results of both passes accumulate in the same per-thread record, which the caller reduces over the CTA.
+  // ---------------------------------------------------------------------------------------------------
+  OBCA_HD static void eval_phase(const PkCtx& C, bool do_err, EvalPart& ep) {
+    const int NS = CTX_P(C).N + 1, NI = CTX_P(C).nOb * NS;
+    OBCA_FOR_ITEMS(i, NI) block_item_eval(C, i, do_err, ep);
+    OBCA_SYNC();
+    OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, do_err, true, e1); part_merge(ep, e1); }
+  }
+  OBCA_HD static void recover_phase(const PkCtx& C, StepPart& sp) {
+    const int NS = CTX_P(C).N + 1, NI = CTX_P(C).nOb * NS;
+    OBCA_FOR_ITEMS(i, NI) block_item_recover(C, i, sp);
+    OBCA_FOR_STAGES(k, NS) { StepPart s1; recover_stage(C, k, s1); part_merge(sp, s1); }
+  }
+  OBCA_HD static void merit_phase(const PkCtx& C, double alpha, MeritPart& mp) {
+    const int NS = CTX_P(C).N + 1, NI = CTX_P(C).nOb * NS;
+    OBCA_FOR_ITEMS(i, NI) block_item_merit(C, i, alpha, mp);
+    OBCA_FOR_STAGES(k, NS) { MeritPart m1; merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
+  }
+  OBCA_HD static void update_phase(const PkCtx& C) {
+    const int NS = CTX_P(C).N + 1, NI = CTX_P(C).nOb * NS;
+    OBCA_FOR_ITEMS(i, NI) block_item_update(C, i);
+    OBCA_FOR_STAGES(k, NS) update_stage(C, k);
   }
 
   // write the solution of stage k in the reference's output layout
@@ -1442,7 +1544,7 @@ struct IpmDriver {
       OBCA_SYNC();
       EvalPart ep;
       part_init(ep);
-      OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
+      M::eval_phase(C, true, ep);
       OBCA_REDUCE(ep);
       OBCA_PROF(0); OBCA_PROF_COUNT(7);
       OBCA_SERIAL {
@@ -1476,7 +1578,7 @@ struct IpmDriver {
       if (S.flag == 1) break;
       if (S.flag == 2) {   // mu changed: the barrier terms of the stage models (and phi) are stale
         part_init(ep);
-        OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, true, true, e1); part_merge(ep, e1); }
+        M::eval_phase(C, true, ep);
         OBCA_REDUCE(ep);
         OBCA_PROF(0); OBCA_PROF_COUNT(7);
         OBCA_SERIAL { apply_errors(C, ep); S.ok = ep.ok; }
@@ -1516,7 +1618,7 @@ struct IpmDriver {
         OBCA_PROF(1);
         if (S.ok != 0) break;
         part_init(ep);
-        OBCA_FOR_STAGES(k, NS) { EvalPart e1; M::stage_eval(C, k, false, true, e1); part_merge(ep, e1); }
+        M::eval_phase(C, false, ep);
         OBCA_REDUCE(ep);
         OBCA_SERIAL { S.ok = ep.ok; }
         OBCA_SYNC();
@@ -1527,7 +1629,7 @@ struct IpmDriver {
       // ---- K4: recover, step lengths, filter line search ----
       StepPart sp;
       part_init(sp);
-      OBCA_FOR_STAGES(k, NS) { StepPart s1; M::recover_stage(C, k, s1); part_merge(sp, s1); }
+      M::recover_phase(C, sp);
       OBCA_REDUCE(sp);
       OBCA_PROF(2);
       OBCA_SERIAL {
@@ -1548,7 +1650,7 @@ struct IpmDriver {
         const double alpha = S.alpha;
         MeritPart mp;
         part_init(mp);
-        OBCA_FOR_STAGES(k, NS) { MeritPart m1; M::merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
+        M::merit_phase(C, alpha, mp);
         OBCA_REDUCE(mp);
         OBCA_PROF(3); OBCA_PROF_COUNT(6);
         OBCA_SERIAL {
@@ -1597,7 +1699,7 @@ struct IpmDriver {
       if (S.flag == -2) continue;     // barrier kick: new direction from the same iterate
       if (S.flag < 0) break;
       // ---- accept ----
-      OBCA_FOR_STAGES(k, NS) M::update_stage(C, k);
+      M::update_phase(C);
       OBCA_SERIAL { M::update_scalars(C); }
       OBCA_SYNC();
       OBCA_PROF(4);

@@ -154,6 +154,7 @@ def eval_batch(x0, xF, N, Ts, L, ego_, XYbounds, nOb, vOb, A, b, rx, ry, ryaw, f
     fk = torch.zeros((B, NS), dtype=torch.float64, device=dev)
     ms = np.zeros(1)
     P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    torch.cuda.synchronize(dev)      # the library launches on its own stream: torch's copies / fills must have landed first
     check(lib().obca_parking_eval_batch_dev(
         C.c_int(B), C.c_int(N), C.c_int(nOb), ptr(vOb), ptr(A), ptr(b), P(bx0), P(bxF), C.c_double(Ts), C.c_double(L),
         ptr(f64(np.asarray(ego_).ravel())), ptr(f64(np.asarray(XYbounds).ravel())), P(brx), P(bry), P(bryaw), P(dxp), P(dup), P(dts),

@@ -22,7 +22,7 @@ static void run_one(const ParkProblem& P, const IpmOpts& O, const PkLay& L, doub
   std::vector<double> ric((size_t)(P.N + 2) * RSTRIDE, 0.0);
   std::vector<double> tile(256, 0.0);
   static const bool use_warp = getenv("OBCA_EMUL_SERIAL_KKT") == nullptr;
-  C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = ric.data(); C.pp = ric.data(); C.pps = RSTRIDE; C.bo = nullptr; C.red_scratch = nullptr; C.tile = use_warp ? tile.data() : nullptr; C.S = &S; C.in = in;
+  C.P = &P; C.O = &O; C.L = L; C.W = W; C.ric = ric.data(); C.pp = ric.data(); C.Wd = W + (size_t)L.dLAM * L.NSP; C.red_scratch = nullptr; C.tile = use_warp ? tile.data() : nullptr; C.S = &S; C.in = in;
   IpmDriver<ParkSolver<VM, SDV> >::solve(C);
   for (int k = 0; k <= P.N; ++k) ParkSolver<VM, SDV>::store_stage(C, k, out);
 }

@@ -23,7 +23,7 @@ def test_header_symbols_exported():
     assert "obca_parking_solve_batch" in names and "obca_dualmultws_batch" in names and len(names) >= 8
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.obca_version() == 100
+    assert lib.obca_version() == 200
 
 
 def test_default_opts_match_reference_call_site():

@@ -251,16 +251,16 @@ def test_dist_and_fixed_time_full_batch_rates(P):
 
 @pytest.mark.parametrize("variant,fix", [("sd", 0), ("d", 0), ("sd", 1)])
 def test_phased_equals_persistent(P, variant, fix):
-    """The phase-split driver (rounds of phase kernels with the state in HBM, OBCA_MODE=2), its tail / small-batch
-    kernel (OBCA_MODE=1), the automatic hand-over between the two, and the monolithic persistent kernel
-    (OBCA_MODE=3) run the same arithmetic in the same order: outputs must be bit-identical."""
+    """The phase-split driver (rounds of k_pk_eval / k_pk_sweep / k_pk_step with the state in HBM, OBCA_MODE=2), its tail /
+    small-batch kernel (OBCA_MODE=1) and the hand-over between the two run the same arithmetic in the same order (the same
+    out-of-line phase functions): outputs must be bit-identical."""
     from obca_b200 import scenarios
     sc = scenarios.reverse_parking_batch(200, 80, seed=5)
     sd = 1 if variant == "sd" else 0
     res = {}
     old = {k: os.environ.get(k) for k in ("OBCA_MODE", "OBCA_TAIL_THRESH")}
     try:
-        for name, mode, thresh in (("mono", "3", None), ("tail", "1", None), ("rounds", "2", "0"), ("handover", "2", "120")):
+        for name, mode, thresh in (("tail", "1", None), ("rounds", "2", "0"), ("handover", "2", "120"), ("auto", "0", None)):
             os.environ["OBCA_MODE"] = mode
             if thresh is None:
                 os.environ.pop("OBCA_TAIL_THRESH", None)
@@ -273,9 +273,9 @@ def test_phased_equals_persistent(P, variant, fix):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    ref = res["mono"]
+    ref = res["tail"]
     assert ref["exitflag"].sum() >= 190
-    for name in ("tail", "rounds", "handover"):
+    for name in ("rounds", "handover", "auto"):
         r = res[name]
         assert (r["iters"] == ref["iters"]).all(), (name, np.flatnonzero(r["iters"] != ref["iters"])[:8])
         assert (r["exitflag"] == ref["exitflag"]).all(), name
@@ -306,12 +306,12 @@ def test_chunked_batches_equal_unchunked(P):
 @pytest.mark.parametrize("nob,N", [(4, 80), (3, 100)])
 def test_phased_rounds_other_shapes(P, nob, N):
     """The phase-split rounds on the other template instantiations / horizons: 4-obstacle parallel parking (ragged half-space
-    counts) and a horizon that is not 80 -- same outputs as the monolithic kernel, feasible by the reference checker."""
+    counts) and a horizon that is not 80 -- same outputs as the persistent kernel, feasible by the reference checker."""
     from obca_b200 import scenarios
     sc = scenarios.parallel_parking_batch(160, N, seed=3, n_obstacles=nob)
     old = {k: os.environ.get(k) for k in ("OBCA_MODE", "OBCA_TAIL_THRESH")}
     try:
-        os.environ["OBCA_MODE"] = "3"
+        os.environ["OBCA_MODE"] = "1"
         ref = solve(P, sc)
         os.environ["OBCA_MODE"] = "2"; os.environ["OBCA_TAIL_THRESH"] = "40"
         r = solve(P, sc)
