@@ -92,6 +92,21 @@ struct PhasedDriver {
   typedef typename M::Ctx Ctx;
   typedef IpmDriver<M> D;
 
+  // B (serial part, one thread, after the sweep): Ipopt's inertia-correction bookkeeping.  `ok`: 1 if every pivot of
+  // the sweep had the required sign, 0 otherwise (also when the local blocks already failed and the sweep was skipped).
+  __device__ static void phase_B_serial(ProbState& S, const IpmOpts& O, int ok) {
+    S.n_fact++;
+    if (!ok) {
+      if (S.dw == 0.0) S.dw = (S.dw_last == 0.0) ? O.dw_first : dmax(O.dw_min, O.kw_minus * S.dw_last);
+      else S.dw *= (S.dw_last == 0.0) ? O.kw_plus_first : O.kw_plus;
+      if (S.dw > O.dw_max) { S.status = -2; ok = -1; }
+    } else if (S.dw > 0.0) {
+      S.dw_last = S.dw;
+    }
+    S.ok = ok;
+    S.phase = ok > 0 ? PH_RECOVER : (ok == 0 ? PH_REASM : PH_END);
+  }
+
   // A: [init] -> evaluate at the current iterate, convergence test, barrier update (+ re-evaluation), or re-assembly
   //    with a larger delta_w.  Leaves phase = PH_KKT (stage models ready) or PH_END (attempt over).
   __device__ __noinline__ static void phase_A(const Ctx& C) {
@@ -101,11 +116,7 @@ struct PhasedDriver {
     const int ph = S.phase;
     EvalPart ep;
     if (ph == PH_REASM) {
-      part_init(ep);
-      M::eval_phase(C, false, ep);
-      OBCA_REDUCE(ep);
-      OBCA_SERIAL { S.ok = ep.ok; S.phase = PH_KKT; S.prof[7]++; }
-      OBCA_SYNC();
+      reassemble(C);
       return;
     }
     if (ph == PH_INIT) {
@@ -158,28 +169,25 @@ struct PhasedDriver {
       S.phase = (S.flag == 1) ? PH_END : PH_KKT;
     }
     OBCA_SYNC();
-    if (S.flag != 2) return;
-    // mu changed: the barrier terms of the stage models (and phi) are stale
-    part_init(ep);
-    M::eval_phase(C, true, ep);
-    OBCA_REDUCE(ep);
-    OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; S.prof[5]++; }
-    OBCA_SYNC();
-  }
-
-  // B (serial part, one thread, after the sweep): Ipopt's inertia-correction bookkeeping.  `ok`: 1 if every pivot of
-  // the sweep had the required sign, 0 otherwise (also when the local blocks already failed and the sweep was skipped).
-  __device__ static void phase_B_serial(ProbState& S, const IpmOpts& O, int ok) {
-    S.n_fact++;
-    if (!ok) {
-      if (S.dw == 0.0) S.dw = (S.dw_last == 0.0) ? O.dw_first : dmax(O.dw_min, O.kw_minus * S.dw_last);
-      else S.dw *= (S.dw_last == 0.0) ? O.kw_plus_first : O.kw_plus;
-      if (S.dw > O.dw_max) { S.status = -2; ok = -1; }
-    } else if (S.dw > 0.0) {
-      S.dw_last = S.dw;
+    if (S.flag == 2) {
+      // mu changed: the barrier terms of the stage models (and phi) are stale
+      part_init(ep);
+      M::eval_phase(C, true, ep);
+      OBCA_REDUCE(ep);
+      OBCA_SERIAL { D::apply_errors(C, ep); S.ok = ep.ok; S.prof[7]++; S.prof[5]++; }
+      OBCA_SYNC();
     }
-    S.ok = ok;
-    S.phase = ok > 0 ? PH_RECOVER : (ok == 0 ? PH_REASM : PH_END);
+  }
+  // Re-assembly with the current delta_w (inertia correction).  (Inertia failures are found by the sweep: a wrong sign among
+  // the local pivots of the blocks alone is rare -- handling it inside this launch did not change the number of rounds.)
+  __device__ static void reassemble(const Ctx& C) {
+    ProbState& S = *C.S;
+    EvalPart ep;
+    part_init(ep);
+    M::eval_phase(C, false, ep);
+    OBCA_REDUCE(ep);
+    OBCA_SERIAL { S.ok = ep.ok; S.phase = PH_KKT; S.prof[7]++; }
+    OBCA_SYNC();
   }
 
   // C: recover the full step, step lengths, filter line search, and -- when a step is accepted -- the iterate update.

@@ -161,12 +161,30 @@ def rect_poly_distance(pose, Aj, bj, g, offset):
 _DW_T = {}
 
 
-def dualmultws_ipm(N, nOb, vOb, A, b, rx, ry, ryaw, ego, opts=None):
-    """DualMultWS.jl:36-77 as one sparse NLP (variables l, n, d; Max sum(d)) solved by oracle/ipm_ref.py with the
-    reference's options (tol=1e-5, max_iter=100, :36-37).  Returns lp (N+1)xV, np (N+1)x4nOb, d (N+1)xnOb."""
+def _dw_templates(v=None):
+    """sympy templates of DualMultWS.jl:52-73 (objective term; norm / rot1 / rot2 / d-definition rows of a block with v half-spaces)."""
     import sympy as sp
-    from . import ipm_ref
-    from .sparse_nlp import Family, SparseNLP, Template
+    from .sparse_nlp import Template
+    dsym = sp.Symbol("d")
+    if "obj" not in _DW_T:
+        _DW_T["obj"] = Template(-dsym, [dsym], [])
+    if v is not None and ("blk", v) not in _DW_T:
+        lam = sp.symbols(f"lam0:{v}"); mu = sp.symbols("mu0:4")
+        a1 = sp.symbols(f"aa0:{v}"); a2 = sp.symbols(f"ab0:{v}"); rho = sp.symbols(f"rho0:{v}")
+        gs = sp.symbols("g0:4"); cs, ss = sp.symbols("cs ss")
+        p1 = sum(a1[i] * lam[i] for i in range(v)); p2 = sum(a2[i] * lam[i] for i in range(v))
+        vs = list(lam) + list(mu); par = list(a1) + list(a2) + list(rho) + list(gs) + [cs, ss]
+        _DW_T[("blk", v)] = (Template(p1 ** 2 + p2 ** 2, vs, par),
+                             Template((mu[0] - mu[2]) + cs * p1 + ss * p2, vs, par),
+                             Template((mu[1] - mu[3]) - ss * p1 + cs * p2, vs, par),
+                             Template(dsym - (-sum(gs[i] * mu[i] for i in range(4)) + sum(rho[i] * lam[i] for i in range(v))),
+                                      vs + [dsym], par))
+    return _DW_T
+
+
+def build_dualmultws_nlp(N, nOb, vOb, A, b, rx, ry, ryaw, ego):
+    """DualMultWS.jl:36-77 as one sparse NLP (variables l, n, d; Max sum(d)).  Returns (nlp, banded symmetric ordering, (oN, oD))."""
+    from .sparse_nlp import Family, SparseNLP
     vOb = [int(x) for x in np.asarray(vOb).ravel()]
     A = np.asarray(A, float).reshape(-1, 2); b = np.asarray(b, float).ravel()
     g, offset = ego_geometry(ego)
@@ -177,25 +195,13 @@ def dualmultws_ipm(N, nOb, vOb, A, b, rx, ry, ryaw, ego, opts=None):
     ks = np.arange(NS)
     c, s = np.cos(ryaw), np.sin(ryaw)
     tcx, tcy = np.asarray(rx) + c * offset, np.asarray(ry) + s * offset
-    dsym = sp.Symbol("d")
-    if "obj" not in _DW_T:
-        _DW_T["obj"] = Template(-dsym, [dsym], [])
+    _dw_templates()
     jj, kk = np.meshgrid(np.arange(nOb), ks, indexing="ij")
     nlp.add_obj(Family("negd", _DW_T["obj"], (oD + nOb * kk.ravel() + jj.ravel()).reshape(-1, 1)))
     nlp.zL[:oD] = 0.0
     for j in range(nOb):
         v = vOb[j]
-        if ("blk", v) not in _DW_T:
-            lam = sp.symbols(f"lam0:{v}"); mu = sp.symbols("mu0:4")
-            a1 = sp.symbols(f"aa0:{v}"); a2 = sp.symbols(f"ab0:{v}"); rho = sp.symbols(f"rho0:{v}")
-            gs = sp.symbols("g0:4"); cs, ss = sp.symbols("cs ss")
-            p1 = sum(a1[i] * lam[i] for i in range(v)); p2 = sum(a2[i] * lam[i] for i in range(v))
-            vs = list(lam) + list(mu); par = list(a1) + list(a2) + list(rho) + list(gs) + [cs, ss]
-            _DW_T[("blk", v)] = (Template(p1 ** 2 + p2 ** 2, vs, par),
-                                 Template((mu[0] - mu[2]) + cs * p1 + ss * p2, vs, par),
-                                 Template((mu[1] - mu[3]) - ss * p1 + cs * p2, vs, par),
-                                 Template(dsym - (-sum(gs[i] * mu[i] for i in range(4)) + sum(rho[i] * lam[i] for i in range(v))),
-                                          vs + [dsym], par))
+        _dw_templates(v)
         tn, t1, t2, td = _DW_T[("blk", v)]
         r0 = voff[j]
         idx = np.stack([V * ks + r0 + r for r in range(v)] + [oN + 4 * nOb * ks + 4 * j + m for m in range(4)], 1)
@@ -206,16 +212,26 @@ def dualmultws_ipm(N, nOb, vOb, A, b, rx, ry, ryaw, ego, opts=None):
         nlp.add_eq(Family(f"rot1_{j}", t1, idx, par))
         nlp.add_eq(Family(f"rot2_{j}", t2, idx, par))
         nlp.add_eq(Family(f"ddef{j}", td, np.concatenate([idx, (oD + nOb * ks + j).reshape(-1, 1)], 1), par))
+    # banded symmetric ordering: (l_k, n_k) -> equality rows of stage k -> d_k  (d has no diagonal of its own, so
+    # it must follow the row that defines it for a pivot-free LDL')
+    vkey = np.zeros(n)
+    vkey[:oN] = 3 * np.repeat(ks, V); vkey[oN:oD] = 3 * np.repeat(ks, 4 * nOb); vkey[oD:] = 3 * np.repeat(ks, nOb) + 2
+    rkey = np.zeros(nlp.mE)
+    for fam in nlp.eq:
+        rkey[fam.row0:fam.row0 + fam.n] = 3 * ks + 1
+    order = np.argsort(np.concatenate([vkey, rkey]), kind="stable")
+    return nlp, order, (oN, oD)
+
+
+def dualmultws_ipm(N, nOb, vOb, A, b, rx, ry, ryaw, ego, opts=None):
+    """build_dualmultws_nlp solved by oracle/ipm_ref.py with the reference's options (tol=1e-5, max_iter=100, DualMultWS.jl:36-37).
+    Returns lp (N+1)xV, np (N+1)x4nOb, d (N+1)xnOb."""
+    from . import ipm_ref
+    nlp, order, (oN, oD) = build_dualmultws_nlp(N, nOb, vOb, A, b, rx, ry, ryaw, ego)
+    n = nlp.n; NS = N + 1; V = int(np.sum(np.asarray(vOb)))
     o = opts or ipm_ref.IpmOptions(tol=1e-5, max_iter=100, linsolve="sparse")
     if o.linsolve == "sparse" and o.order is None:
-        # banded symmetric ordering: (l_k, n_k) -> equality rows of stage k -> d_k  (d has no diagonal of its own, so
-        # it must follow the row that defines it for a pivot-free LDL')
-        vkey = np.zeros(n)
-        vkey[:oN] = 3 * np.repeat(ks, V); vkey[oN:oD] = 3 * np.repeat(ks, 4 * nOb); vkey[oD:] = 3 * np.repeat(ks, nOb) + 2
-        rkey = np.zeros(nlp.mE)
-        for fam in nlp.eq:
-            rkey[fam.row0:fam.row0 + fam.n] = 3 * ks + 1
-        o.order = np.argsort(np.concatenate([vkey, rkey]), kind="stable")
+        o.order = order
     res = ipm_ref.solve(nlp, np.zeros(n), o)          # JuMP default start = 0 (DualMultWS.jl has no setvalue)
     z = res.z
     return z[:oN].reshape(NS, V), z[oN:oD].reshape(NS, 4 * nOb), z[oD:].reshape(NS, nOb), res

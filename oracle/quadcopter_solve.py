@@ -9,8 +9,9 @@ from . import ipm_ref
 from .quadcopter_nlp import build_quadcopter_nlp, initial_point, stage_order
 
 
-def solve_quadcopter(x0, xF, N, Ts, R, obs, xWS, timeWS=1.0, variant="sd", opts=None, verbose=False, dual_ws=True):
-    """13 arguments of QuadcopterSignedDist.jl:25 (ob1..ob5 = obs rows; uWS is ignored by the reference, :202)."""
+def solve_quadcopter(x0, xF, N, Ts, R, obs, xWS, timeWS=1.0, variant="sd", opts=None, verbose=False, dual_ws=True, engine="python"):
+    """13 arguments of QuadcopterSignedDist.jl:25 (ob1..ob5 = obs rows; uWS is ignored by the reference, :202).
+    engine: "python" = oracle/ipm_ref.py, "compiled" = its C++ restatement oracle/cpu_ipm (same algorithm, same callbacks)."""
     nlp = build_quadcopter_nlp(x0, xF, N, Ts, R, obs, variant)
     lay = nlp.lay
     for k in (0, N):                    # pinned end states: drop the redundant bounds (same KKT points)
@@ -32,7 +33,13 @@ def solve_quadcopter(x0, xF, N, Ts, R, obs, xWS, timeWS=1.0, variant="sd", opts=
     xw[:, 0] = x0; xw[:, N] = xF                         # the pinned end states define the first / last warm-start block
     z0 = initial_point(lay, xw, timeWS, obs if dual_ws else None)
     t0 = time.time()
-    res = ipm_ref.solve(nlp, z0, o)
+    if engine == "compiled":
+        from types import SimpleNamespace
+        from . import cpu_ipm
+        r = cpu_ipm.solve_batch([nlp], [z0], m, stage_order(nlp), cpu_ipm.default_opts(o), 1)
+        res = SimpleNamespace(z=r["z"][0], status=int(r["status"][0]), iters=int(r["iters"][0]), err=float(r["err"][0]))
+    else:
+        res = ipm_ref.solve(nlp, z0, o)
     xp, up, ts, lp, sl = lay.unpack(res.z)
     exitflag = 1 if res.status == 1 else 0
     if variant == "sd" and exitflag == 1 and sl.sum() > 1e-3:

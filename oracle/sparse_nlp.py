@@ -35,6 +35,8 @@ class Template:
                     self.hpairs.append((i, j))
                     hexpr.append(h)
         args = list(vars_) + list(params)
+        # kept for the C code generator of the compiled CPU baseline (oracle/cpu_ipm/gen.py)
+        self.expr, self.vars_, self.params, self.grad_expr, self.hess_expr = expr, list(vars_), list(params), grad, hexpr
         self._f = sp.lambdify(args, expr, "numpy", cse=True)
         self._g = sp.lambdify(args, grad, "numpy", cse=True)
         self._h = sp.lambdify(args, hexpr, "numpy", cse=True) if hexpr else None

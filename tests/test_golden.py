@@ -12,13 +12,22 @@ from obca_b200 import scenarios
 from oracle import checkers, kkt_check
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("_"))
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+               if not os.path.basename(p).startswith(("_", "quad_")))        # quadcopter goldens: tests/test_quadcopter.py
+
+
+def golden_scenario(g):
+    """The batch a golden was generated from (tests/golden/make_golden.py): BASELINE config 2 (reverse parking, seed 0) or
+    config 3 (parallel parking, seed 1, 3 or 4 obstacles)."""
+    kind = str(g["scenario"]) if "scenario" in g else "reverse"
+    if kind.startswith("parallel"):
+        return scenarios.parallel_parking_batch(8, 80, int(g["seed"]), int(kind[-1]))
+    return scenarios.reverse_parking_batch(8, 80, int(g["seed"]))
 
 
 def load(case):
     g = np.load(os.path.join(HERE, "golden", case + ".npz"))
-    sc = scenarios.reverse_parking_batch(8, 80, int(g["seed"]))
-    return g, sc
+    return g, golden_scenario(g)
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -33,7 +42,7 @@ def test_golden_is_kkt_point_and_feasible(case):
     e = kkt_check.reference_kkt_error(sc, i, r, variant, fix)
     assert e["E0"] < 1e-5 and abs(e["f"] - float(g["f"])) < 1e-9
     Ts = sc["Ts_fix"] if fix else sc["Ts"]
-    ok = checkers.ParkingConstraints(sc["x0"][i], sc["xF"], 80, Ts, sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"],
+    ok = checkers.ParkingConstraints(sc["x0"][i], sc["xF"], 80, Ts, sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"],
                                      sc["b"], g["xp"], g["up"], g["lp"], g["np"], g["ts"], fix, 1 if variant == "sd" else 0)
     assert ok == 1
 

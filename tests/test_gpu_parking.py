@@ -53,22 +53,48 @@ def test_dualmultws_known_answers_and_distances(P, cfg2):
     assert (lp >= 0).all() and (npp >= 0).all()
 
 
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("_"))
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+               if not os.path.basename(p).startswith(("_", "quad_")))
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_matches_oracle_golden(P, cfg2, case):
-    """Same inputs (incl. the oracle's DualMultWS warm start) -> same KKT point as the IPOPT stand-in.
-    Tolerance: two interior-point runs stopped at tol = 1e-5 sit O(mu) ~ 1e-5 apart on the central path."""
+def test_matches_oracle_golden(P, case):
+    """Same inputs (incl. the oracle's DualMultWS warm start) -> same KKT point as the IPOPT stand-in, for BASELINE config 2
+    (reverse parking) and config 3 (parallel parking, 3 and 4 obstacles).
+    Tolerances: two interior-point runs stopped at tol = 1e-5 sit O(mu) ~ 1e-5 apart on the central path (primal: 2e-4).
+    The dual outputs lp, np (part of the reference's return tuple, ParkingSignedDist.jl:313) are unique only where the
+    distance row of their block is ACTIVE (row multiplier > 0: the block's (lambda, mu) is then the unique solution of the
+    dual distance problem at the pose); there they are compared at 2e-3 -- the sensitivity of the dual distance solution
+    to the 2e-4 primal tolerance -- and at 5e-3 elsewhere (inactive blocks are only weakly determined through the barrier)."""
+    from test_golden import golden_scenario
     g = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    sc = golden_scenario(g)
     i, variant, fix = int(g["index"]), str(g["variant"]), int(g["fixTime"])
-    sub = dict(cfg2); sub.update(B=1, x0=cfg2["x0"][i:i + 1], rx=cfg2["rx"][i:i + 1], ry=cfg2["ry"][i:i + 1],
-                                 ryaw=cfg2["ryaw"][i:i + 1], xWS=cfg2["xWS"][i:i + 1], uWS=cfg2["uWS"][i:i + 1])
+    sub = dict(sc); sub.update(B=1, x0=sc["x0"][i:i + 1], rx=sc["rx"][i:i + 1], ry=sc["ry"][i:i + 1],
+                               ryaw=sc["ryaw"][i:i + 1], xWS=sc["xWS"][i:i + 1], uWS=sc["uWS"][i:i + 1])
     r = solve(P, sub, fix, 1 if variant == "sd" else 0, g["lWS"][None], g["nWS"][None])
     assert r["exitflag"][0] == 1
     assert np.abs(r["xp"][0] - g["xp"]).max() < 2e-4 and np.abs(r["up"][0] - g["up"]).max() < 2e-4
     assert np.abs(r["ts"][0] - g["ts"]).max() < 1e-5
     assert np.abs(r["lp"][0] - g["lp"]).max() < 5e-3 and np.abs(r["np"][0] - g["np"]).max() < 5e-3
+    # blocks whose distance row is active in the golden: d(pose, obstacle) - dmin [+ sl] ~ 0 <=> (SD) sl off its free optimum
+    vo = np.concatenate([[0], np.cumsum(sc["vOb"])])
+    n_active = 0
+    for j in range(sc["nOb"]):
+        if variant == "sd":
+            act = np.flatnonzero(100.0 + 2e4 * g["sl"][j] > 5e-2)            # row multiplier = 1e2 + 2e4 sl (stationarity in sl)
+        else:
+            from oracle import dualmultws_ref
+            gg, off = dualmultws_ref.ego_geometry(sc["ego"])
+            dist = np.array([dualmultws_ref.rect_poly_distance((g["xp"][0, k], g["xp"][1, k], g["xp"][2, k]), sc["A"][vo[j]:vo[j + 1]],
+                                                               sc["b"].ravel()[vo[j]:vo[j + 1]], gg, off) for k in range(81)])
+            act = np.flatnonzero(dist < 0.05 + 2e-4)
+        n_active += len(act)
+        if len(act):
+            assert np.abs(r["lp"][0][vo[j]:vo[j + 1]][:, act] - g["lp"][vo[j]:vo[j + 1]][:, act]).max() < 2e-3, (case, j)
+            assert np.abs(r["np"][0][4 * j:4 * j + 4][:, act] - g["np"][4 * j:4 * j + 4][:, act]).max() < 2e-3, (case, j)
+    if variant == "sd":
+        assert np.abs(r["sl"][0] - g["sl"]).max() < 2e-5
 
 
 @pytest.mark.parametrize("variant,fix", [("sd", 0), ("d", 0), ("sd", 1), ("d", 1)])
@@ -409,3 +435,102 @@ def test_invariances_and_idempotence(P):
     dxp = np.abs(r2["xp"][both] - r["xp"][both]).max(axis=(1, 2)); dup = np.abs(r2["up"][both] - r["up"][both]).max(axis=(1, 2))
     assert np.quantile(dxp, 0.95) < 2e-3 and dxp.max() < 5e-2 and np.quantile(dup, 0.95) < 2e-3 and dup.max() < 5e-2
     # (no claim on the iteration count: an interior-point restart at mu = 0.1 first pushes the point back into the interior)
+
+
+def _opts(**kw):
+    import obca_b200
+    o = obca_b200.default_opts()
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _check(P, sc, r, sd):
+    return P.check_parking_batch(sc["x0"], sc["xF"], sc["N"], sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"],
+                                 sc["b"], r["xp"], r["up"], r["lp"], r["np"], r["ts"], 0, sd, r["sl"])[0]
+
+
+def test_retry_branch_signed_dist(P):
+    """ParkingSignedDist.jl:256-283 with a first attempt that is forced to fail (small max_iter -> :UserLimit): the reference
+    solves once more from the last iterate; if that converges exitflag = 1, after a second failure ParkingConstraints (sd = 1)
+    decides.  Driven through the round kernels AND the persistent kernel (same outputs).  Two iteration limits so that both
+    branches occur: with K = 20 most problems fail twice, with K = 45 most second attempts converge."""
+    from obca_b200 import scenarios
+    sc = scenarios.reverse_parking_batch(160, 80, seed=11)
+    seen_second_ok = seen_both_failed = 0
+    for K in (20, 45):
+        r0 = solve(P, sc, opts=_opts(max_iter=K, retry=0))                      # single attempt
+        assert (r0["iters"] <= K).all() and (r0["exitflag"] == 1).sum() < 160
+        old = {k: os.environ.get(k) for k in ("OBCA_MODE", "OBCA_TAIL_THRESH")}
+        try:
+            os.environ["OBCA_MODE"] = "1"; os.environ.pop("OBCA_TAIL_THRESH", None)
+            r1 = solve(P, sc, opts=_opts(max_iter=K, retry=1))
+            os.environ["OBCA_MODE"] = "2"; os.environ["OBCA_TAIL_THRESH"] = "30"
+            r2 = solve(P, sc, opts=_opts(max_iter=K, retry=1))
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        for key in ("xp", "up", "ts", "lp", "np", "iters", "exitflag"):
+            assert np.array_equal(r1[key], r2[key]), key
+        first_ok = r0["exitflag"] == 1
+        assert np.array_equal(r1["iters"][first_ok], r0["iters"][first_ok]) and (r1["exitflag"][first_ok] == 1).all()   # :256-257
+        retried = ~first_ok
+        d2 = r1["iters"] - r0["iters"]                                             # iterations of the second attempt (:258-263)
+        assert (d2[retried] >= 0).all() and (d2 <= K).all() and (d2[retried] > 0).mean() > 0.9
+        second_ok = retried & (r1["kkt_err"] <= 1e-5)
+        both_failed = retried & (d2 == K) & (r1["kkt_err"] > 1e-5)
+        assert (r1["exitflag"][second_ok] == 1).all()                             # :265-266
+        feas = _check(P, sc, r1, 1)
+        assert np.array_equal(r1["exitflag"][both_failed], feas[both_failed])     # :267-283: ParkingConstraints(..., 1) decides
+        seen_second_ok += int(second_ok.sum()); seen_both_failed += int(both_failed.sum())
+    assert seen_second_ok > 0 and seen_both_failed > 0                            # the test exercised both branches
+
+
+def test_retry_branch_dist_and_q4(P):
+    """ParkingDist.jl:245-289: after a failed FIRST attempt ParkingConstraints (sd = 0) decides -- a feasible point is accepted
+    (exitflag 1, no second solve), an infeasible one is solved again; after a SECOND failure the reference's test is inverted
+    (:278-282, Feasible == 0 -> exitflag 1): reproduced with opts.q4 = 1, fixed (exitflag = Feasible) by default."""
+    from obca_b200 import scenarios
+    K = 30
+    sc = scenarios.reverse_parking_batch(160, 80, seed=12)
+    r0 = solve(P, sc, sd=0, opts=_opts(max_iter=K, retry=0))
+    ra = solve(P, sc, sd=0, opts=_opts(max_iter=K, retry=1, q4=0))
+    rb = solve(P, sc, sd=0, opts=_opts(max_iter=K, retry=1, q4=1))
+    for key in ("xp", "up", "ts", "lp", "np", "iters"):
+        assert np.array_equal(ra[key], rb[key]), key                          # q4 only changes the flag
+    first_ok = r0["exitflag"] == 1
+    assert (ra["exitflag"][first_ok] == 1).all() and np.array_equal(ra["iters"][first_ok], r0["iters"][first_ok])
+    feas0 = _check(P, sc, r0, 0)                                               # the checker on the point of the first attempt
+    accepted = ~first_ok & (feas0 == 1)                                        # :259-262 feasible -> exitflag 1, no second solve
+    assert (ra["exitflag"][accepted] == 1).all() and np.array_equal(ra["iters"][accepted], r0["iters"][accepted])
+    assert np.array_equal(ra["xp"][accepted], r0["xp"][accepted])
+    resolved = ~first_ok & (feas0 == 0)
+    d2 = ra["iters"] - r0["iters"]
+    assert resolved.sum() > 0 and (d2[resolved] > 0).mean() > 0.9
+    both_failed = resolved & (d2 == K) & (ra["kkt_err"] > 1e-5)
+    feas = _check(P, sc, ra, 0)
+    assert both_failed.sum() > 0
+    assert np.array_equal(ra["exitflag"][both_failed], feas[both_failed])              # fixed polarity
+    assert np.array_equal(rb["exitflag"][both_failed], 1 - feas[both_failed])          # the reference as written
+    other = ~both_failed
+    assert np.array_equal(ra["exitflag"][other], rb["exitflag"][other])
+
+
+def test_returned_time_is_the_solve_alone(P, cfg2):
+    """The reference's `time` is the wall time of solve(m) (ParkingSignedDist.jl:239-241, :297): DualMultWS (:219) is outside.
+    obca_last_times reports both device times; with caller-provided lWS / nWS the DualMultWS part is (about) zero."""
+    import ctypes as C
+    import obca_b200
+    r = solve(P, cfg2)
+    ws = C.c_double(-1.0); sv = C.c_double(-1.0)
+    assert obca_b200.lib().obca_last_times(C.c_int(0), C.byref(ws), C.byref(sv)) == 0
+    assert abs(sv.value - r["time"]) < 1e-9 and ws.value > 1e-6 and sv.value > ws.value
+    lp, npp = P.dualmultws_batch(cfg2["N"], cfg2["nOb"], cfg2["vOb"], cfg2["A"], cfg2["b"], cfg2["rx"], cfg2["ry"], cfg2["ryaw"], cfg2["ego"])
+    r2 = solve(P, cfg2, lWS=lp, nWS=npp)
+    obca_b200.lib().obca_last_times(C.c_int(0), C.byref(ws), C.byref(sv))
+    assert ws.value < 2e-5
+    for key in ("xp", "up", "lp", "np", "iters"):
+        assert np.array_equal(r[key], r2[key]), key       # the library's own DualMultWS == the public one

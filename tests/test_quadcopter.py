@@ -82,3 +82,44 @@ def test_gpu_quadcopter_config4(variant):
     xp, up, tsp, ef, t, lp, status = f(sc["x0"][i][None], sc["xF"][i][None], N, sc["Ts"], sc["R"], *sc["obs"], sc["xWS"][i], np.full((4, N), 0.5), 1)
     assert xp.shape == (12, N + 1) and up.shape == (4, N) and tsp.shape == (N + 1,) and lp.shape == (30, N + 1) and ef == 1 and status == "Optimal"
     assert obca_b200.constrSatisfaction(xp, up, tsp, sc["x0"][i][None], sc["xF"][i][None], sc["Ts"], lp, *sc["obs"], sc["R"]) is True
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["quad_sd_p0", "quad_d_p1"])
+def test_gpu_quadcopter_matches_oracle_golden(case):
+    """BASELINE config 4 (N = 100): the library's solution against the golden of the IPOPT stand-in on the restated reference NLP
+    (tests/golden/make_golden.py), same inputs.  Primal trajectory 5e-4 (two interior-point runs stopped at tol 1e-5; the
+    quadcopter objective is flat along the time-optimal path), time scale 1e-4, objective 1e-4 relative."""
+    import os
+    from obca_b200 import quadcopter
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
+    N = int(g["N"]); i = int(g["index"]); variant = str(g["variant"])
+    sc = scenarios.quadcopter_batch(4, N, int(g["seed"]))
+    assert int(g["status"]) == 1
+    r = quadcopter.quadcopter_solve_batch(sc["x0"][i:i + 1], sc["xF"][i:i + 1], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"][i:i + 1], 1.0,
+                                          1 if variant == "sd" else 0)
+    assert r["exitflag"][0] == int(g["exitflag"])
+    assert np.abs(r["ts"][0] - g["ts"]).max() < 1e-4
+    assert np.abs(r["xp"][0] - g["xp"]).max() < 5e-4 and np.abs(r["up"][0] - g["up"]).max() < 5e-4
+    e, _ = _cert(sc, i, N, variant, r["xp"][0], r["up"][0], r["ts"][0], r["lp"][0], r["slack"][0])
+    assert e["E0"] < 1e-4 and abs(e["f"] - float(g["f"])) < 1e-4 * abs(float(g["f"]))
+
+
+@pytest.mark.gpu
+def test_gpu_quadcopter_full_config4_batch():
+    """BASELINE config 4 at its full size (B = 2048, N = 100, SD): convergence rate, the verbatim constrSatisfaction on every
+    returned trajectory (GPU twin), the slack gate of QuadcopterSignedDist.jl:283-288, and the reference-formulation KKT
+    certificate on a sample."""
+    from obca_b200 import quadcopter
+    N, B = 100, 2048
+    sc = scenarios.quadcopter_batch(B, N, 2)
+    r = quadcopter.quadcopter_solve_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"], 1.0, 1)
+    ok = r["exitflag"] >= 1
+    assert ok.mean() >= 0.97, ok.mean()
+    feas, worst = quadcopter.check_quadcopter_batch(r["xp"], r["up"], r["ts"], sc["x0"], sc["xF"], sc["Ts"], r["lp"], sc["obs"], sc["R"])
+    assert feas[r["exitflag"] == 1].all()
+    gate = r["slack"].reshape(B, -1).sum(1) > 1e-3
+    assert np.array_equal(r["exitflag"][ok] == 2, gate[ok])
+    for i in np.flatnonzero(r["exitflag"] == 1)[:3]:
+        e, _ = _cert(sc, int(i), N, "sd", r["xp"][i], r["up"][i], r["ts"][i], r["lp"][i], r["slack"][i])
+        assert e["E0"] < 1e-4 and e["constr_viol"] < 1e-4
