@@ -478,7 +478,7 @@ k_pk_eval(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
 #define OBCA_SWEEP_DEPTH 8
 #endif
 constexpr int SWEEP_DEPTH = OBCA_SWEEP_DEPTH;      // ring slots per warp (power of two)
-constexpr int SWEEP_WARP_DOUBLES = SWEEP_DEPTH * RSTRIDE + 240;   // ring + tile (ParkSolver::WIDE_TILE)
+constexpr int SWEEP_WARP_DOUBLES = SWEEP_DEPTH * RSTRIDE + 256;   // ring + tile (ParkSolver::WIDE_TILE)
 static_assert((RSTRIDE * 8) % 16 == 0 && (SWEEP_WARP_DOUBLES % 2) == 0, "16-byte alignment of the ring slots");
 
 __device__ __forceinline__ void sweep_prefetch(double* ring, const double* gslots, int k, int lane, int n) {
@@ -639,7 +639,9 @@ k_pk_tail(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
     __syncthreads();
     for (;;) {
       pk_step_A<VM, SDV>(C, out, bp, b, s_fin);
-      if (S.phase == PH_DONE) break;
+      const int ph = S.phase;
+      __syncthreads();      // every thread has read the phase before thread 0 moves it on (phase_B_serial)
+      if (ph == PH_DONE) break;
       if (threadIdx.x < 32) {
         int ok = S.ok;
         if (ok) ok = PS::kkt_solve_warp(C, s_tile);

@@ -245,13 +245,19 @@ struct PkCtx {
   PkInputs in;
 };
 
-#define WA(name, k) (C.W[(size_t)(CTX_L(C).name) * CTX_L(C).NSP + (k)])
-#define WV(name, i, k) (C.W[(size_t)(CTX_L(C).name + (i)) * CTX_L(C).NSP + (k)])
+// The context lives in shared memory and is passed by reference: after every store through a double* the compiler has to
+// assume that C.W / C.ric / ... changed and reloads them.  Functions that use the accessors below therefore start with
+// OBCA_LOCALS(C), which copies the base pointers into locals (registers) once.
+#define OBCA_LOCALS(C)                                                                                              \
+  double* const W_ = (C).W; double* const Wd_ = (C).Wd; double* const ric_ = (C).ric; const double* const pp_ = (C).pp; \
+  (void)W_; (void)Wd_; (void)ric_; (void)pp_
+#define WA(name, k) (W_[(size_t)(CTX_L(C).name) * CTX_L(C).NSP + (k)])
+#define WV(name, i, k) (W_[(size_t)(CTX_L(C).name + (i)) * CTX_L(C).NSP + (k)])
 // step rows that live in the step buffer (dLAM, dMU, dSL, PIn, YNn, YRn, dSD, dSN, dRS: contiguous in the layout)
-#define WD(name, k) (C.Wd[(size_t)(CTX_L(C).name - CTX_L(C).dLAM) * CTX_L(C).NSP + (k)])
-#define WDV(name, i, k) (C.Wd[(size_t)(CTX_L(C).name - CTX_L(C).dLAM + (i)) * CTX_L(C).NSP + (k)])
-#define RIC(off, k) (C.ric[(k) * RSTRIDE + (off)])
-#define PPV(off, k) (C.pp[(size_t)(k) * RSTRIDE + (off)])
+#define WD(name, k) (Wd_[(size_t)(CTX_L(C).name - CTX_L(C).dLAM) * CTX_L(C).NSP + (k)])
+#define WDV(name, i, k) (Wd_[(size_t)(CTX_L(C).name - CTX_L(C).dLAM + (i)) * CTX_L(C).NSP + (k)])
+#define RIC(off, k) (ric_[(k) * RSTRIDE + (off)])
+#define PPV(off, k) (pp_[(size_t)(k) * RSTRIDE + (off)])
 
 OBCA_HD double push_lo(double x, double lo, double hi, double k1, double k2) {
   const double pl = dmin_(k1 * dmax(1.0, dabs(lo)), k2 * (hi - lo));
@@ -282,6 +288,7 @@ struct ParkSolver {
     }
   }
   OBCA_HD static void load_vars(const PkCtx& C, int k, int j, const ObsRows<VM>& R, ObsVars<VM>& Q) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
 #pragma unroll
     for (int i = 0; i < VM; ++i) {
@@ -305,6 +312,7 @@ struct ParkSolver {
   // restart != 0: re-initialise from the current iterate (the reference's second solve(m) restarts Ipopt from
   // JuMP's stored primal values, ParkingSignedDist.jl:256-263) instead of from the warm-start inputs.
   OBCA_HD_NI static void init_stage(const PkCtx& C, int k, int restart) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const IpmOpts& O = CTX_O(C);
     const int N = P.N;
@@ -349,6 +357,7 @@ struct ParkSolver {
   }
   // slacks need the pushed primal point of the neighbours -> separate phase
   OBCA_HD_NI static void init_slacks(const PkCtx& C, int k) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const IpmOpts& O = CTX_O(C);
     const int N = P.N;
@@ -380,6 +389,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD static void block_eval(const PkCtx& C, int k, int j, double X, double Y, double cs_, double sn_, double mu_b,
                                  double dw, bool do_err, bool do_asm, BlockOut& B) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, fobj = 0.0;
     LogAcc lacc;
@@ -452,6 +462,7 @@ struct ParkSolver {
   // area) and merges the block's KKT-error / merit partials into the thread's running EvalPart.
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD_NI static void block_item_eval(const PkCtx& C, int i, bool do_err, EvalPart& acc) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int NS = P.N + 1;
@@ -484,6 +495,7 @@ struct ParkSolver {
   // stage pass of an evaluation: everything of stage k that is not an obstacle block (state objective and bounds, controls,
   // input-rate terms, steering-rate row, dynamics with second derivatives, time scale) + the sums of the block hand-overs
   OBCA_HD_NI static void stage_eval(const PkCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -505,6 +517,8 @@ struct ParkSolver {
     // the stage model (packed 9x9 Q, q) is accumulated directly in the stage slot (shared memory on the device)
 #pragma unroll
     for (int i = 0; i < NQ + NYV; ++i) RIC(RQ + i, k) = 0.0;
+#pragma unroll
+    for (int i = RR4 + 4; i < RSTRIDE; ++i) RIC(i, k) = 0.0;      // padding of the slot (it is copied out as a whole)
     double e_dual = 0.0, e_pr = 0.0, cmax = 0.0, cmin = 1e300, sum_y = 0.0, sum_z = 0.0, th = 0.0, phi = 0.0, fobj = 0.0;
     double rz_t = 0.0;
     int ok = 1;
@@ -679,6 +693,7 @@ struct ParkSolver {
   //     returns 1 if every pivot is positive (KKT inertia (n, m, 0)).
   // ---------------------------------------------------------------------------------------------------
   OBCA_HD static int kkt_solve(const PkCtx& C) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     ProbState& S = *C.S;
     const int N = P.N;
@@ -732,6 +747,7 @@ struct ParkSolver {
   // Light and strictly sequential: run by one thread.  The new multipliers of the dynamics rows are computed
   // afterwards, stage-parallel, in recover_stage().
   OBCA_HD static int kkt_root_forward(const PkCtx& C, double ptt, double pt) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     ProbState& S = *C.S;
     const int N = P.N;
@@ -789,14 +805,16 @@ struct ParkSolver {
   //   step 3 (35 tasks): 2x2 pivot on (de, a) (every lane: one reciprocal), gain column, new P entry / p entry
   //                                                                                               reads H         writes P, T(:, X|Y)
   // Tile (doubles): P 7x7 full [0,49) | p [49,56) | T 7x10 (columns of the stage vector + g) [56,126) |
-  //                 H 9x10 (column 9 = hv) [126,216) | zeros [216,224) | dump [224,240)
+  //                 H 9x10 (column 9 = hv) [126,216) | zeros [216,224) | dump [224,256): one cell per lane for the stores of
+  //                 its idle tasks (a lane only ever races with itself there)
   // Gains go to the stage's slot (RK..), rows 0..3 of P_k / p_k too (RPP.., Rpp..: consumed Q/q space) for recover_stage.
   // -------------------------------------------------------------------------------------------------
-  static constexpr int WP = 0, Wp = 49, WT = 56, WH = 126, WZ = 216, WDUMP = 224, WIDE_TILE = 240;
+  static constexpr int WP = 0, Wp = 49, WT = 56, WH = 126, WZ = 216, WDUMP = 224, WIDE_TILE = 256;
   struct WideLane {
     int s1_p[2], s1_j[2], s1_js[2], s1_x[2], s1_o[2];
     int s2_q[2], s2_j[2], s2_js[2], s2_t[2], s2_x[2], s2_o1[2], s2_o2[2];
     int s3_h[2], s3_hid[2], s3_hia[2], s3_hdj[2], s3_haj[2], s3_o1[2], s3_o2[2], s3_t1[2], s3_t2[2], s3_g1[2], s3_g2[2], s3_k[2], s3_ks[2];
+    int dump;
     int ok;
   };
   OBCA_HD static constexpr int col5(int c) { return c == 0 ? IP : c == 1 ? IV : c == 2 ? IT : c == 3 ? IDE : IAC; }
@@ -808,6 +826,8 @@ struct ParkSolver {
     j = i + t;
   }
   OBCA_HD static void wl_init(WideLane& L, int lane) {
+    const int dump = WDUMP + lane;
+    L.dump = dump;
     for (int u = 0; u < 2; ++u) {
       const int t = lane + 32 * u;
       // ---- step 1: task t = 6 a + c6 ----
@@ -819,7 +839,7 @@ struct ParkSolver {
         L.s1_x[u] = c6 == 2 ? WP + 7 * a + 6 : c6 == 3 ? WP + 7 * a + 4 : c6 == 4 ? WP + 7 * a + 5 : c6 == 5 ? Wp + a : WZ;
         L.s1_o[u] = WT + 10 * a + (c6 < 5 ? col5(c6) : 9);
       } else {
-        L.s1_p[u] = WP; L.s1_j[u] = RDYN; L.s1_js[u] = 5; L.s1_x[u] = WZ; L.s1_o[u] = WDUMP + u;
+        L.s1_p[u] = WP; L.s1_j[u] = RDYN; L.s1_js[u] = 5; L.s1_x[u] = WZ; L.s1_o[u] = dump;
       }
       // ---- step 2: t < 45: H(i, j), i <= j;  45 <= t < 54: hv(i) ----
       if (t < 54) {
@@ -835,9 +855,9 @@ struct ParkSolver {
         L.s2_t[u] = WT + c;
         L.s2_x[u] = r == IT ? WT + 60 + c : r == IDE ? WT + 40 + c : r == IAC ? WT + 50 + c : r == IX ? WT + c : r == IY ? WT + 10 + c : WZ;
         L.s2_o1[u] = WH + 10 * i + j;
-        L.s2_o2[u] = (j < 9 && i != j) ? WH + 10 * j + i : WDUMP + 2 + u;
+        L.s2_o2[u] = (j < 9 && i != j) ? WH + 10 * j + i : dump;
       } else {
-        L.s2_q[u] = RQ; L.s2_j[u] = -1; L.s2_js[u] = 1; L.s2_t[u] = WT; L.s2_x[u] = WZ; L.s2_o1[u] = WDUMP + 4 + u; L.s2_o2[u] = WDUMP + 6 + u;
+        L.s2_q[u] = RQ; L.s2_j[u] = -1; L.s2_js[u] = 1; L.s2_t[u] = WT; L.s2_x[u] = WZ; L.s2_o1[u] = dump; L.s2_o2[u] = dump;
       }
       // ---- step 3: t < 28: P(i, j), i <= j < 7;  28 <= t < 35: p(i) ----
       if (t < 35) {
@@ -847,19 +867,19 @@ struct ParkSolver {
         L.s3_hdj[u] = WH + 10 * IDE + j; L.s3_haj[u] = WH + 10 * IAC + j;
         if (j < 7) {
           L.s3_o1[u] = WP + 7 * i + j; L.s3_o2[u] = WP + 7 * j + i;
-          L.s3_t1[u] = j < 2 ? WT + 10 * i + j : WDUMP + 8 + u;              // T(:, X | Y) = P(:, 0 | 1)
-          L.s3_t2[u] = (i < 2 && i != j) ? WT + 10 * j + i : WDUMP + 10 + u;
+          L.s3_t1[u] = j < 2 ? WT + 10 * i + j : dump;              // T(:, X | Y) = P(:, 0 | 1)
+          L.s3_t2[u] = (i < 2 && i != j) ? WT + 10 * j + i : dump;
           L.s3_g1[u] = i < 4 ? RPP + NSV * i + j : -1;
           L.s3_g2[u] = (j < 4 && i != j) ? RPP + NSV * j + i : -1;
           L.s3_k[u] = i == 0 ? RK + j : -1; L.s3_ks[u] = NSV;
         } else {
-          L.s3_o1[u] = Wp + i; L.s3_o2[u] = WDUMP + 12 + u; L.s3_t1[u] = WDUMP + 8 + u; L.s3_t2[u] = WDUMP + 10 + u;
+          L.s3_o1[u] = Wp + i; L.s3_o2[u] = dump; L.s3_t1[u] = dump; L.s3_t2[u] = dump;
           L.s3_g1[u] = i < 4 ? Rpp + i : -1; L.s3_g2[u] = -1;
           L.s3_k[u] = i == 0 ? RK + 14 : -1; L.s3_ks[u] = 1;
         }
       } else {
         L.s3_h[u] = WZ; L.s3_hid[u] = WZ; L.s3_hia[u] = WZ; L.s3_hdj[u] = WZ; L.s3_haj[u] = WZ;
-        L.s3_o1[u] = WDUMP + 12 + u; L.s3_o2[u] = WDUMP + 12 + u; L.s3_t1[u] = WDUMP + 8 + u; L.s3_t2[u] = WDUMP + 10 + u;
+        L.s3_o1[u] = dump; L.s3_o2[u] = dump; L.s3_t1[u] = dump; L.s3_t2[u] = dump;
         L.s3_g1[u] = -1; L.s3_g2[u] = -1; L.s3_k[u] = -1; L.s3_ks[u] = 1;
       }
     }
@@ -872,6 +892,7 @@ struct ParkSolver {
     if (lane < 28) slotN[RPP + lane] = 0.0;
   }
   OBCA_HD static void wl_terminal(int lane, double* tile, double* slotN, const PkCtx& C) {
+    OBCA_LOCALS(C);
     const int N = CTX_P(C).N;
     if (lane < 4) {
       const double rho = 1.0 / CTX_O(C).dc, pl = -WV(PI, lane, N - 1);
@@ -913,10 +934,10 @@ struct ParkSolver {
       const double hdj = tile[L.s3_hdj[u]], haj = tile[L.s3_haj[u]];
       const double K0 = -fma(n00, hdj, n01 * haj), K1 = -fma(n01, hdj, n11 * haj);
       const double v = fma(tile[L.s3_hia[u]], K1, fma(tile[L.s3_hid[u]], K0, tile[L.s3_h[u]]));
-      double* const g1 = L.s3_g1[u] >= 0 ? out + L.s3_g1[u] : tile + WDUMP + 14;
-      double* const g2 = L.s3_g2[u] >= 0 ? out + L.s3_g2[u] : tile + WDUMP + 14;
-      double* const kp = L.s3_k[u] >= 0 ? out + L.s3_k[u] : tile + WDUMP + 14;
-      const int ks = L.s3_k[u] >= 0 ? L.s3_ks[u] : 1;
+      double* const g1 = L.s3_g1[u] >= 0 ? out + L.s3_g1[u] : tile + L.dump;
+      double* const g2 = L.s3_g2[u] >= 0 ? out + L.s3_g2[u] : tile + L.dump;
+      double* const kp = L.s3_k[u] >= 0 ? out + L.s3_k[u] : tile + L.dump;
+      const int ks = L.s3_k[u] >= 0 ? L.s3_ks[u] : 0;
       *g1 = v; *g2 = v;
       kp[0] = K0; kp[ks] = K1;
       tile[L.s3_o1[u]] = v; tile[L.s3_o2[u]] = v; tile[L.s3_t1[u]] = v; tile[L.s3_t2[u]] = v;
@@ -959,6 +980,7 @@ struct ParkSolver {
         if (k + 1 < N) dxw[k + 1] = sn;
         else Sout->eN[xr] = sn;
       }
+      __syncwarp();      // every lane is done with slot k before the ring slot is refilled (sweep kernel)
     }
     if (write) {
       if (lane < 4) { dxw[0] = 0.0; dxw[N] = 0.0; }
@@ -1034,6 +1056,7 @@ struct ParkSolver {
   struct RBlockOut { double apr_g, apr_d, adu_g, adu_d, dphi; };
   OBCA_HD static void block_recover(const PkCtx& C, int k, int j, double X, double Y, double cs_, double sn_, double dX, double dY,
                                     double dP, double mu_b, double dw, RBlockOut& rbo) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const double tau = 0.0;      // (unused by ftb: the fractions are scaled by tau when the stage is finished)
     Ftb apr, adu;
@@ -1101,6 +1124,7 @@ struct ParkSolver {
   // K4a, item pass: step of the unknowns of block i = (obstacle j, stage k); its tightest fractions to the boundary and its
   // part of the barrier directional derivative go straight into the thread's running StepPart (min / min / sum)
   OBCA_HD_NI static void block_item_recover(const PkCtx& C, int i, StepPart& acc) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int NS = P.N + 1;
@@ -1119,6 +1143,7 @@ struct ParkSolver {
 
   // K4a, stage pass (everything of stage k that is not an obstacle block)
   OBCA_HD_NI static void recover_stage(const PkCtx& C, int k, StepPart& out) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1202,6 +1227,7 @@ struct ParkSolver {
   // ---------------------------------------------------------------------------------------------------
   // item pass: block i = (obstacle j, stage k) at the trial point
   OBCA_HD_NI static void block_item_merit(const PkCtx& C, int i, double alpha, MeritPart& acc) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int NS = P.N + 1;
@@ -1245,6 +1271,7 @@ struct ParkSolver {
 
   // stage pass: everything of stage k that is not an obstacle block
   OBCA_HD_NI static void merit_stage(const PkCtx& C, int k, double alpha, MeritPart& out) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1316,6 +1343,7 @@ struct ParkSolver {
   }
   // item pass: the variables of block i = (obstacle j, stage k)
   OBCA_HD_NI static void block_item_update(const PkCtx& C, int i) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int NS = P.N + 1;
@@ -1362,6 +1390,7 @@ struct ParkSolver {
 
   // stage pass: pose, speed, controls, rate slack, multipliers of the dynamics rows
   OBCA_HD_NI static void update_stage(const PkCtx& C, int k) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
@@ -1426,6 +1455,7 @@ struct ParkSolver {
 
   // write the solution of stage k in the reference's output layout
   OBCA_HD static void store_stage(const PkCtx& C, int k, const PkOutputs& o) {
+    OBCA_LOCALS(C);
     const ParkProblem& P = CTX_P(C);
     const int N = P.N, NS = N + 1;
     o.xp[4 * k + 0] = WA(X, k); o.xp[4 * k + 1] = WA(Y, k); o.xp[4 * k + 2] = WA(PS, k); o.xp[4 * k + 3] = WA(VL, k);

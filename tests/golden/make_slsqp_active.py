@@ -11,7 +11,16 @@ SLSQP starts from the reference's initial point (ParkingSignedDist.jl:213-222 wi
 projection of the starting point into the bounds (kappa_1 = kappa_2 = 1e-2: lambda, mu >= 0.01 -- at lambda = 0 the rows
 |A' lambda|^2 == 1 have a zero gradient and SLSQP's LSQ subproblem is singular).  Output:
 tests/golden/_slsqp/slsqp_active_<variant>.npz (z of SLSQP, objective, constraint violation).   Run:  PYTHONPATH=. python
-tests/golden/make_slsqp_active.py sd d
+tests/golden/make_slsqp_active.py sd d d_local      (about an hour per variant on 4 cores)
+
+Findings (committed fixtures):
+  sd       SLSQP stops (status 8: no further descent at its numerical limit, |c| 3e-14) at f = 6.134674280 -- the interior-point
+           solvers stop at 6.134674284: same primal point to 7e-6, lambda on the five active blocks identical, mu to 3e-7.
+  d        from the same far start SLSQP heads for a DIFFERENT local minimum (another manoeuvre, f = 21.914 against 22.042 of the
+           interior-point solvers, 4.9 m apart; iteration limit reached): the Dist NLP is not convex and which minimum a solver
+           reaches depends on its path -- a limit of what any stand-in can say about IPOPT's answer.
+  d_local  SLSQP started from the interior-point solution perturbed by 1e-3 (random, seed 0) returns to it: the point
+           with 8 active distance rows is a strict local minimiser by an independent method.
 """
 import sys
 import time
@@ -39,7 +48,8 @@ def dense(M):
 
 def main(variants):
     sc, i = problem()
-    for variant in variants:
+    for tag in variants:
+        variant, local = tag.split("_")[0], tag.endswith("_local")
         nlp = solver_view(build_parking_nlp(sc["x0"][i], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
                                             sc["rx"][i], sc["ry"][i], sc["ryaw"][i], 0, variant))
         lay = nlp.lay
@@ -51,6 +61,13 @@ def main(variants):
         lWS, nWS, _ = dualmultws(N, 3, sc["vOb"], sc["A"], sc["b"], sc["rx"][i], sc["ry"][i], sc["ryaw"][i], sc["ego"])
         from oracle.ipm_ref import _push
         z0 = _push(initial_point(lay, sc["xWS"][i], sc["uWS"][i], lWS, nWS), nlp.zL, nlp.zU, 1e-2, 1e-2)
+        if local:
+            from oracle import cpu_ipm, ipm_ref
+            rr = cpu_ipm.ParkingCall(sc, [i], variant, 0).run(opts=cpu_ipm.default_opts(ipm_ref.IpmOptions(tol=1e-9, max_iter=400)),
+                                                              lWS=[lWS], nWS=[nWS])
+            assert rr["status"][0] == 1
+            z0 = rr["z"][0] + 1e-3 * np.random.default_rng(0).normal(size=nlp.n)
+            z0 = np.minimum(np.maximum(z0, np.where(np.isfinite(nlp.zL), nlp.zL, -1e300)), np.where(np.isfinite(nlp.zU), nlp.zU, 1e300))
         bounds = [(None if not np.isfinite(lo) else lo, None if not np.isfinite(hi) else hi) for lo, hi in zip(nlp.zL, nlp.zU)]
         t0 = time.time()
         it = [0]
@@ -61,8 +78,8 @@ def main(variants):
                 print(f"  {variant} it {it[0]} f {nlp.f(z):.9f} |cE| {np.abs(nlp.cE(z)).max():.2e} t {time.time() - t0:.0f}s", flush=True)
         r = minimize(nlp.f, z0, jac=nlp.grad, method="SLSQP", constraints=cons, bounds=bounds, options=dict(ftol=1e-14, maxiter=600), callback=cb)
         viol = max(np.abs(nlp.cE(r.x)).max(), np.maximum(gL - nlp.g(r.x), 0).max(), np.maximum(nlp.g(r.x) - gU, 0).max())
-        print(variant, "status", r.status, r.message, "nit", r.nit, "f", r.fun, "viol", viol, "time", time.time() - t0, flush=True)
-        np.savez_compressed(f"tests/golden/_slsqp/slsqp_active_{variant}.npz", z=r.x, f=r.fun, status=r.status, nit=r.nit, viol=viol,
+        print(tag, "status", r.status, r.message, "nit", r.nit, "f", r.fun, "viol", viol, "time", time.time() - t0, flush=True)
+        np.savez_compressed(f"tests/golden/_slsqp/slsqp_active_{tag}.npz", z=r.x, f=r.fun, status=r.status, nit=r.nit, viol=viol,
                             N=N, problem=i, variant=variant, lWS=lWS, nWS=nWS)
 
 

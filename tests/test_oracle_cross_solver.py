@@ -73,3 +73,75 @@ def test_slsqp_and_ipm_standin_and_kernel_sources_agree(variant, fix):
     xp, up, ts = lay.unpack(r.x)[:3]
     tol = 5e-5       # interior point: O(mu / z) inside weakly active bounds
     assert np.abs(k["xp"][0].T - xp).max() < tol and np.abs(k["up"][0].T - up).max() < tol and np.abs(k["ts"][0] - ts).max() < tol
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Independent solver with ACTIVE OBCA rows: fixtures of tests/golden/make_slsqp_active.py (SLSQP needs about an hour there)
+# ----------------------------------------------------------------------------------------------------------------------
+def active_problem():
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_slsqp_active as ms
+    sc, i = ms.problem()
+    sub = dict(sc); sub.update(B=1, x0=sc["x0"][i:i + 1], rx=sc["rx"][i:i + 1], ry=sc["ry"][i:i + 1], ryaw=sc["ryaw"][i:i + 1],
+                               xWS=sc["xWS"][i:i + 1], uWS=sc["uWS"][i:i + 1], Ts_fix=sc["Ts"])
+    return sub, ms.N
+
+
+def active_blocks(sc, N, variant, xp):
+    """(obstacle, stages) with the distance row at its bound in the point xp: d == dmin (Dist) / d + sl == dmin with sl at its
+    free optimum -0.005 (SignedDist)."""
+    from oracle import dualmultws_ref
+    g, off = dualmultws_ref.ego_geometry(sc["ego"])
+    A = sc["A"]; b = sc["b"].ravel(); vo = np.concatenate([[0], np.cumsum(sc["vOb"])])
+    out = []
+    for j in range(sc["nOb"]):
+        dist = np.array([dualmultws_ref.rect_poly_distance((xp[0, k], xp[1, k], xp[2, k]), A[vo[j]:vo[j + 1]], b[vo[j]:vo[j + 1]], g, off)
+                         for k in range(N + 1)])
+        act = np.flatnonzero(dist < (0.055 if variant == "sd" else 0.05) + 2e-5)
+        if len(act):
+            out.append((j, act, slice(vo[j], vo[j + 1])))
+    return out
+
+
+@pytest.mark.parametrize("tag", ["sd", "d_local"])
+def test_active_rows_slsqp_fixture_vs_interior_point_and_kernel_sources(tag):
+    """SLSQP's point (fixture) = the IPOPT stand-in's point (compiled restatement oracle/cpu_ipm, tol 1e-9) = the kernels' own
+    source (host build), on a config-2 start pose whose optimum has active distance rows (5 blocks SD / 8 blocks Dist).
+    Primal (x, timeScale, u): 2e-5.  lambda, mu ON THE ACTIVE BLOCKS (unique there): 1e-5 / 5e-4 for the kernel sources."""
+    from oracle import cpu_ipm
+    variant = tag.split("_")[0]
+    fx = np.load(os.path.join(HERE, "golden", "_slsqp", f"slsqp_active_{tag}.npz"))
+    sc, N = active_problem()
+    assert float(fx["viol"]) < 1e-9
+    r = cpu_ipm.ParkingCall(sc, [0], variant, 0).run(opts=cpu_ipm.default_opts(ipm_ref.IpmOptions(tol=1e-9, max_iter=400)),
+                                                     lWS=[fx["lWS"]], nWS=[fx["nWS"]])
+    assert r["status"][0] == 1
+    lay = r["nlp0"].lay
+    zs, zi = fx["z"], r["z"][0]
+    assert np.abs(zs[:lay.oL] - zi[:lay.oL]).max() < 2e-5 and abs(float(fx["f"]) - r["nlp0"].f(zi)) < 1e-7
+    xs, us, ts_s, ls, ns = lay.unpack(zs)[:5]
+    li, ni = lay.unpack(zi)[3:5]
+    blocks = active_blocks(sc, N, variant, xs)
+    assert sum(len(a) for _, a, _ in blocks) >= 5
+    for j, act, rows in blocks:
+        assert np.abs(ls[rows][:, act] - li[rows][:, act]).max() < 1e-5 and np.abs(ns[4 * j:4 * j + 4][:, act] - ni[4 * j:4 * j + 4][:, act]).max() < 1e-5
+    # the kernels' per-stage source, host build
+    o = emul.default_opts(); o.tol = 1e-8; o.mu_min = 1e-9
+    k = emul.solve_batch(sc, 0, variant, o, fx["lWS"][None], fx["nWS"][None])
+    assert k["status"][0] == 1
+    assert np.abs(k["xp"][0].T - xs).max() < 5e-5 and np.abs(k["up"][0].T - us).max() < 5e-5 and np.abs(k["ts"][0] - ts_s).max() < 5e-5
+    for j, act, rows in blocks:
+        assert np.abs(k["lp"][0].T[rows][:, act] - ls[rows][:, act]).max() < 5e-4
+        assert np.abs(k["np"][0].T[4 * j:4 * j + 4][:, act] - ns[4 * j:4 * j + 4][:, act]).max() < 5e-4
+
+
+def test_dist_variant_has_a_second_local_minimum():
+    """Recorded finding, not a pin: from the far start SLSQP heads for another manoeuvre of the Dist NLP (lower objective, metres
+    away from the interior-point solution).  The NLP is non-convex; no stand-in can promise IPOPT's local minimum."""
+    from oracle import cpu_ipm
+    fx = np.load(os.path.join(HERE, "golden", "_slsqp", "slsqp_active_d.npz"))
+    sc, N = active_problem()
+    r = cpu_ipm.ParkingCall(sc, [0], "d", 0).run(lWS=[fx["lWS"]], nWS=[fx["nWS"]])
+    lay = r["nlp0"].lay
+    assert r["status"][0] == 1 and float(fx["f"]) < r["nlp0"].f(r["z"][0]) - 0.05
+    assert np.abs(fx["z"][:4 * (N + 1)] - r["z"][0][:4 * (N + 1)]).max() > 1.0

@@ -11,10 +11,11 @@ run() {   # tool tag env... -- args
   env "$@" $CS --tool $tool --print-limit 20 python tools/sanitize_case.py $CASE > $log 2>&1
   echo "$tool $tag: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -n 1) | $(grep -E '^(parking|dist|quad) mode' $log | cut -c1-160)"
 }
-for tool in memcheck racecheck synccheck initcheck; do
-  CASE="parking 6 25"; run $tool sd_tail OBCA_MODE=1
-  CASE="parking 6 25"; run $tool sd_rounds OBCA_MODE=2 OBCA_TAIL_THRESH=0
-  CASE="parking 8 25"; run $tool sd_handover OBCA_MODE=2 OBCA_TAIL_THRESH=4
-  CASE="dist 6 25";    run $tool d_rounds OBCA_MODE=2 OBCA_TAIL_THRESH=0
-  CASE="quad 3 12";    run $tool quad OBCA_MODE=0
+for tool in memcheck racecheck; do
+  CASE="parking 4 10"; run $tool sd_handover OBCA_MODE=2 OBCA_TAIL_THRESH=2      # rounds (k_pk_eval / k_pk_sweep / k_pk_step) then k_pk_tail
+  CASE="dist 2 10";    run $tool d_tail OBCA_MODE=1
+  CASE="quad 2 8";     run $tool quad OBCA_MODE=0
+done
+for tool in synccheck initcheck; do
+  CASE="parking 4 10"; run $tool sd_handover OBCA_MODE=2 OBCA_TAIL_THRESH=2
 done
