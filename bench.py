@@ -95,17 +95,31 @@ class CpuArm:
                     per_dualws=float(r["dualws"]["seconds"].mean()))
 
 
+def best_threads(arm, threads):
+    """The host may expose more logical CPUs than it can run the solves on at full speed (SMT, memory bandwidth, cgroup quota):
+    time the same prepared sample with threads, threads/2, threads/4, threads/8 and keep the best throughput."""
+    best = None
+    for t in sorted({threads, max(1, threads // 2), max(1, threads // 4), max(1, threads // 8)}, reverse=True):
+        arm.threads = t
+        a = arm.run()
+        if best is None or a["conv"] / a["wall"] > best[1]["conv"] / best[1]["wall"]:
+            best = (t, a)
+    arm.threads = best[0]
+    return best
+
+
 def cpu_baseline_line(threads):
-    """Bounded sample: 8 problems per thread (about 1 s of CPU work per problem-thread), all threads + a single-thread figure."""
-    arm = CpuArm(8 * threads, threads)
+    """Bounded sample: 4 problems per host thread of the benchmark batch; the best thread count + a single-thread figure."""
+    arm = CpuArm(4 * threads, threads)
     arm.run()                                   # warm-up (page-in, OpenMP pool)
-    a = arm.run()
+    t_best, a = best_threads(arm, threads)
     one = CpuArm(8, 1)
     o = one.run()
-    return {"value": a["conv"] / a["wall"], "unit": "traj/s", "cores": threads, "kind": CPU_KIND,
-            "sample": f"{arm.n} problems of the same batch (seed 0), one per OpenMP thread, DualMultWS + solve {a['wall']:.2f} s wall "
-                      f"(solve alone {a['wall_solve']:.2f} s = the reference's `time` semantic), mean {a['per_solve'] * 1e3:.0f} ms/solve + "
-                      f"{a['per_dualws'] * 1e3:.0f} ms DualMultWS, mean {a['iters']:.0f} iterations; model build (python, untimed) {arm.setup_s:.1f} s",
+    return {"value": a["conv"] / a["wall"], "unit": "traj/s", "cores": t_best, "kind": CPU_KIND,
+            "sample": f"{arm.n} problems of the same batch (seed 0), one per OpenMP thread, {t_best} threads (best of {threads} and fractions of it on a "
+                      f"{threads}-CPU host), DualMultWS + solve {a['wall']:.2f} s wall (solve alone {a['wall_solve']:.2f} s = the reference's `time` "
+                      f"semantic), mean {a['per_solve'] * 1e3:.0f} ms/solve + {a['per_dualws'] * 1e3:.0f} ms DualMultWS, mean {a['iters']:.0f} iterations; "
+                      f"model build (python, untimed) {arm.setup_s:.1f} s",
             "solve_only_value": a["conv"] / a["wall_solve"],
             "single_thread_value": o["conv"] / o["wall"], "single_thread_solve_only_value": o["conv"] / o["wall_solve"]}
 
@@ -115,8 +129,10 @@ def reference_arm(args):
     if rank != 0:
         return
     threads = host_cores()
-    arm = CpuArm(4 * threads, threads)          # one step = 4 problems per host thread (about half a second of wall time)
-    for _ in range(max(args.warmup, 1)):
+    arm = CpuArm(4 * threads, threads)          # one step = 4 problems per host thread
+    arm.run()
+    threads_used, _ = best_threads(arm, threads)      # (warm-up; all the host threads it can use)
+    for _ in range(max(args.warmup - 1, 0)):
         arm.run()
     t0 = time.time(); conv = 0; its = []; solve_s = 0.0
     for _ in range(args.steps):
@@ -129,8 +145,9 @@ def reference_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample_per_step": arm.n, "iters_mean": float(np.mean(its)),
                        "solve_only_traj_per_s": conv / solve_s, "model_build_s_untimed": arm.setup_s},
-            "cpu_baseline": {"value": val, "unit": "traj/s", "cores": threads, "kind": CPU_KIND,
-                             "sample": f"{arm.n} problems/step of the same batch (seed 0), one per OpenMP thread, DualMultWS + solve timed; "
+            "cpu_baseline": {"value": val, "unit": "traj/s", "cores": threads_used, "kind": CPU_KIND,
+                             "sample": f"{arm.n} problems/step of the same batch (seed 0), one per OpenMP thread ({threads_used} threads: best of "
+                                       f"{threads} and fractions of it), DualMultWS + solve timed; "
                                        "model build untimed (as in the reference's `time`)"},
             "e2e": {"value": val, "unit": "traj/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

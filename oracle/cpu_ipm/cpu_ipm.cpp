@@ -320,7 +320,7 @@ struct Ipm {
     const double theta_max = 1e4 * std::max(1.0, th0), theta_min = 1e-4 * std::max(1.0, th0);
     double dw_last = 0.0;
     status = 0; err = INFINITY;
-    std::vector<double> yI(mI), resid(NT), corr(NT);
+    std::vector<double> yI(mI), resid(NT), corr(NT), Kcopy(M.nenv), zero(mE, 0.0), gdummy(n), accv(n);      // (no allocation inside the loop)
     int it = 0;
     for (it = 0; it <= O.max_iter; ++it) {
       double dinf, cinf, pinf;
@@ -355,9 +355,8 @@ struct Ipm {
       {
         std::vector<double>& w = tmp;      // reuse: weights of the inequality rows
         for (int i = 0; i < mI; ++i) w[i] = gam[i] + Ss[i] * (gI[i] - s[i]);
-        std::vector<double> zero(mE, 0.0), gdummy(n), acc(n);
-        grad_lag(z.data(), zero.data(), w.data(), gdummy.data(), acc.data());     // acc = grad f + JI' w
-        for (int i = 0; i < n; ++i) rhs[M.pos[i]] = -(bz[i] + (acc[i] - gdummy[i]));
+        grad_lag(z.data(), zero.data(), w.data(), gdummy.data(), accv.data());     // accv = grad f + JI' w
+        for (int i = 0; i < n; ++i) rhs[M.pos[i]] = -(bz[i] + (accv[i] - gdummy[i]));
         for (int i = 0; i < mE; ++i) rhs[M.pos[n + i]] = -cE[i] - dc[i] * yE[i];
         if (O.freeze_degenerate > 0) {      // oracle/ipm_ref.py: rows |p|^2 == 1 linearised at p = 0 carry no information
           double v[64], g[64], h[1024], fv;
@@ -380,8 +379,7 @@ struct Ipm {
       bool ok = false, first = true;
       for (;;) {
         assemble(dw, yI.data());
-        std::vector<double> Kcopy;      // the residual check needs K itself: recompute products from the assembled copy
-        Kcopy = K;
+        Kcopy = K;      // iterative refinement needs the unfactored matrix
         if (factor()) {
           ldl_solve(rhs.data(), sol.data());
           // two steps of iterative refinement with the unfactored matrix

@@ -1,5 +1,5 @@
 """Extract per-kernel DRAM traffic / duration of one full-load round from an `ncu --page raw --csv` dump into the small JSON
-bench.py reads for its `traffic` fields (profiles/ncu_traffic_r01.json).  usage: ncu_traffic.py raw.csv out.json"""
+bench.py reads for its `traffic` fields (profiles/ncu_traffic_r02.json).  usage: ncu_traffic.py raw.csv out.json"""
 import csv, json, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
