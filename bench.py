@@ -197,14 +197,22 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from obca_b200 import sharding
     dist = None
+    cpus = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        cpus = sharding.pin_rank_to_cpus(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))   # one CPU slice per rank
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = obca_b200.lib()
-    B, N, NS = args.batch, N_HORIZON, N_HORIZON + 1
-    sc = scenarios.reverse_parking_batch(B, N, seed=rank)          # independent problems per rank (batch shard)
+    N, NS = N_HORIZON, N_HORIZON + 1
+    if args.scaling == "strong":
+        # strong scaling: ONE global batch of --batch problems (seed 0), rank r solves its contiguous slice (sharding.shard_batch)
+        sc = sharding.shard_batch(scenarios.reverse_parking_batch(args.batch, N, seed=0), world, rank)
+    else:
+        sc = scenarios.reverse_parking_batch(args.batch, N, seed=rank)      # weak scaling: --batch independent problems per rank
+    B = sc["B"]
     nOb, V = sc["nOb"], int(np.sum(sc["vOb"]))
     vOb = np.ascontiguousarray(sc["vOb"], np.int32); A = np.asfortranarray(sc["A"]); b = np.ascontiguousarray(sc["b"]).ravel()
     ego = np.ascontiguousarray(sc["ego"]); xyb = np.ascontiguousarray(sc["XYbounds"])
@@ -276,13 +284,11 @@ def gpu_arm(args):
     e2e_s = time.perf_counter() - t0
     sampler.stop = True; sampler.join()
     conv_h = int(hflag.sum().item())
-    stats = torch.tensor([dev_s, e2e_s, wall_s], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([conv, conv_h, it_sum, evals], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)     # time = max over ranks
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)       # the one collective: throughput counters over NVLink
-    dev_s, e2e_s, wall_s = [float(x) for x in stats.tolist()]
-    conv_all, conv_h_all, it_all, evals_all = [float(x) for x in cnt.tolist()]
+    # the collectives of the path (obca_b200.sharding): counters SUM over NVLink, times MAX over the ranks
+    red = sharding.reduce_stats(dist, "cuda", dict(conv=conv, conv_h=conv_h, it_sum=it_sum, evals=evals, problems=B),
+                                dict(dev_s=dev_s, e2e_s=e2e_s, wall_s=wall_s))
+    dev_s, e2e_s, wall_s = red["dev_s"], red["e2e_s"], red["wall_s"]
+    conv_all, conv_h_all, it_all, evals_all, B_all = red["conv"], red["conv_h"], red["it_sum"], red["evals"], red["problems"]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -296,10 +302,11 @@ def gpu_arm(args):
     d2h = sum(int(v.numel()) * 8 for v in hout.values()) + 8 * B
     line = {"metric": "OBCA trajs/sec, reverse-parking N=80 3-obs batch", "value": value, "unit": "traj/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": int(B_all), "parallelism": f"batch-shard x{world}",
+                       "cpu_pinning_rank0": (f"{len(cpus)} CPUs" if cpus else "none"),
                        "l2": "256 MB flush between timed steps", "tol": 1e-5, "max_iter": 200,
-                       "converged_frac": conv_all / (B * world), "iters_mean": it_all / (B * world), "iters_max_rank0": it_max,
+                       "converged_frac": conv_all / B_all, "iters_mean": it_all / B_all, "iters_max_rank0": it_max,
                        "wall_ms_per_step": 1e3 * wall_s / args.steps,
                        "dualws_ms_per_step_rank0": 1e3 * ws_s[0] / args.steps,
                        "solve_only_ms_per_step_rank0": 1e3 * sv_s[0] / args.steps},
@@ -489,6 +496,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="obca")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the headline): --batch problems PER GPU; strong: --batch problems in total, sharded over the GPUs")
     ap.add_argument("--workload", default="reverse", choices=["reverse", "parallel", "parallel4", "quadcopter", "dist", "fixed"],
                     help="reverse = BASELINE config 2 (the headline line, default); the others print a secondary line")
     args = ap.parse_args()

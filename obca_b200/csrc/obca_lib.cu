@@ -384,29 +384,67 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
     cudaEventRecord(c.tev[n_ev++], st);
   };
   auto cap = [](int n, int m) { return n < m ? (n > 0 ? n : 1) : m; };
-  for (; r < max_rounds; ++r) {
-    const int* a_in = act[r & 1]; int* a_out = act[(r + 1) & 1];
-    int* n_in = c.ncnt + (r % 3); int* n_out = c.ncnt + ((r + 1) % 3); int* n_zero = c.ncnt + ((r + 2) % 3);
+  // one round = three launches + the read-back of the active count; grids from an upper bound nb of the active count
+  auto launch_round = [&](int rr, int nb, bool readback) -> int {
+    const int* a_in = act[rr & 1]; int* a_out = act[(rr + 1) & 1];
+    int* n_in = c.ncnt + (rr % 3); int* n_out = c.ncnt + ((rr + 1) % 3); int* n_zero = c.ncnt + ((rr + 2) % 3);
     mark();
-    k_pk_eval<VM, SDV><<<cap(n_bound, eval_cap), PK_THREADS, smem_slots, st>>>(P, O, L, bp, c.W, c.slots, Sg, a_in, n_in, a_out, n_out,
-                                                                            r == 0 ? 1 : 0);
+    k_pk_eval<VM, SDV><<<cap(nb, eval_cap), PK_THREADS, smem_slots, st>>>(P, O, L, bp, c.W, c.slots, Sg, a_in, n_in, a_out, n_out, rr == 0 ? 1 : 0);
     mark();
-    k_pk_sweep<VM, SDV><<<(n_bound + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, smem_sweep, st>>>(P, O, L, c.W, c.slots, Sg, a_out,
-                                                                                              n_out, n_zero);
+    k_pk_sweep<VM, SDV><<<(nb + SWEEP_WARPS - 1) / SWEEP_WARPS, 32 * SWEEP_WARPS, smem_sweep, st>>>(P, O, L, c.W, c.slots, Sg, a_out, n_out, n_zero);
     mark();
-    k_pk_step<VM, SDV><<<cap(n_bound, step_cap), PK_THREADS, smem_step, st>>>(P, O, L, bp, c.W, c.slots, Sg, a_out, n_out);
+    k_pk_step<VM, SDV><<<cap(nb, step_cap), PK_THREADS, smem_step, st>>>(P, O, L, bp, c.W, c.slots, Sg, a_out, n_out);
     mark();
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c.h_n + (r & 15), n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(c.evr[r & 15], st));
-    // the active set only shrinks: the count of any completed round bounds every later round
-    if (r - done_r >= 8) CK(cudaEventSynchronize(c.evr[done_r & 15]));
-    while (done_r <= r && cudaEventQuery(c.evr[done_r & 15]) == cudaSuccess) { n_bound = c.h_n[done_r & 15]; ++done_r; }
-    if (n_bound <= thresh) {
-      CK(cudaStreamSynchronize(st));
-      n_bound = c.h_n[r & 15];
-      ++r;
-      break;
+    if (readback) CK(cudaMemcpyAsync(c.h_n + (rr & 15), n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
+  // Rounds as a CUDA graph: the buffer pattern of a round (active lists: period 2, counters: period 3) repeats every 6 rounds, so
+  // rounds 1..6 are captured once per call and the graph is replayed -- about 14 driver calls per solve instead of ~420
+  // (3 launches + copy + event per round), which is what paces the host when 8 ranks share one box.  The grids inside the graph
+  // are those of the count at capture time (an upper bound later on: surplus CTAs / warps exit at once); the host looks at the
+  // active count once per replay, one replay behind, so the hand-over point is overshot by up to 12 rounds (the solve time is
+  // flat there, see above).  OBCA_GRAPH=0 or OBCA_PHASE_TIMING=1: plain launches, count read back every round.
+  const bool use_graph = !timing && env_int("OBCA_GRAPH", 1) != 0;
+  if (use_graph) {
+    rc = launch_round(0, B, true);
+    if (rc) return rc;
+    r = 1;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int q = 0; q < 6 && rc == 0; ++q) rc = launch_round(1 + q, B, q == 5);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CK(ce);
+    CK(cudaGraphInstantiate(&gexec, graph, 0));
+    int g = 0;
+    for (; r < max_rounds; ++g) {
+      CK(cudaGraphLaunch(gexec, st));
+      CK(cudaEventRecord(c.evr[g & 1], st));
+      r += 6;
+      if (g >= 1) {
+        CK(cudaEventSynchronize(c.evr[(g - 1) & 1]));
+        n_bound = c.h_n[(1 + 5) & 15];      // count after the last round of a replay (the replay in flight may refresh it: still a bound)
+        if (n_bound <= thresh) break;
+      }
+    }
+    CK(cudaStreamSynchronize(st));
+    n_bound = c.h_n[(1 + 5) & 15];
+    cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph);
+  } else {
+    for (; r < max_rounds; ++r) {
+      rc = launch_round(r, n_bound, true);
+      if (rc) return rc;
+      CK(cudaEventRecord(c.evr[r & 15], st));
+      // the active set only shrinks: the count of any completed round bounds every later round
+      if (r - done_r >= 8) CK(cudaEventSynchronize(c.evr[done_r & 15]));
+      while (done_r <= r && cudaEventQuery(c.evr[done_r & 15]) == cudaSuccess) { n_bound = c.h_n[done_r & 15]; ++done_r; }
+      if (n_bound <= thresh) {
+        CK(cudaStreamSynchronize(st));
+        n_bound = c.h_n[r & 15];
+        ++r;
+        break;
+      }
     }
   }
   c.last_rounds = r; c.last_tail = n_bound;

@@ -14,26 +14,52 @@ def shard_range(B: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def shard_batch(sc: dict, world: int, rank: int) -> dict:
-    """Slice every per-problem array of a scenario batch (obca_b200.scenarios) for this rank."""
-    lo, hi = shard_range(sc["B"], world, rank)
+    """Slice every per-problem array of a scenario batch (obca_b200.scenarios: parking or quadcopter) for this rank: every
+    numpy array whose leading dimension is the batch size B."""
+    B = sc["B"]
+    lo, hi = shard_range(B, world, rank)
     out = dict(sc)
-    for k in ("x0", "rx", "ry", "ryaw", "xWS", "uWS"):
-        out[k] = sc[k][lo:hi]
-    if np.ndim(sc["xF"]) == 2:
-        out["xF"] = sc["xF"][lo:hi]
+    for k, v in sc.items():
+        if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == B and k not in ("A", "b", "vOb", "ego", "XYbounds", "obs"):
+            out[k] = v[lo:hi]
     out["B"] = hi - lo
     out["offset"] = lo
     return out
 
 
-def reduce_counters(dist, device, converged: int, iterations: int, problems: int, seconds: float):
-    """The single collective of the path.  dist = torch.distributed (nccl on GPUs, gloo in the CPU tests)."""
+def reduce_stats(dist, device, sums: dict, maxes: dict) -> dict:
+    """The collectives of the path: ONE all-reduce (SUM) of the counters and ONE (MAX) of the times.  dist = torch.distributed
+    (nccl on GPUs, gloo in the CPU tests) or None for a single process."""
     import torch
-    cnt = torch.tensor([converged, iterations, problems], dtype=torch.float64, device=device)
-    tmax = torch.tensor([seconds], dtype=torch.float64, device=device)
+    ks, km = list(sums), list(maxes)
+    ts = torch.tensor([float(sums[k]) for k in ks], dtype=torch.float64, device=device)
+    tm = torch.tensor([float(maxes[k]) for k in km], dtype=torch.float64, device=device)
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    c, i, p = [float(x) for x in cnt.tolist()]
-    return dict(converged=int(c), iterations=int(i), problems=int(p), seconds=float(tmax.item()),
-                traj_per_s=c / max(float(tmax.item()), 1e-300))
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    out = {k: float(v) for k, v in zip(ks, ts.tolist())}
+    out.update({k: float(v) for k, v in zip(km, tm.tolist())})
+    return out
+
+
+def reduce_counters(dist, device, converged: int, iterations: int, problems: int, seconds: float):
+    """converged / iterations / problems summed over the ranks, device time = max over the ranks, whole-job trajectories per second."""
+    r = reduce_stats(dist, device, dict(converged=converged, iterations=iterations, problems=problems), dict(seconds=seconds))
+    return dict(converged=int(r["converged"]), iterations=int(r["iterations"]), problems=int(r["problems"]), seconds=r["seconds"],
+                traj_per_s=r["converged"] / max(r["seconds"], 1e-300))
+
+
+def pin_rank_to_cpus(local_rank: int, local_world: int):
+    """One disjoint slice of the host's CPUs per rank (the solver's host loop issues a few hundred driver calls per step; ranks that
+    share cores pace each other).  Returns the CPU list or None when the platform does not support affinities."""
+    import os
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(local_world, 1)
+        if per < 1:
+            return None
+        mine = cpus[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None

@@ -52,3 +52,22 @@ def test_two_rank_gloo_counters():
         assert r["problems"] == 11 and r["converged"] == int((sc["x0"][:, 0] < 5).sum())
         assert r["iterations"] == sum(range(1, 12)) and r["seconds"] == 1.5
         assert abs(r["traj_per_s"] - r["converged"] / 1.5) < 1e-12
+
+
+def test_shard_batch_slices_every_per_problem_array_and_pins_cpus():
+    """Parking and quadcopter batches: every array with leading dimension B is sliced, shared data (A, b, obstacles) is not."""
+    scq = scenarios.quadcopter_batch(7, 10, seed=2)
+    a, b = sharding.shard_batch(scq, 2, 0), sharding.shard_batch(scq, 2, 1)
+    assert a["B"] + b["B"] == 7 and a["x0"].shape == (4, 12) and b["xWS"].shape[0] == 3 and a["obs"].shape == scq["obs"].shape
+    assert np.array_equal(np.concatenate([a["xF"], b["xF"]]), scq["xF"])
+    scp = scenarios.reverse_parking_batch(5, 20, seed=0)
+    c = sharding.shard_batch(scp, 5, 3)
+    assert c["B"] == 1 and c["offset"] == 3 and np.array_equal(c["rx"][0], scp["rx"][3]) and c["A"].shape == scp["A"].shape
+    r = sharding.reduce_stats(None, "cpu", dict(a=2, b=3), dict(t=0.25))
+    assert r == dict(a=2.0, b=3.0, t=0.25)
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        mine = sharding.pin_rank_to_cpus(1, 2)
+        assert mine is None or (len(mine) == len(before) // 2 and set(mine) <= set(before))
+    finally:
+        os.sched_setaffinity(0, before)
