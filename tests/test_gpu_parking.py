@@ -557,3 +557,37 @@ def test_gpu_solution_equals_independent_sqp_with_active_rows(P, tag):
     for j, act, rows in blocks:
         assert np.abs(r["lp"][0][rows][:, act] - ls[rows][:, act]).max() < 5e-4
         assert np.abs(r["np"][0][4 * j:4 * j + 4][:, act] - ns[4 * j:4 * j + 4][:, act]).max() < 5e-4
+
+
+def test_config1_main_flow_on_device(P):
+    """BASELINE config 1 = the flow of AutonomousParking/main.jl with its default problem (x0 = [-6, 9.5, 0, 0], main.jl:213), B = 1:
+    Hybrid A* decides N (main.jl:217, :251), obstHrep (:252), then ParkingDist (:258) and ParkingSignedDist (:269) on the GPU, then
+    the reference's acceptance test.  Runs examples/main_parking.py as a user would and checks what it prints; then the same flow
+    through the API with the KKT certificate of the oracle on both solutions."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    p = subprocess.run([sys.executable, os.path.join(root, "examples", "main_parking.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Hybrid A*:" in p.stdout and "N = 64" in p.stdout
+    assert p.stdout.count("exitflag 1") == 2 and p.stdout.count("ParkingConstraints passed") == 2, p.stdout
+    import obca_b200
+    from obca_b200 import scenarios
+    from obca_b200.planner import warmstart
+    from oracle import kkt_check
+    sc = scenarios.reverse_parking_scenario()
+    x0 = np.array([-6.0, 9.5, 0.0, 0.0])
+    w = warmstart.plan_warm_start(x0, sc["xF"], "backwards")
+    N, Ts = w["N"], w["Ts"]
+    ego = np.array([3.7, 1.0, 1.0, 1.0]); XYb = np.array([-15.0, 15.0, 1.0, 10.0])
+    for fn, variant in ((obca_b200.ParkingDist, "d"), (obca_b200.ParkingSignedDist, "sd")):
+        xp, up, ts, ef, t, lp, np_ = fn(x0[None], sc["xF"][None], N, Ts, 2.7, ego, XYb, sc["nOb"], sc["vOb"], sc["A"], sc["b"], w["rx"], w["ry"],
+                                        w["ryaw"], 0, w["xWS"], w["uWS"][:N])
+        assert ef == 1 and xp.shape == (4, N + 1) and np.allclose(xp[:, 0], x0) and np.allclose(xp[:, -1], sc["xF"], atol=1e-9)
+        one = dict(sc); one.update(B=1, N=N, Ts=Ts, L=2.7, ego=ego, XYbounds=XYb, x0=x0[None], rx=np.asarray(w["rx"])[None],
+                                   ry=np.asarray(w["ry"])[None], ryaw=np.asarray(w["ryaw"])[None])
+        r = P.parking_solve_batch(x0[None], sc["xF"], N, Ts, 2.7, ego, XYb, sc["nOb"], sc["vOb"], sc["A"], sc["b"], w["rx"], w["ry"], w["ryaw"], 0,
+                                  np.asarray(w["xWS"])[None], np.asarray(w["uWS"])[None, :N], 1 if variant == "sd" else 0)
+        assert np.array_equal(r["xp"][0], xp)
+        e = kkt_check.reference_kkt_error(one, 0, r, variant=variant, fixTime=0)
+        assert e["E0"] < 1e-4, e

@@ -246,3 +246,42 @@ def test_example_main_parking_dry_run():
     assert "Hybrid A*:" in p.stdout and "N = 64" in p.stdout
     assert "Traceback" not in p.stderr
     assert p.returncode == 2 and "solve not run" in p.stdout
+
+
+def _read_export(d):
+    """What julia/main_parking.jl reads (same files, same shapes)."""
+    s = dict(ln.strip().split(",") for ln in open(os.path.join(d, "scalars.csv")))
+    rd = lambda n, **kw: np.atleast_2d(np.loadtxt(os.path.join(d, n), delimiter=",", **kw))
+    path = rd("path.csv", skiprows=1)
+    return dict(N=int(float(s["N"])), Ts=float(s["Ts"]), L=float(s["L"]), fixTime=int(float(s["fixTime"])), nOb=int(float(s["nOb"])),
+                x0=rd("x0.csv"), xF=rd("xF.csv"), ego=rd("ego.csv").ravel(), XYbounds=rd("XYbounds.csv").ravel(),
+                vOb=rd("vOb.csv").ravel().astype(int), A=rd("A.csv"), b=rd("b.csv").reshape(-1, 1), rx=path[:, 0], ry=path[:, 1], ryaw=path[:, 2],
+                xWS=rd("xWS.csv"), uWS=rd("uWS.csv"))
+
+
+def test_warm_start_export_for_the_julia_runner(tmp_path):
+    """obca_b200.planner.export_warmstart writes what main.jl holds before its NLP calls (main.jl:215-252) in the shapes the
+    reference's drivers take (x0, xF 1x4 rows; xWS (N+1)x4; uWS Nx2; A sum(vOb)x2) -- the input of julia/main_parking.jl."""
+    from obca_b200.planner import export_warmstart
+    N = export_warmstart.export(str(tmp_path))
+    e = _read_export(str(tmp_path))
+    assert e["N"] == N == 64 and e["x0"].shape == (1, 4) and e["xF"].shape == (1, 4)
+    assert e["xWS"].shape == (N + 1, 4) and e["uWS"].shape == (N, 2) and len(e["rx"]) == N + 1
+    assert e["A"].shape == (int(e["vOb"].sum()), 2) and e["b"].shape == (int(e["vOb"].sum()), 1) and e["nOb"] == len(e["vOb"]) == 3
+    assert np.allclose(e["xWS"][0, :3], e["x0"][0, :3]) and np.allclose(e["xWS"][:, 0], e["rx"])
+
+
+@pytest.mark.gpu
+def test_julia_runner_data_flow_through_the_ctypes_twin(tmp_path):
+    """The data flow of julia/main_parking.jl (CSV files -> the reference's 17 positional arguments -> ParkingDist,
+    ParkingSignedDist, ParkingConstraints) executed through the tested ctypes twin of the Julia shims."""
+    import obca_b200
+    from obca_b200.planner import export_warmstart
+    export_warmstart.export(str(tmp_path))
+    e = _read_export(str(tmp_path))
+    for fn, sd in ((obca_b200.ParkingDist, 0), (obca_b200.ParkingSignedDist, 1)):
+        xp, up, ts, ef, t, lp, np_ = fn(e["x0"], e["xF"], e["N"], e["Ts"], e["L"], e["ego"], e["XYbounds"], e["nOb"], e["vOb"], e["A"], e["b"],
+                                        e["rx"], e["ry"], e["ryaw"], e["fixTime"], e["xWS"], e["uWS"])
+        assert ef == 1 and t > 0
+        assert obca_b200.ParkingConstraints(e["x0"], e["xF"], e["N"], e["Ts"], e["L"], e["ego"], e["XYbounds"], e["nOb"], e["vOb"], e["A"], e["b"],
+                                            xp, up, lp, np_, ts, e["fixTime"], sd) == 1
