@@ -397,6 +397,11 @@ def gpu_arm(args):
             import emul
             nprob = min(1024, 8 * host_cores())
             scc = scenarios.reverse_parking_batch(nprob, N, seed=0)
+            try:      # the emulation's `omp parallel for` takes the global thread count (torch / the launcher may have set it to 1)
+                C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(host_cores()))
+            except OSError:
+                pass
+            emul.lib()
             t0 = time.time()
             lpe, npe, _, _ = emul.dualmultws_batch(scc)
             re_ = emul.solve_batch(scc, 0, "sd", None, lpe, npe)
