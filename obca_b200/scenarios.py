@@ -3,9 +3,9 @@
 * ``obst_hrep``           -- twin of AutonomousParking/obstHrep.jl:31-102 (vertices -> stacked H-rep).
 * ``reverse_parking_*``   -- scenario constants of AutonomousParking/main.jl:36-213 ("backwards").
 * ``warmstart_reverse``   -- deterministic geometric warm start (straight / left arc / reverse right arc /
-  reverse straight) standing in for the Hybrid A* + veloSmooth pipeline of main.jl:217-248, which is
-  out of scope this round.  Produces the same artefacts main.jl hands to
-  ParkingSignedDist: rx, ry, ryaw (N+1), xWS (N+1)x4, uWS Nx2.
+  reverse straight): the cheap synthetic stand-in for the Hybrid A* + veloSmooth pipeline of main.jl:217-248 that
+  the benchmark batches use (the pipeline itself is obca_b200/planner/).  Produces the same
+  artefacts main.jl hands to ParkingSignedDist: rx, ry, ryaw (N+1), xWS (N+1)x4, uWS Nx2.
 * ``reverse_parking_batch`` -- BASELINE config 2: randomised start poses, numpy default_rng(seed).
 """
 from __future__ import annotations
