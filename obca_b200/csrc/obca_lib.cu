@@ -548,6 +548,8 @@ static int launch_quad(DevCtx& c, const QuadProblem& P, const IpmOpts& O, const 
   int rc = ensure((void**)&c.W, &c.Wbytes, need);
   if (rc) return rc;
   CK(cudaMemcpyToSymbolAsync(c_pkO, &O, sizeof(O), 0, cudaMemcpyHostToDevice, c.st));   // IpmDriver reads the options here
+  CK(cudaMemcpyToSymbolAsync(c_qP, &P, sizeof(P), 0, cudaMemcpyHostToDevice, c.st));
+  CK(cudaMemcpyToSymbolAsync(c_qL, &L, sizeof(L), 0, cudaMemcpyHostToDevice, c.st));
   CK(cudaMemsetAsync(c.counter, 0, sizeof(int), c.st));
   k_quad_solve<SDV><<<grid, L.NSP, smem, c.st>>>(P, O, L, bp, c.W, c.counter);
   CK(cudaGetLastError());
@@ -555,6 +557,14 @@ static int launch_quad(DevCtx& c, const QuadProblem& P, const IpmOpts& O, const 
 }
 
 extern "C" {
+
+#ifdef OBCA_QPROF   // development builds only: cycles of the quadcopter sweep's phases, summed over CTAs; resets the counters
+int obca_debug_qprof(unsigned long long* out8) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out8, g_qprof, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(g_qprof, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int obca_version(void) { return OBCA_VERSION; }
 int obca_device_count(void) {

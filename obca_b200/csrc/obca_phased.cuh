@@ -499,7 +499,7 @@ __device__ int pk_sweep_warp(const ParkProblem& Pp, const IpmOpts& O, const PkLa
   const int N = Pp.N;
   const int lane = threadIdx.x & 31;
   PkCtx C;
-  C.P = &Pp; C.O = &O; C.L = Lay; C.W = W;
+  C.P = &Pp; C.O = &O; C.L = Lay; C.W = W; C.Wd = W; C.ric = ring; C.pp = gslots;   // ric: any shared address (OBCA_LOCALS)
   typename PS::WideLane L;
 #pragma unroll
   for (int a = 1; a < SWEEP_DEPTH; ++a) sweep_prefetch(ring, gslots, N - a, lane, N);
@@ -588,7 +588,7 @@ k_pk_step(const __grid_constant__ ParkProblem P, const __grid_constant__ IpmOpts
     if (threadIdx.x == 0) {
       pk_make_ctx<VM, SDV>(C, out, P, O, L, bp, b, Wall + (size_t)b * L.total * L.NSP);
       C.Wd = s_step;
-      C.ric = nullptr; C.pp = slots + (size_t)b * NS * RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
+      C.ric = s_step /* unused here; a shared address as OBCA_LOCALS assumes */; C.pp = slots + (size_t)b * NS * RSTRIDE; C.red_scratch = s_red; C.tile = nullptr; C.S = &S;
     }
     __syncthreads();
     if (threadIdx.x == 0) S.prof[6] = 0;

@@ -84,7 +84,24 @@ struct QCtx {
   QInputs in;
 };
 
-#define QA(name, i, k) (C.W[(size_t)(C.L.name + (i)) * C.L.NSP + (k)])
+// Problem, options and layout: __constant__ memory on the device (as for the parking model, obca_solver.cuh), the context on the host.
+#if defined(__CUDACC__)
+__constant__ QuadProblem c_qP;
+__constant__ QLay c_qL;
+#endif
+#if defined(__CUDA_ARCH__)
+#define QCTX_P(C) c_qP
+#define QCTX_O(C) c_pkO
+#define QCTX_L(C) c_qL
+// the workspace is global memory: lets the compiler emit LDG / STG instead of generic accesses
+#define QLOCALS(C) double* const W_ = (C).W; __builtin_assume(__isGlobal(W_)); (void)W_
+#else
+#define QCTX_P(C) (*(C).P)
+#define QCTX_O(C) (*(C).O)
+#define QCTX_L(C) ((C).L)
+#define QLOCALS(C) double* const W_ = (C).W; (void)W_
+#endif
+#define QA(name, i, k) (W_[(size_t)(QCTX_L(C).name + (i)) * QCTX_L(C).NSP + (k)])
 
 OBCA_HD void quad_jac_tables(const int*& jr, const int*& jc, const int*& hi, const int*& hj) {
   static constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
@@ -94,28 +111,31 @@ OBCA_HD void quad_jac_tables(const int*& jr, const int*& jc, const int*& hi, con
   jr = JR; jc = JC; hi = HI; hj = HJ;
 }
 
+#ifdef OBCA_QPROF
+__device__ unsigned long long g_qprof[8];   // development: cycles of the sweep's phases (thread 0 of every CTA)
+#endif
 template <bool SDV>
 struct QuadSolver {
   typedef QCtx Ctx;
   typedef QLocalDims<SDV> LD;
 
-  OBCA_HD static int n_stages(const QCtx& C) { return C.P->N + 1; }
+  OBCA_HD static int n_stages(const QCtx& C) { return QCTX_P(C).N + 1; }
   OBCA_HD static bool fixed_time(const QCtx&) { return false; }
   OBCA_HD static void mult_counts(const QCtx& C, double& n_mult, double& n_bmult) {
-    const double N = C.P->N, NS = N + 1;
+    const double N = QCTX_P(C).N, NS = N + 1;
     double nb = 24.0 * (N - 1) + 8.0 * N + 30.0 * NS + 2.0 * NS + (SDV ? 5.0 * NS : 0.0);   // variable bounds
     nb += 5.0 * NS;                                                                          // dist slack bounds
     n_bmult = nb; n_mult = nb + 12.0 * N + 5.0 * NS + 5.0 * NS;
   }
   OBCA_HD static void init_scalars(const QCtx& C, int restart) {
     ProbState& S = *C.S;
-    S.t = push_lo(restart ? S.t : C.in.timeWS, 0.5, 2.0, C.O->kappa1, C.O->kappa2);   // :96, :199
+    S.t = push_lo(restart ? S.t : C.in.timeWS, 0.5, 2.0, QCTX_O(C).kappa1, QCTX_O(C).kappa2);   // :96, :199
     S.zTL = 1.0; S.zTU = 1.0; S.dt = 0.0;
   }
   OBCA_HD static void update_scalars(const QCtx& C) {
     ProbState& S = *C.S;
     double q = S.t, zl = S.zTL, zu = S.zTU;
-    upd_pair(q, S.dt, zl, zu, 0.5, 2.0, S.alpha, S.a_du, S.mu, C.O->kappa_sigma);
+    upd_pair(q, S.dt, zl, zu, 0.5, 2.0, S.alpha, S.a_du, S.mu, QCTX_O(C).kappa_sigma);
     S.t = q; S.zTL = zl; S.zTU = zu;
   }
   OBCA_HD static void ftb(double gap, double dgap, double tau, double& amax) {
@@ -135,7 +155,8 @@ struct QuadSolver {
   }
 
   OBCA_HD static void load_obs(const QCtx& C, int k, int o, QObsVars& Q, double alpha) {
-    qobs_load_const(Q, C.P->obs[o]);
+    QLOCALS(C);
+    qobs_load_const(Q, QCTX_P(C).obs[o]);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       Q.lam[i] = QA(LAM, 6 * o + i, k) + (alpha != 0.0 ? alpha * QA(dLAM, 6 * o + i, k) : 0.0);
@@ -150,8 +171,9 @@ struct QuadSolver {
 
   // ---- P0 ----
   OBCA_HD_NI static void init_stage(const QCtx& C, int k, int restart) {
-    const QuadProblem& P = *C.P;
-    const IpmOpts& O = *C.O;
+    QLOCALS(C);
+    const QuadProblem& P = QCTX_P(C);
+    const IpmOpts& O = QCTX_O(C);
     const int N = P.N;
     const bool free_x = (k >= 1 && k <= N - 1);
     for (int i = 0; i < QNX; ++i) {
@@ -169,7 +191,7 @@ struct QuadSolver {
     for (int o = 0; o < QNOB; ++o) {
       double lw[6];
       if (!restart) {
-        if (C.O->quad_dual_ws) {
+        if (QCTX_O(C).quad_dual_ws) {
           const double pos[3] = {QA(X, 0, k), QA(X, 1, k), QA(X, 2, k)};
           quad_dual_ws(pos, P.obs[o], lw);                                  // closed-form dual warm start
         } else {
@@ -187,21 +209,23 @@ struct QuadSolver {
     }
   }
   OBCA_HD_NI static void init_slacks(const QCtx& C, int k) {
-    const QuadProblem& P = *C.P;
+    QLOCALS(C);
+    const QuadProblem& P = QCTX_P(C);
     double pos[3] = {QA(X, 0, k), QA(X, 1, k), QA(X, 2, k)};
     for (int o = 0; o < QNOB; ++o) {
       QObsVars Q; QObsGeom G;
       load_obs(C, k, o, Q, 0.0);
       Q.sd = 0.0;
       qobs_geom<SDV>(pos, Q, G);
-      QA(SD, o, k) = dmax(G.gd, P.R + C.O->kappa1 * dmax(1.0, dabs(P.R)));
+      QA(SD, o, k) = dmax(G.gd, P.R + QCTX_O(C).kappa1 * dmax(1.0, dabs(P.R)));
       QA(VD, o, k) = 1.0;
     }
   }
 
   // ---- K1 ----
   OBCA_HD_NI static void stage_eval(const QCtx& C, int k, bool do_err, bool do_asm, EvalPart& out) {
-    const QuadProblem& P = *C.P;
+    QLOCALS(C);
+    const QuadProblem& P = QCTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
     const double mu_b = S.mu, dw = S.dw, t = S.t;
@@ -327,7 +351,7 @@ struct QuadSolver {
         const int piv = qobs_choose_pivot(G);
         if (piv != 0) { qobs_swap(Q, piv); qobs_geom<SDV>(pos, Q, G); }
         double Sxx[6], rx3[3];
-        ok &= qobs_condense<SDV>(P.R, Q, G, mu_b, dw, C.O->dc, Sxx, rx3, &QA(LF, o * C.L.nfac, k), C.L.NSP);
+        ok &= qobs_condense<SDV>(P.R, Q, G, mu_b, dw, QCTX_O(C).dc, Sxx, rx3, &QA(LF, o * QCTX_L(C).nfac, k), QCTX_L(C).NSP);
         if (free_x && has_u) {
           QQ(0, 0) += Sxx[0]; QQ(0, 1) += Sxx[1]; QQ(0, 2) += Sxx[2]; QQ(1, 1) += Sxx[3]; QQ(1, 2) += Sxx[4]; QQ(2, 2) += Sxx[5];
           Qq(0) += rx3[0]; Qq(1) += rx3[1]; Qq(2) += rx3[2];
@@ -361,14 +385,15 @@ struct QuadSolver {
 
   // ---- K3: dense Riccati sweep over [x | w | t] (17) with 4 controls, run by one thread ----
   OBCA_HD static int kkt_dense(const QCtx& C) {
-    const QuadProblem& Pp = *C.P;
+    QLOCALS(C);
+    const QuadProblem& Pp = QCTX_P(C);
     ProbState& S = *C.S;
     const int N = Pp.N;
     const int *jr, *jc, *hi, *hj;
     quad_jac_tables(jr, jc, hi, hj);
     double P[QNSV][QNSV], p[QNSV];
     for (int a = 0; a < QNSV; ++a) { p[a] = 0.0; for (int b = 0; b < QNSV; ++b) P[a][b] = 0.0; }
-    const double rho = 1.0 / C.O->dc;
+    const double rho = 1.0 / QCTX_O(C).dc;
     for (int i = 0; i < QNX; ++i) { P[i][i] = rho; p[i] = -QA(PI, i, N - 1); }
     int ok = 1;
     for (int k = N - 1; k >= 0 && ok; --k) {
@@ -545,12 +570,22 @@ struct QuadSolver {
       if (c2 < QNYV) H[c1 * QNYV + c2] = acc; else hv[c1] = acc;
     }
   }
-  __device__ static int kkt_solve_block(const QCtx& C) {
-    const QuadProblem& Pp = *C.P;
+#ifdef OBCA_QPROF
+#define QPROF(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); qacc[i] += t_ - qt; qt = t_; } } while (0)
+#else
+#define QPROF(i) do { } while (0)
+#endif
+  __device__ __noinline__ static int kkt_solve_block(const QCtx& C) {
+    QLOCALS(C);
+    extern __shared__ __align__(16) double obca_dyn_smem[];      // == C.tile; named here so that the accesses are LDS / STS
+#ifdef OBCA_QPROF
+    long long qacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qt = clock64();
+#endif
+    const QuadProblem& Pp = QCTX_P(C);
     ProbState& S = *C.S;
     const int N = Pp.N;
     const int tid = threadIdx.x, nt = blockDim.x;
-    double* sm = C.tile;
+    double* const sm = obca_dyn_smem;
     double *P = sm + SM_P, *p = sm + SM_p, *g = sm + SM_g, *T = sm + SM_T, *H = sm + SM_H, *hv = sm + SM_hv, *K = sm + SM_K,
            *sv = sm + SM_s, *uv = sm + SM_u, *stg = sm + SM_STG, *Kall = sm + SM_Kall;
     static constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
@@ -558,9 +593,9 @@ struct QuadSolver {
     static constexpr int RPT[QNX + 1] = OBCA_QD_ROW_PTR;
     static constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
     static constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
-    const double rho = 1.0 / C.O->dc;
-    const size_t nsp = (size_t)C.L.NSP;
-    const double* const gQ = C.W + (size_t)C.L.QS * nsp;     // QS, qs, JV, R12 are consecutive arrays of the workspace
+    const double rho = 1.0 / QCTX_O(C).dc;
+    const size_t nsp = (size_t)QCTX_L(C).NSP;
+    const double* const gQ = W_ + (size_t)QCTX_L(C).QS * nsp;     // QS, qs, JV, R12 are consecutive arrays of the workspace
     auto prefetch = [&](int k, int buf, int first, int count) {   // elements [first, first+count) of stage k
       if (k >= 0 && k < N)
         for (int e = tid; e < count; e += nt) cp_async8(stg + buf * STG_N + first + e, gQ + (size_t)(first + e) * nsp + k);
@@ -587,8 +622,10 @@ struct QuadSolver {
       const double* const Jv = qv + QNYV;
       const double* const r12 = Jv + QD_NJ;
       prefetch(k - 1, (k - 1) & 1, 0, STG_N);
+      QPROF(0);
       cp_async_wait<1>();
       __syncthreads();                     // stage data landed; P, p of stage k+1 final
+      QPROF(1);
       // rows 0..11 of P_{k+1}, p_{k+1} for the multiplier recovery (fire-and-forget stores)
       for (int e = tid; e < QNX * QNSV; e += nt) QA(RP, e, k + 1) = P[e];
       for (int i = tid; i < QNX; i += nt) QA(RP, QNX * QNSV + i, k + 1) = p[i];
@@ -610,6 +647,7 @@ struct QuadSolver {
         }
       }
       __syncthreads();
+      QPROF(2);
       // H = Q + Phi' T ; hv = q + Phi' g:  lane c2 <= 21 holds column c2 of T (21: g); warp w computes the rows w, w+4, ...
       if (lane <= QNYV) {
         double Tc[QNSV];
@@ -623,6 +661,7 @@ struct QuadSolver {
         }
       }
       __syncthreads();
+      QPROF(3);
       // K = -Huu^{-1} [Hus | hu]: column c = 0..17, one thread per column, each with its own LDL' of Huu
       if (tid <= QNSV) {
         const int c = tid;
@@ -663,6 +702,7 @@ struct QuadSolver {
         for (int a = 0; a < QNU; ++a) { K[a * (QNSV + 1) + c] = -k4[a]; Kall[k * KROW + a * (QNSV + 1) + c] = -k4[a]; }
       }
       __syncthreads();
+      QPROF(4);
       if (sm[SM_flag] == 0.0) { cp_async_wait<0>(); return 0; }
       // value function of stage k (a <= b, mirrored); the barrier at the top of the next stage publishes it
       for (int i = 0; i < 2; ++i) {
@@ -682,6 +722,7 @@ struct QuadSolver {
     }
     cp_async_wait<0>();
     __syncthreads();
+    QPROF(5);
     // root
     if (tid == 0) {
       const double ptt = P[QIT * QNSV + QIT];
@@ -732,6 +773,10 @@ struct QuadSolver {
       if (lane < QNU) QA(dU, lane, N) = 0.0;
     }
     __syncthreads();
+#ifdef OBCA_QPROF
+    QPROF(6);
+    if (threadIdx.x == 0) { for (int i = 0; i < 7; ++i) atomicAdd(&g_qprof[i], (unsigned long long)qacc[i]); atomicAdd(&g_qprof[7], 1ull); }
+#endif
     return 1;
   }
   __device__ static int kkt_solve_warp(const QCtx&, double*) { return 0; }   // unused (KKT_BLOCK)
@@ -739,7 +784,8 @@ struct QuadSolver {
 
   // ---- K4a ----
   OBCA_HD_NI static void recover_stage(const QCtx& C, int k, StepPart& out) {
-    const QuadProblem& P = *C.P;
+    QLOCALS(C);
+    const QuadProblem& P = QCTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
     const double mu_b = S.mu, tau = S.tau;
@@ -785,7 +831,7 @@ struct QuadSolver {
       const int piv = qobs_choose_pivot(G);
       if (piv != 0) { qobs_swap(Q, piv); qobs_geom<SDV>(pos, Q, G); }
       QObsStep St;
-      qobs_recover<SDV>(P.R, Q, G, mu_b, &QA(LF, o * C.L.nfac, k), C.L.NSP, dpos, St);
+      qobs_recover<SDV>(P.R, Q, G, mu_b, &QA(LF, o * QCTX_L(C).nfac, k), QCTX_L(C).NSP, dpos, St);
       if (piv != 0) {
         for (int i = 1; i < 6; ++i)
           if (i == piv) {
@@ -826,7 +872,8 @@ struct QuadSolver {
 
   // ---- K4b ----
   OBCA_HD_NI static void merit_stage(const QCtx& C, int k, double alpha, MeritPart& out) {
-    const QuadProblem& P = *C.P;
+    QLOCALS(C);
+    const QuadProblem& P = QCTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
     const double mu_b = S.mu;
@@ -890,10 +937,11 @@ struct QuadSolver {
 
   // ---- K4c ----
   OBCA_HD_NI static void update_stage(const QCtx& C, int k) {
-    const QuadProblem& P = *C.P;
+    QLOCALS(C);
+    const QuadProblem& P = QCTX_P(C);
     const ProbState& S = *C.S;
     const int N = P.N;
-    const double mu_b = S.mu, ks = C.O->kappa_sigma;
+    const double mu_b = S.mu, ks = QCTX_O(C).kappa_sigma;
     const double alpha = S.alpha, adu = S.a_du, ay = dmin_(S.alpha, S.a_du);
     const bool free_x = (k >= 1 && k <= N - 1);
     if (free_x)
@@ -937,24 +985,25 @@ struct QuadSolver {
   // phase wrappers of the generic driver (the quadcopter model has no separate item pass: its 5 box blocks are evaluated
   // inside the stage functions)
   OBCA_HD static void eval_phase(const QCtx& C, bool do_err, EvalPart& ep) {
-    const int NS = C.P->N + 1;
+    const int NS = QCTX_P(C).N + 1;
     OBCA_FOR_STAGES(k, NS) { EvalPart e1; stage_eval(C, k, do_err, true, e1); part_merge(ep, e1); }
   }
   OBCA_HD static void recover_phase(const QCtx& C, StepPart& sp) {
-    const int NS = C.P->N + 1;
+    const int NS = QCTX_P(C).N + 1;
     OBCA_FOR_STAGES(k, NS) { StepPart s1; recover_stage(C, k, s1); part_merge(sp, s1); }
   }
   OBCA_HD static void merit_phase(const QCtx& C, double alpha, MeritPart& mp) {
-    const int NS = C.P->N + 1;
+    const int NS = QCTX_P(C).N + 1;
     OBCA_FOR_STAGES(k, NS) { MeritPart m1; merit_stage(C, k, alpha, m1); part_merge(mp, m1); }
   }
   OBCA_HD static void update_phase(const QCtx& C) {
-    const int NS = C.P->N + 1;
+    const int NS = QCTX_P(C).N + 1;
     OBCA_FOR_STAGES(k, NS) update_stage(C, k);
   }
 
   OBCA_HD static void store_stage(const QCtx& C, int k, const QOutputs& o) {
-    const int N = C.P->N;
+    QLOCALS(C);
+    const int N = QCTX_P(C).N;
     for (int i = 0; i < QNX; ++i) o.xp[(size_t)QNX * k + i] = QA(X, i, k);
     if (k < N) for (int j = 0; j < QNU; ++j) o.up[(size_t)QNU * k + j] = QA(U, j, k);
     o.ts[k] = C.S->t;

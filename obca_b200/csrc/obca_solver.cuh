@@ -248,8 +248,17 @@ struct PkCtx {
 // The context lives in shared memory and is passed by reference: after every store through a double* the compiler has to
 // assume that C.W / C.ric / ... changed and reloads them.  Functions that use the accessors below therefore start with
 // OBCA_LOCALS(C), which copies the base pointers into locals (registers) once.
+#if defined(__CUDA_ARCH__)
+// the workspace is global memory and the stage slots are shared memory in every kernel: with the address space known the
+// compiler emits LDG / STG / LDS / STS (32-bit shared addresses) instead of generic accesses.  Wd and pp are shared in some
+// kernels and global in others and stay generic.
+#define OBCA_ASSUME_SPACES() __builtin_assume(__isGlobal(W_)); __builtin_assume(__isShared(ric_))
+#else
+#define OBCA_ASSUME_SPACES() (void)0
+#endif
 #define OBCA_LOCALS(C)                                                                                              \
   double* const W_ = (C).W; double* const Wd_ = (C).Wd; double* const ric_ = (C).ric; const double* const pp_ = (C).pp; \
+  OBCA_ASSUME_SPACES();                                                                                             \
   (void)W_; (void)Wd_; (void)ric_; (void)pp_
 #define WA(name, k) (W_[(size_t)(CTX_L(C).name) * CTX_L(C).NSP + (k)])
 #define WV(name, i, k) (W_[(size_t)(CTX_L(C).name + (i)) * CTX_L(C).NSP + (k)])

@@ -19,3 +19,9 @@ for sd in (1, 0):
     tot = p[:6].sum() or 1.0
     print("  phase share:", {n: round(p[i] / tot, 3) for i, n in enumerate(names)}, "cycles/iter", int(tot / max(it.sum(), 1)),
           "k1 evals/iter", round(p[7] / max(it.sum(), 1), 2), "merit/iter", round(p[6] / max(it.sum(), 1), 2))
+    L = obca_b200.lib()
+    if hasattr(L, "obca_debug_qprof"):
+        q = (C.c_ulonglong * 8)(); L.obca_debug_qprof(q); q = np.array(list(q), float)
+        n = max(q[7], 1.0) * 100.0
+        print("  sweep cycles/stage: issue+rp", int(q[0] / n), "wait", int(q[1] / n), "T", int(q[2] / n), "H", int(q[3] / n), "K", int(q[4] / n),
+              "P(loop tail)", int(q[5] / n), "forward", int(q[6] / n), "sweeps", int(q[7]))
