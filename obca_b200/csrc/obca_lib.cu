@@ -3,7 +3,7 @@
 // Kernels
 //   obca_phased.cuh          the parking solver: phase-split rounds (k_pk_eval, k_pk_sweep, k_pk_step) over all active
 //                            problems + the persistent tail kernel k_pk_tail
-//   k_quad_solve<SDV>        quadcopter model (config 4): persistent CTA per problem, block-cooperative 17x21 KKT sweep
+//   k_quad_solve<SDV>        quadcopter model (config 4): persistent CTA per problem, block-cooperative KKT sweep on FP64 tensor cores (DMMA)
 //   k_dualws<VM>             K2: one thread per (problem, stage, obstacle) micro interior-point solve.
 //   k_check                  K5: ParkingConstraints twin + strict audit, one CTA per problem.
 // There is NO CPU fallback: every compute entry point returns OBCA_ERR_NO_DEVICE without a CUDA device.

@@ -7,9 +7,9 @@
 // stage-1 values x0[9..11] (constants).
 //
 // Stage vector of the KKT sweep:  y = [ x (12) | w = previous control (4) | t | u (4) ],  17 states + 4 controls.
-// First version of this path: the stage models live in the per-CTA global workspace and the Riccati sweep is a plain
-// dense recursion run by one thread (the warp-cooperative shared-memory version of the parking model is the template
-// for the next round).
+// The stage models live in the per-CTA global workspace ([array][stage]); the Riccati sweep is block-cooperative: the three
+// matrix products of a stage run on the FP64 tensor cores (DMMA) over dense zero-padded tiles in shared memory
+// (kkt_solve_block); kkt_dense is the same elimination as a plain one-thread recursion (host emulation, tests).
 #pragma once
 #include "obca_quad_dyn_gen.cuh"
 #include "obca_quad_local.cuh"
@@ -58,7 +58,7 @@ inline QLay make_qlayout(const QuadProblem& P) {
   L.nfac = P.signed_dist ? QLocalDims<true>::NFAC : QLocalDims<false>::NFAC;
   L.LF = take(QNOB * L.nfac);
   L.QS = take(QNQ); L.qs = take(QNYV); L.JV = take(QD_NJ); L.R12 = take(QNX);
-  L.RK = take(QNU * QNSV + QNU); L.RP = take(QNX * QNSV + QNX);
+  L.RK = take(4 * 24); L.RP = take(QNX * QNSV + QNX);
   L.total = c;
   return L;
 }
@@ -517,152 +517,183 @@ struct QuadSolver {
   }
   OBCA_HD static int kkt_host(const QCtx& C) { return kkt_dense(C); }
   static constexpr int STG_N = QNQ + QNYV + QD_NJ + QNX;     // per-stage data of the sweep: Q 231 | q 21 | Jv 66 | r 12
-  static constexpr int SM_P = 0, SM_p = SM_P + QNSV * QNSV, SM_g = SM_p + QNSV, SM_T = SM_g + QNSV, SM_H = SM_T + QNSV * QNYV,
-                       SM_hv = SM_H + QNYV * QNYV, SM_K = SM_hv + QNYV, SM_s = SM_K + QNU * (QNSV + 1), SM_u = SM_s + QNSV,
-                       SM_flag = SM_u + QNU, SM_STG = SM_flag + 1 + ((SM_flag + 1) & 1), SM_Kall = SM_STG + 2 * STG_N;
-  static constexpr int KROW = QNU * (QNSV + 1);     // 72 gain entries per stage
-  OBCA_HD static int smem_doubles(int N) { return SM_Kall + N * KROW; }
+  // shared-memory layout of the tensor-core sweep (kkt_solve_block below)
+  static constexpr int V2_LDP = 20, V2_LDF = 24, V2_LDT = 24, V2_LDQ = 24, V2_LDH = 28, V2_LDK = 24;
+  static constexpr int V2_FSZ = 20 * V2_LDF, V2_QSZ = 24 * V2_LDQ;
+  static constexpr int V2_P = 0, V2_p = V2_P + 24 * V2_LDP, V2_F = V2_p + 24, V2_Q = V2_F + 2 * V2_FSZ, V2_T = V2_Q + 2 * V2_QSZ,
+                       V2_H = V2_T + 20 * V2_LDT, V2_K = V2_H + 24 * V2_LDH, V2_y = V2_K + 4 * V2_LDK, V2_flag = V2_y + 24,
+                       V2_TOTAL = V2_flag + 2;
+  static constexpr int V2_KG = 4 * V2_LDK;          // gains of one stage in global memory (dense 4 x 24)
+  static constexpr int V2_FD = 4, V2_SLOT = V2_KG + QD_NJ + QNX + 2;     // forward ring: [K 96 | Jv 66 | r 12 | pad]
+  static_assert(V2_FD * V2_SLOT <= 2 * V2_QSZ, "forward ring must fit into the Q buffers");
+  static_assert((V2_F % 2) == 0 && (V2_Q % 2) == 0 && (V2_T % 2) == 0 && (V2_H % 2) == 0 && (V2_K % 2) == 0, "16-byte alignment");
+
+  OBCA_HD static int smem_doubles(int) { return V2_TOTAL; }
   static constexpr bool KKT_BLOCK = true;
 
 #if defined(__CUDA_ARCH__)
-  // -------------------------------------------------------------------------------------------------
-  // Device version: the whole CTA cooperates on every stage of the backward sweep through shared memory (entry-parallel
-  // T = P Phi, H = Q + Phi' T, gains, value-function update), four barriers per stage; the per-stage data (Q, q, the
-  // dynamics Jacobian values and residual: 330 doubles scattered over the [array][stage] workspace) is fetched one
-  // stage ahead with 8-byte cp.async into a double buffer, so no global-memory latency sits inside a stage.  The 4x4
-  // pivot block Huu is factored (LDL', no square roots) redundantly by each of the 18 threads that then solve one
-  // column of the gain.  The forward roll-out is run by warp 0 alone (shuffle-free, two __syncwarp per stage).
-  // Same elimination as kkt_dense(); P is computed for a <= b and mirrored.  Shared layout (doubles):
-  //   P 17x17 | p 17 | g 17 | T 17x21 | H 21x21 | hv 21 | K 4x18 | s 17 | u 4 | flag | stage buffers 2 x 330 | Kall N x 72
-  // -------------------------------------------------------------------------------------------------
-  // ---- statically unrolled pieces of the sweep: Phi's sparsity (generated tables) is folded at compile time ----
-  // T(a, c) for the columns c = G, G+4, ... of one row a of P (held in registers);  G = warp index
-  template <int G>
-  __device__ static __forceinline__ void sweep_T_cols(const double (&Pr)[QNSV], const double* Jv, double* Trow) {
-    constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
-    constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
-    constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
-#pragma unroll
-    for (int c = G; c < QNYV; c += 4) {
-      double acc = 0.0;
-#pragma unroll
-      for (int q = CPT[c]; q < CPT[c + 1]; ++q) acc += Pr[JR[CIX[q]]] * Jv[CIX[q]];
-      if (c >= QIU) acc += Pr[QIW + (c - QIU)];
-      if (c == QIT) acc += Pr[QIT];
-      Trow[c] = acc;
-    }
-  }
-  // H(c1, c2) = Q(c1, c2) + Phi(:, c1)' T(:, c2) for the rows c1 = G, G+4, ... and one column c2 (T(:, c2) in registers);
-  // c2 == QNYV stands for the gradient column: hv(c1) = q(c1) + Phi(:, c1)' g
-  template <int G>
-  __device__ static __forceinline__ void sweep_H_rows(const double (&Tc)[QNSV], int c2, const double* Qs, const double* qv,
-                                                      const double* Jv, double* H, double* hv) {
-    constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
-    constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
-    constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
-#pragma unroll
-    for (int c1 = G; c1 < QNYV; c1 += 4) {
-      double acc = (c2 < QNYV) ? Qs[c1 <= c2 ? sym_idx<QNYV>(c1, c2) : sym_idx<QNYV>(c2, c1)] : qv[c1];
-#pragma unroll
-      for (int q = CPT[c1]; q < CPT[c1 + 1]; ++q) acc += Jv[CIX[q]] * Tc[JR[CIX[q]]];
-      if (c1 >= QIU) acc += Tc[QIW + (c1 - QIU)];
-      if (c1 == QIT) acc += Tc[QIT];
-      if (c2 < QNYV) H[c1 * QNYV + c2] = acc; else hv[c1] = acc;
-    }
-  }
 #ifdef OBCA_QPROF
 #define QPROF(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); qacc[i] += t_ - qt; qt = t_; } } while (0)
 #else
 #define QPROF(i) do { } while (0)
 #endif
+  // -------------------------------------------------------------------------------------------------
+  // Device version: the whole CTA cooperates on every stage of the backward sweep; the three matrix steps of a stage run on the
+  // FP64 tensor cores (mma.sync m8n8k4, SASS DMMA).
+  // All operands are dense, zero-padded tiles in shared memory:
+  //   P    24 x 20   value function of stage k+1 (rows / columns >= 17 are zero)
+  //   F    20 x 24   [ Phi | r~ ]: the dynamics Jacobian scattered to its dense positions, the identity rows of w+ = u and t+ = t,
+  //                  and the dynamics residual as column 21                       (double buffered, filled by cp.async)
+  //   Q    24 x 24   stage Hessian (upper triangle) with the stage gradient as column 21   (double buffered, cp.async)
+  //   T  = P F  (+ p on column 21)           9 tiles x 5 k-steps
+  //   H  = Q + F' T                           6 upper tiles x 5 k-steps;   column 21 of H is the gradient hv = q + Phi'(p + P r~)
+  //   K  = -Huu^{-1} [Hus | hu]               18 threads, LDL' of the 4x4 pivot block (inertia test); feed-forward as column 21
+  //   P' = Hss + Hsu K                        6 upper tiles x 1 k-step, mirrored;   column 21 is the new p
+  // so the gradient recursion rides along as one more column of the same products.  Same elimination as kkt_dense().
+  // Four barriers per stage.  The gains go to global memory ([stage][4 x 24], contiguous) and come back through a four-deep cp.async
+  // ring in the forward roll-out (warp 0), together with the Jacobian values and residuals of the stage.
+  // -------------------------------------------------------------------------------------------------
+  __device__ static __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+  }
+  // shared-memory destination of element e of the per-stage record [Q 231 | q 21 | Jv 66 | r 12]: offset inside buffer 0 and
+  // the distance to the same element in buffer 1
+  __device__ static __forceinline__ void v2_dst(int e, int& off, int& bstride) {
+    const int *jr, *jc, *hi, *hj;
+    quad_jac_tables(jr, jc, hi, hj);
+    if (e < QNQ) {
+      int i = 0, r = e;
+      while (r >= QNYV - i) { r -= QNYV - i; ++i; }
+      off = V2_Q + i * V2_LDQ + (i + r); bstride = V2_QSZ;
+    } else if (e < QNQ + QNYV) {
+      off = V2_Q + (e - QNQ) * V2_LDQ + 21; bstride = V2_QSZ;
+    } else if (e < QNQ + QNYV + QD_NJ) {
+      const int q = e - QNQ - QNYV;
+      off = V2_F + jr[q] * V2_LDF + jc[q]; bstride = V2_FSZ;
+    } else {
+      off = V2_F + (e - QNQ - QNYV - QD_NJ) * V2_LDF + 21; bstride = V2_FSZ;
+    }
+  }
+  static constexpr int QPROF_N = 7;
   __device__ __noinline__ static int kkt_solve_block(const QCtx& C) {
     QLOCALS(C);
     extern __shared__ __align__(16) double obca_dyn_smem[];      // == C.tile; named here so that the accesses are LDS / STS
 #ifdef OBCA_QPROF
     long long qacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qt = clock64();
 #endif
-    const QuadProblem& Pp = QCTX_P(C);
     ProbState& S = *C.S;
-    const int N = Pp.N;
+    const int N = QCTX_P(C).N;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
     double* const sm = obca_dyn_smem;
-    double *P = sm + SM_P, *p = sm + SM_p, *g = sm + SM_g, *T = sm + SM_T, *H = sm + SM_H, *hv = sm + SM_hv, *K = sm + SM_K,
-           *sv = sm + SM_s, *uv = sm + SM_u, *stg = sm + SM_STG, *Kall = sm + SM_Kall;
-    static constexpr int JR[QD_NJ] = OBCA_QD_J_ROW;
+    double *const Pm = sm + V2_P, *const pv = sm + V2_p, *const Tm = sm + V2_T, *const Hm = sm + V2_H, *const Km = sm + V2_K, *const yv = sm + V2_y;
     static constexpr int JC[QD_NJ] = OBCA_QD_J_COL;
     static constexpr int RPT[QNX + 1] = OBCA_QD_ROW_PTR;
-    static constexpr int CPT[QNYV + 1] = OBCA_QD_CSC_PTR;
-    static constexpr int CIX[QD_NJ] = OBCA_QD_CSC_IDX;
     const double rho = 1.0 / QCTX_O(C).dc;
     const size_t nsp = (size_t)QCTX_L(C).NSP;
     const double* const gQ = W_ + (size_t)QCTX_L(C).QS * nsp;     // QS, qs, JV, R12 are consecutive arrays of the workspace
-    auto prefetch = [&](int k, int buf, int first, int count) {   // elements [first, first+count) of stage k
-      if (k >= 0 && k < N)
-        for (int e = tid; e < count; e += nt) cp_async8(stg + buf * STG_N + first + e, gQ + (size_t)(first + e) * nsp + k);
+    double* const gK = W_ + (size_t)QCTX_L(C).RK * nsp;           // gains, [stage][4 x 24]
+    double* const gRP = W_ + (size_t)QCTX_L(C).RP * nsp;
+    // ---- per-thread constants of the stage prefetch: issued by the upper half of the warps (they have one tile of the
+    //      value-function update, the lower half two); six elements per thread when the CTA has four warps ----
+    constexpr int PFN = 6;
+    const int pf_w0 = nwarp >= 2 ? nwarp / 2 : 0;                  // first prefetching warp
+    const int pf_nt = nt - pf_w0 * 32, pf_tid = tid - pf_w0 * 32;  // prefetching threads, this thread's index among them
+    const bool pf_fast = (pf_nt * PFN >= STG_N);
+    const double* pf_src[PFN];
+    int pf_off[PFN], pf_bs[PFN];
+#pragma unroll
+    for (int i = 0; i < PFN; ++i) {
+      const int e = pf_tid + i * pf_nt;
+      const bool on = pf_tid >= 0 && e < STG_N;
+      pf_src[i] = gQ + (size_t)(on ? e : 0) * nsp;
+      pf_off[i] = -1; pf_bs[i] = 0;
+      if (on) v2_dst(e, pf_off[i], pf_bs[i]);
+    }
+    auto prefetch = [&](int k) {      // stage k -> buffer k & 1
+      if (k >= 0 && pf_tid >= 0) {
+        const int buf = k & 1;
+        if (pf_fast) {
+#pragma unroll
+          for (int i = 0; i < PFN; ++i)
+            if (pf_off[i] >= 0) cp_async8(sm + pf_off[i] + buf * pf_bs[i], pf_src[i] + k);
+        } else {
+          for (int e = pf_tid; e < STG_N; e += pf_nt) {
+            int off, bs;
+            v2_dst(e, off, bs);
+            cp_async8(sm + off + buf * bs, gQ + (size_t)e * nsp + k);
+          }
+        }
+      }
       cp_async_commit();
     };
-    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    // the (at most two) entries a <= b of the value function this thread updates in every stage
-    int pa[2] = {-1, -1}, pb[2] = {-1, -1};
-    for (int i = 0; i < 2; ++i) {
-      const int e = tid + i * nt;
-      if (e < QNP) {
-        int a = 0, off = e;
-        while (off >= QNSV - a) { off -= QNSV - a; ++a; }
-        pa[i] = a; pb[i] = a + off;
-      }
+    // rows 0..11 of P_{k+1} and p_{k+1} go to global memory for the multiplier recovery: stored during the gain phase by the
+    // warps that have no gain column (all of them but warp 0 when there are several)
+    const int rp_t0 = nwarp >= 2 ? 32 : 0, rp_nt = nt - rp_t0;
+    constexpr int RPN = 3;                                          // 216 values / 96 threads
+    const bool rp_fast = (rp_nt * RPN >= QNX * QNSV + QNX);
+    double* rp_dst[RPN];
+    int rp_src[RPN];
+#pragma unroll
+    for (int i = 0; i < RPN; ++i) {
+      const int e = (tid - rp_t0) + i * rp_nt;
+      const bool on = tid >= rp_t0 && e < QNX * QNSV + QNX;
+      rp_dst[i] = gRP + (size_t)(on ? e : 0) * nsp;
+      rp_src[i] = !on ? -1 : (e < QNX * QNSV ? V2_P + (e / QNSV) * V2_LDP + (e % QNSV) : V2_p + (e - QNX * QNSV));
     }
-    for (int e = tid; e < QNSV * QNSV; e += nt) P[e] = (e / QNSV == e % QNSV && e / QNSV < QNX) ? rho : 0.0;
-    for (int a = tid; a < QNSV; a += nt) p[a] = a < QNX ? -QA(PI, a, N - 1) : 0.0;
-    if (tid == 0) sm[SM_flag] = 1.0;
-    prefetch(N - 1, (N - 1) & 1, 0, STG_N);
+    // ---- initial contents: zeros, the constant entries of F, the terminal value function ----
+    for (int e = tid; e < V2_TOTAL; e += nt) sm[e] = 0.0;
+    __syncthreads();
+    if (tid < 2 * (QNU + 1)) {
+      const int buf = tid / (QNU + 1), j = tid % (QNU + 1);
+      double* F = sm + V2_F + buf * V2_FSZ;
+      if (j < QNU) F[(QIW + j) * V2_LDF + QIU + j] = 1.0;      // w+ = u
+      else F[QIT * V2_LDF + QIT] = 1.0;                        // t+ = t
+    }
+    for (int i = tid; i < QNX; i += nt) { Pm[i * V2_LDP + i] = rho; pv[i] = -QA(PI, i, N - 1); }
+    if (tid == 0) sm[V2_flag] = 1.0;
+    prefetch(N - 1);
     for (int k = N - 1; k >= 0; --k) {
-      const double* const Qs = stg + (k & 1) * STG_N;
-      const double* const qv = Qs + QNQ;
-      const double* const Jv = qv + QNYV;
-      const double* const r12 = Jv + QD_NJ;
-      prefetch(k - 1, (k - 1) & 1, 0, STG_N);
+      const double* const Fb = sm + V2_F + (k & 1) * V2_FSZ;
+      const double* const Qb = sm + V2_Q + (k & 1) * V2_QSZ;
+      prefetch(k - 1);
       QPROF(0);
       cp_async_wait<1>();
       __syncthreads();                     // stage data landed; P, p of stage k+1 final
       QPROF(1);
-      // rows 0..11 of P_{k+1}, p_{k+1} for the multiplier recovery (fire-and-forget stores)
-      for (int e = tid; e < QNX * QNSV; e += nt) QA(RP, e, k + 1) = P[e];
-      for (int i = tid; i < QNX; i += nt) QA(RP, QNX * QNSV + i, k + 1) = p[i];
-      // g = p + P r~ ;  T = P Phi:  lane a < 17 of every warp holds row a of P; warp w computes the columns w, w+4, ...
-      if (lane < QNSV) {
-        double Pr[QNSV];
+      // ---- T = P F (+ p on column 21): tiles idx = warp, warp + nwarp, ... of the 3 x 3 grid ----
+      for (int idx = warp; idx < 9; idx += nwarp) {
+        const int m = idx / 3, n = idx % 3;
+        double c0 = 0.0, c1 = 0.0;
+        const double* const ap = Pm + (m * 8 + gid) * V2_LDP + tig;
+        const double* const bp = Fb + tig * V2_LDF + n * 8 + gid;
 #pragma unroll
-        for (int l = 0; l < QNSV; ++l) Pr[l] = P[lane * QNSV + l];
-        for (int gi = warp; gi < 4; gi += nwarp) {
-          if (gi == 0) {
-            double acc = p[lane];
-#pragma unroll
-            for (int l = 0; l < QNX; ++l) acc += Pr[l] * r12[l];
-            g[lane] = acc;
-            sweep_T_cols<0>(Pr, Jv, T + lane * QNYV);
-          } else if (gi == 1) sweep_T_cols<1>(Pr, Jv, T + lane * QNYV);
-          else if (gi == 2) sweep_T_cols<2>(Pr, Jv, T + lane * QNYV);
-          else sweep_T_cols<3>(Pr, Jv, T + lane * QNYV);
+        for (int ks = 0; ks < 5; ++ks) dmma(c0, c1, ap[ks * 4], bp[ks * 4 * V2_LDF]);
+        const int row = m * 8 + gid;
+        if (row < 20) {
+          if (n == 2 && tig == 2) c1 += pv[row];
+          *reinterpret_cast<double2*>(Tm + row * V2_LDT + n * 8 + tig * 2) = make_double2(c0, c1);
         }
       }
       __syncthreads();
       QPROF(2);
-      // H = Q + Phi' T ; hv = q + Phi' g:  lane c2 <= 21 holds column c2 of T (21: g); warp w computes the rows w, w+4, ...
-      if (lane <= QNYV) {
-        double Tc[QNSV];
+      // ---- H = Q + F' T: the six upper tiles ----
+      for (int idx = warp; idx < 6; idx += nwarp) {
+        const int m = idx < 3 ? 0 : (idx < 5 ? 1 : 2), n = idx < 3 ? idx : (idx < 5 ? idx - 2 : 2);
+        const double2 q2 = *reinterpret_cast<const double2*>(Qb + (m * 8 + gid) * V2_LDQ + n * 8 + tig * 2);
+        double c0 = q2.x, c1 = q2.y;
+        const double* const ap = Fb + tig * V2_LDF + m * 8 + gid;
+        const double* const bp = Tm + tig * V2_LDT + n * 8 + gid;
 #pragma unroll
-        for (int l = 0; l < QNSV; ++l) Tc[l] = (lane < QNYV) ? T[l * QNYV + lane] : g[l];
-        for (int gi = warp; gi < 4; gi += nwarp) {
-          if (gi == 0) sweep_H_rows<0>(Tc, lane, Qs, qv, Jv, H, hv);
-          else if (gi == 1) sweep_H_rows<1>(Tc, lane, Qs, qv, Jv, H, hv);
-          else if (gi == 2) sweep_H_rows<2>(Tc, lane, Qs, qv, Jv, H, hv);
-          else sweep_H_rows<3>(Tc, lane, Qs, qv, Jv, H, hv);
-        }
+        for (int ks = 0; ks < 5; ++ks) dmma(c0, c1, ap[ks * 4 * V2_LDF], bp[ks * 4 * V2_LDT]);
+        *reinterpret_cast<double2*>(Hm + (m * 8 + gid) * V2_LDH + n * 8 + tig * 2) = make_double2(c0, c1);
       }
       __syncthreads();
       QPROF(3);
-      // K = -Huu^{-1} [Hus | hu]: column c = 0..17, one thread per column, each with its own LDL' of Huu
+      // ---- K = -Huu^{-1} [Hus | hu]: column c = 0..17 (17: the feed-forward, stored as column 21), one thread per column, each with its
+      //      own LDL' of the 4x4 pivot block (inertia test: all pivots positive) -- 18 short dependent chains side by side instead of one
+      //      factorisation followed by a hand-over.  Meanwhile the other warps store rows 0..11 of P_{k+1} for the multiplier recovery. ----
       if (tid <= QNSV) {
         const int c = tid;
         double Lm[QNU][QNU], dd[QNU], di[QNU];      // unit lower factor, pivots d and 1/d
@@ -671,22 +702,22 @@ struct QuadSolver {
         for (int a = 0; a < QNU; ++a) {
 #pragma unroll
           for (int b = 0; b < a; ++b) {
-            double acc = H[(QIU + a) * QNYV + QIU + b];
+            double acc = Hm[(QIU + b) * V2_LDH + QIU + a];
 #pragma unroll
             for (int l = 0; l < b; ++l) acc -= Lm[a][l] * Lm[b][l] * dd[l];
             Lm[a][b] = acc * di[b];
           }
-          double d = H[(QIU + a) * QNYV + QIU + a];
+          double d = Hm[(QIU + a) * V2_LDH + QIU + a];
 #pragma unroll
           for (int l = 0; l < a; ++l) d -= Lm[a][l] * Lm[a][l] * dd[l];
           if (!(d > 0.0)) { ok = 0; d = 1e300; }
           dd[a] = d; di[a] = __drcp_rn(d);
         }
-        if (!ok && tid == 0) sm[SM_flag] = 0.0;
+        if (!ok && tid == 0) sm[V2_flag] = 0.0;
         double y4[QNU], k4[QNU];
 #pragma unroll
         for (int a = 0; a < QNU; ++a) {
-          double acc = c < QNSV ? H[(QIU + a) * QNYV + c] : hv[QIU + a];
+          double acc = c < QNSV ? Hm[c * V2_LDH + QIU + a] : Hm[(QIU + a) * V2_LDH + 21];
 #pragma unroll
           for (int l = 0; l < a; ++l) acc -= Lm[a][l] * y4[l];
           y4[a] = acc;
@@ -698,26 +729,37 @@ struct QuadSolver {
           for (int l = a + 1; l < QNU; ++l) acc -= Lm[l][a] * k4[l];
           k4[a] = acc;
         }
+        const int col = c < QNSV ? c : 21;
+        double* const kg = gK + (size_t)k * V2_KG + col;
 #pragma unroll
-        for (int a = 0; a < QNU; ++a) { K[a * (QNSV + 1) + c] = -k4[a]; Kall[k * KROW + a * (QNSV + 1) + c] = -k4[a]; }
+        for (int a = 0; a < QNU; ++a) { Km[a * V2_LDK + col] = -k4[a]; kg[a * V2_LDK] = -k4[a]; }
+      }
+      if (tid >= rp_t0) {      // P, p of stage k+1 (unchanged since the top of the stage) for the multiplier recovery
+        if (rp_fast) {
+#pragma unroll
+          for (int i = 0; i < RPN; ++i)
+            if (rp_src[i] >= 0) rp_dst[i][k + 1] = sm[rp_src[i]];
+        } else {
+          for (int e = tid - rp_t0; e < QNX * QNSV + QNX; e += rp_nt)
+            gRP[(size_t)e * nsp + k + 1] = e < QNX * QNSV ? Pm[(e / QNSV) * V2_LDP + (e % QNSV)] : pv[e - QNX * QNSV];
+        }
       }
       __syncthreads();
       QPROF(4);
-      if (sm[SM_flag] == 0.0) { cp_async_wait<0>(); return 0; }
-      // value function of stage k (a <= b, mirrored); the barrier at the top of the next stage publishes it
-      for (int i = 0; i < 2; ++i) {
-        const int a = pa[i], b = pb[i];
-        if (a < 0) continue;
-        double v = H[a * QNYV + b];
-#pragma unroll
-        for (int l = 0; l < QNU; ++l) v += H[a * QNYV + QIU + l] * K[l * (QNSV + 1) + b];
-        P[a * QNSV + b] = v; P[b * QNSV + a] = v;
-      }
-      for (int a = tid; a < QNSV; a += nt) {
-        double acc = hv[a];
-#pragma unroll
-        for (int l = 0; l < QNU; ++l) acc += H[a * QNYV + QIU + l] * K[l * (QNSV + 1) + QNSV];
-        p[a] = acc;
+      if (sm[V2_flag] == 0.0) { cp_async_wait<0>(); return 0; }
+      // ---- value function of stage k: P = Hss + Hsu K on the six upper tiles (one DMMA each), mirrored; column 21 is p ----
+      for (int idx = warp; idx < 6; idx += nwarp) {
+        const int m = idx < 3 ? 0 : (idx < 5 ? 1 : 2), n = idx < 3 ? idx : (idx < 5 ? idx - 2 : 2);
+        const double* const hrow = Hm + (m * 8 + gid) * V2_LDH;
+        const double2 h2 = *reinterpret_cast<const double2*>(hrow + n * 8 + tig * 2);
+        double c0 = h2.x, c1 = h2.y;
+        dmma(c0, c1, hrow[QIU + tig], Km[tig * V2_LDK + n * 8 + gid]);
+        const int a = m * 8 + gid, b = n * 8 + tig * 2;
+        if (a < QNSV) {
+          if (b < QNSV && a <= b) { Pm[a * V2_LDP + b] = c0; Pm[b * V2_LDP + a] = c0; }
+          if (b + 1 < QNSV && a <= b + 1) { Pm[a * V2_LDP + b + 1] = c1; Pm[(b + 1) * V2_LDP + a] = c1; }
+          if (b + 1 == 21) pv[a] = c1;
+        }
       }
     }
     cp_async_wait<0>();
@@ -725,47 +767,63 @@ struct QuadSolver {
     QPROF(5);
     // root
     if (tid == 0) {
-      const double ptt = P[QIT * QNSV + QIT];
-      if (!(ptt > 0.0)) sm[SM_flag] = 0.0;
-      else S.dt = -p[QIT] / ptt;
+      const double ptt = Pm[QIT * V2_LDP + QIT];
+      if (!(ptt > 0.0)) sm[V2_flag] = 0.0;
+      else S.dt = -pv[QIT] / ptt;
     }
     __syncthreads();
-    if (sm[SM_flag] == 0.0) return 0;
-    // forward roll-out: warp 0 alone; Jv and r of the next stage are prefetched while the current one is applied
+    if (sm[V2_flag] == 0.0) return 0;
+    // ---- forward roll-out: warp 0 alone; gains, Jacobian values and residuals of the next stages arrive through a ring ----
     if (tid < 32) {
-      const int lane = tid;
-      constexpr int FW0 = QNQ + QNYV, FWN = QD_NJ + QNX;       // Jv | r
-      auto pf = [&](int k, int buf) {
-        if (k < N)
-          for (int e = lane; e < FWN; e += 32) cp_async8(stg + buf * STG_N + FW0 + e, gQ + (size_t)(FW0 + e) * nsp + k);
+      double* const ring = sm + V2_Q;
+      const double* const gJ = gQ + (size_t)(QNQ + QNYV) * nsp;       // Jv | r
+      auto pf = [&](int k) {
+        if (k < N) {
+          double* const slot = ring + (k % V2_FD) * V2_SLOT;
+          for (int i = lane; i < V2_KG / 2; i += 32) cp_async16(slot + 2 * i, gK + (size_t)k * V2_KG + 2 * i);
+          for (int e = lane; e < QD_NJ + QNX; e += 32) cp_async8(slot + V2_KG + e, gJ + (size_t)e * nsp + k);
+        }
         cp_async_commit();
       };
-      if (lane < QNSV) sv[lane] = (lane == QIT) ? S.dt : 0.0;
-      pf(0, 0);
-      __syncwarp();
-      for (int k = 0; k < N; ++k) {
-        pf(k + 1, (k + 1) & 1);
-        if (lane < QNU) {
-          const double* kr = Kall + k * KROW + lane * (QNSV + 1);
-          double acc = kr[QNSV];
+      if (lane < 24) yv[lane] = (lane == QIT) ? S.dt : 0.0;
 #pragma unroll
-          for (int c = 0; c < QNSV; ++c) acc += kr[c] * sv[c];
-          uv[lane] = acc;
-          QA(dU, lane, k) = acc;
-        }
-        cp_async_wait<1>();
+      for (int a = 0; a < V2_FD - 1; ++a) pf(a);
+      __syncwarp();
+      const int ua = lane >> 3, uj = lane & 7;
+      // row `lane` of the dynamics Jacobian (CSR): first entry, number of entries (at most 9), columns -- in registers
+      constexpr int RMAX = 9;
+      const int rq0 = lane < QNX ? RPT[lane] : 0, rnq = lane < QNX ? RPT[lane + 1] - RPT[lane] : 0;
+      int rcol[RMAX];
+#pragma unroll
+      for (int i = 0; i < RMAX; ++i) rcol[i] = i < rnq ? JC[rq0 + i] : 0;
+      for (int k = 0; k < N; ++k) {
+        pf(k + V2_FD - 1);
+        cp_async_wait<V2_FD - 1>();
         __syncwarp();
-        const double* const Jv = stg + (k & 1) * STG_N + FW0;
+        const double* const slot = ring + (k % V2_FD) * V2_SLOT;
+        const double* const kr = slot + ua * V2_LDK;
+        // u = kf + K s: eight lanes per control, three terms each, butterfly sum
+        double part = kr[uj] * yv[uj] + kr[uj + 8] * yv[uj + 8];
+        if (uj == 0) part += kr[16] * yv[16];
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        const double uval = part + kr[21];
+        if (uj == 0) { yv[QIU + ua] = uval; QA(dU, ua, k) = uval; }
+        __syncwarp();
+        const double* const Jv = slot + V2_KG;
         const double* const r12 = Jv + QD_NJ;
         double snv = 0.0;
         if (lane < QNX) {
           snv = r12[lane];
-          for (int q = RPT[lane]; q < RPT[lane + 1]; ++q) { const int c = JC[q]; snv += Jv[q] * (c < QNSV ? sv[c] : uv[c - QIU]); }
+#pragma unroll
+          for (int i = 0; i < RMAX; ++i)
+            if (i < rnq) snv += Jv[rq0 + i] * yv[rcol[i]];
           if (k + 1 < N) QA(dX, lane, k + 1) = snv; else S.eNq[lane] = snv;
         }
         __syncwarp();
-        if (lane < QNX) sv[lane] = snv;
-        else if (lane < QNX + QNU) sv[lane] = uv[lane - QNX];
+        if (lane < QNX) yv[lane] = snv;
+        else if (lane < QNX + QNU) yv[lane] = yv[QIU + (lane - QNX)];      // w+ = u
         __syncwarp();
       }
       cp_async_wait<0>();
@@ -775,7 +833,7 @@ struct QuadSolver {
     __syncthreads();
 #ifdef OBCA_QPROF
     QPROF(6);
-    if (threadIdx.x == 0) { for (int i = 0; i < 7; ++i) atomicAdd(&g_qprof[i], (unsigned long long)qacc[i]); atomicAdd(&g_qprof[7], 1ull); }
+    if (threadIdx.x == 0) { for (int i = 0; i < QPROF_N; ++i) atomicAdd(&g_qprof[i], (unsigned long long)qacc[i]); atomicAdd(&g_qprof[7], 1ull); }
 #endif
     return 1;
   }
