@@ -85,6 +85,36 @@ def test_gpu_quadcopter_config4(variant):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [20, 40, 70, 100])
+def test_gpu_tensor_core_sweep_equals_host_recursion(N):
+    """The device sweep (dense zero-padded tiles, DMMA products, kkt_solve_block) against the plain one-thread recursion of the same
+    elimination (kkt_dense, host build of the same sources) -- one, two, three and four warps per problem (N + 1 rounded up to 32
+    threads): the first Newton step and the iterate after five iterations agree up to round-off x the terminal penalty 1/dc (as in
+    test_kernel_sources_vs_oracle, dc = 1e-6 for this comparison); then the full solve converges to a KKT point that passes the verbatim checker."""
+    import emul
+    import obca_b200
+    from obca_b200 import quadcopter
+    B = 3
+    sc = scenarios.quadcopter_batch(B, N, 2)
+    for variant in ("sd", "d"):
+        for it, tol in ((1, 1e-8), (5, 1e-4)):
+            oe = emul.default_opts(); oe.max_iter = it; oe.dc = 1e-6
+            og = obca_b200.default_opts(); og.max_iter = it; og.dc = 1e-6
+            re_ = emul.quad_solve_batch(sc, variant, oe)
+            rg = quadcopter.quadcopter_solve_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"], 1.0, 1 if variant == "sd" else 0, og)
+            for k in ("xp", "up", "ts", "lp"):
+                scale = 1.0 + np.abs(re_[k]).max()
+                assert np.abs(rg[k] - re_[k]).max() < tol * scale, (variant, it, k, np.abs(rg[k] - re_[k]).max())
+        r = quadcopter.quadcopter_solve_batch(sc["x0"], sc["xF"], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"], 1.0, 1 if variant == "sd" else 0)
+        assert (r["exitflag"] >= 1).all()
+        feas, _ = quadcopter.check_quadcopter_batch(r["xp"], r["up"], r["ts"], sc["x0"], sc["xF"], sc["Ts"], r["lp"], sc["obs"], sc["R"])
+        assert feas[r["exitflag"] == 1].all()
+        i = int(np.argmax(r["exitflag"] == 1))
+        e, _ = _cert(sc, i, N, variant, r["xp"][i], r["up"][i], r["ts"][i], r["lp"][i], r["slack"][i])
+        assert e["E0"] < 1e-4
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", ["quad_sd_p0", "quad_d_p1"])
 def test_gpu_quadcopter_matches_oracle_golden(case):
     """BASELINE config 4 (N = 100): the library's solution against the golden of the IPOPT stand-in on the restated reference NLP

@@ -15,7 +15,7 @@ o = obca_b200.default_opts()
 if len(sys.argv) > 3:
     o.max_iter = int(sys.argv[3])
 if what == "quad":
-    sc = scenarios.quadcopter_batch(B, 40, 2)
+    sc = scenarios.quadcopter_batch(B, int(os.environ.get("QUAD_N", "40")), 2)      # N = 40: two warps, N = 100: four (the fast paths)
     r = quadcopter.quadcopter_solve_batch(sc["x0"], sc["xF"], sc["N"], sc["Ts"], sc["R"], sc["obs"], sc["xWS"], 1.0, 1, o)
     f, _ = quadcopter.check_quadcopter_batch(r["xp"], r["up"], r["ts"], sc["x0"], sc["xF"], sc["Ts"], r["lp"], sc["obs"], sc["R"])
 else:
