@@ -346,6 +346,11 @@ static int launch_phased(DevCtx& c, const ParkProblem& P, const IpmOpts& O, cons
   if (occ_t < 1) occ_t = 1;
   if (occ_e < 1) occ_e = 1;
   if (occ_s < 1) occ_s = 1;
+  {   // development: fewer resident CTAs per SM than the occupancy allows (how much do co-resident CTAs slow each other down?)
+    const int oe = env_int("OBCA_EVAL_OCC", occ_e), os = env_int("OBCA_STEP_OCC", occ_s);
+    if (oe >= 1 && oe < occ_e) occ_e = oe;
+    if (os >= 1 && os < occ_s) occ_s = os;
+  }
   const int tail_cap = c.sms * occ_t, eval_cap = c.sms * occ_e, step_cap = c.sms * occ_s;
   int rc = ensure((void**)&c.W, &c.Wbytes, (size_t)B * L.total * L.NSP * sizeof(double));
   if (rc) return rc;
