@@ -145,3 +145,49 @@ def test_dist_variant_has_a_second_local_minimum():
     lay = r["nlp0"].lay
     assert r["status"][0] == 1 and float(fx["f"]) < r["nlp0"].f(r["z"][0]) - 0.05
     assert np.abs(fx["z"][:4 * (N + 1)] - r["z"][0][:4 * (N + 1)]).max() > 1.0
+
+
+# ----------------------------------------------------------------------------------------------------------
+# quadcopter (QuadcopterSignedDist.jl / QuadcopterDist.jl): independent-solver pin with active obstacle rows
+# ----------------------------------------------------------------------------------------------------------
+def quad_problem():
+    """tests/golden/make_slsqp_quad.py: start / goal pair 5 of quadcopter_batch(16, 12, 2), N = 12; four ball-against-box rows active."""
+    N, i = 12, 5
+    sc = scenarios.quadcopter_batch(16, N, 2)
+    return sc, N, i
+
+
+@pytest.mark.parametrize("variant", ["sd", "d"])
+def test_quadcopter_slsqp_fixture_vs_interior_point_and_kernel_sources(variant):
+    """SLSQP (active-set SQP; shares only the NLP callbacks) started 1e-3 away from the interior-point solution returns to a KKT point
+    (reference-formulation certificate) with the same objective (1e-7 relative) and the same time scale (1e-9); the kernels' host build
+    reaches the same objective (3e-5 relative at the default tol = 1e-5) and time scale (1e-5).  The primal trajectory itself is NOT
+    pinned by this problem: the objective is flat across the corridor between the boxes (points 0.13 m apart differ by 1e-5 relative in f),
+    and from the far start SLSQP finds another route altogether (f = 20.153 against 23.556, fixture *_far) -- the same
+    non-convexity finding as for ParkingDist."""
+    from oracle import kkt_check
+    from oracle.quadcopter_nlp import build_quadcopter_nlp
+    from oracle.quadcopter_solve import solve_quadcopter
+    sc, N, i = quad_problem()
+    g = np.load(os.path.join(HERE, "golden", "_slsqp", f"slsqp_quad_{variant}_local.npz"))
+    nlp = build_quadcopter_nlp(sc["x0"][i], sc["xF"][i], N, sc["Ts"], sc["R"], sc["obs"], variant)
+    lay = nlp.lay
+    e = kkt_check.kkt_certificate(nlp, g["z"])
+    assert e["constr_viol"] < 1e-7 and e["E0"] < 5e-5
+    gg = nlp.g(g["z"])
+    assert int(((gg - nlp.gL) < 1e-6).sum()) == 4                      # four distance rows are active
+    out, res, _ = solve_quadcopter(sc["x0"][i], sc["xF"][i], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"][i], 1.0, variant,
+                                   ipm_ref.IpmOptions(tol=1e-9, max_iter=3000), engine="compiled")
+    assert res.status == 1
+    ts_s = lay.unpack(g["z"])[2]
+    assert abs(nlp.f(res.z) - float(g["f"])) < 1e-7 * abs(float(g["f"]))
+    assert np.abs(out[2] - ts_s).max() < 1e-9
+    sub = {k: (v[i:i + 1] if isinstance(v, np.ndarray) and v.shape[:1] == (16,) else v) for k, v in sc.items()}
+    sub["B"] = 1
+    r = emul.quad_solve_batch(sub, variant)
+    assert r["status"][0] == 1
+    zk = lay.pack(r["xp"][0], r["up"][0], r["ts"][0], r["lp"][0], r["slack"][0] if variant == "sd" else None)
+    assert abs(nlp.f(zk) - float(g["f"])) < 3e-5 * abs(float(g["f"]))
+    assert np.abs(r["ts"][0] - ts_s).max() < 1e-5
+    far = np.load(os.path.join(HERE, "golden", "_slsqp", f"slsqp_quad_{variant}_far.npz"))
+    assert float(far["f"]) < float(g["f"]) - 1.0 and float(far["viol"]) < 1e-6          # another local minimum, recorded

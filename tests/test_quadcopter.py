@@ -153,3 +153,24 @@ def test_gpu_quadcopter_full_config4_batch():
     for i in np.flatnonzero(r["exitflag"] == 1)[:3]:
         e, _ = _cert(sc, int(i), N, "sd", r["xp"][i], r["up"][i], r["ts"][i], r["lp"][i], r["slack"][i])
         assert e["E0"] < 1e-4 and e["constr_viol"] < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["sd", "d"])
+def test_gpu_quadcopter_objective_equals_independent_sqp(variant):
+    """The SLSQP fixture of tests/golden/make_slsqp_quad.py (N = 12, four active ball-against-box rows; an active-set SQP solver that
+    shares only the NLP callbacks with the oracle): the library reaches the same objective (3e-5 relative at tol = 1e-5) and the same
+    time scale (1e-5), and its point is a KKT point of the reference NLP.  (The trajectory itself is not pinned by this problem -- the
+    objective is flat across the corridor between the boxes, tests/test_oracle_cross_solver.py.)"""
+    import os
+    from obca_b200 import quadcopter
+    N, i = 12, 5
+    sc = scenarios.quadcopter_batch(16, N, 2)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "_slsqp", f"slsqp_quad_{variant}_local.npz"))
+    r = quadcopter.quadcopter_solve_batch(sc["x0"][i:i + 1], sc["xF"][i:i + 1], N, sc["Ts"], sc["R"], sc["obs"], sc["xWS"][i:i + 1], 1.0,
+                                          1 if variant == "sd" else 0)
+    assert r["exitflag"][0] == 1
+    e, nlp = _cert(sc, i, N, variant, r["xp"][0], r["up"][0], r["ts"][0], r["lp"][0], r["slack"][0])
+    assert e["E0"] < 1e-4 and e["constr_viol"] < 1e-4
+    assert abs(e["f"] - float(g["f"])) < 3e-5 * abs(float(g["f"]))
+    assert np.abs(r["ts"][0] - nlp.lay.unpack(g["z"])[2]).max() < 1e-5
