@@ -127,3 +127,22 @@ function constrSatisfaction(x, u, timeScale, x0, xF, Ts, lambda, ob1, ob2, ob3, 
                C_NULL, feas, C_NULL)
     return rc == 0 && feas[] == 1
 end
+
+
+# ---- warm-start producer (include/obca_planner.h -> libobca_planner.so: Hybrid A* + veloSmooth + main.jl:215-248) ------------------
+# Replaces hybrid_a_star.calc_hybrid_astar_path (main.jl:217) and the warm-start extraction (main.jl:222-248) for a Julia that can
+# no longer run the reference's 0.5/0.6 planner files.  scenario: 0 = "backwards", 1 = "parallel" (main.jl:36).
+const LIBOBCA_PLANNER = get(ENV, "LIBOBCA_PLANNER", joinpath(@__DIR__, "..", "obca_b200", "planner", "libobca_planner.so"))
+
+function plan_warm_start(x0::AbstractVector, xF::AbstractVector, scenario::Int; Ts::Float64 = 0.0, L::Float64 = 2.7, sampleN::Int = 3)
+    cap = 1024
+    rx = zeros(cap); ry = zeros(cap); ryaw = zeros(cap); xWS = zeros(4 * cap); uWS = zeros(2 * cap); N = Ref{Cint}(0)
+    rc = ccall((:obca_plan_warmstart, LIBOBCA_PLANNER), Cint,
+               (Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Cdouble, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                Ptr{Cdouble}, Ref{Cint}),
+               Float64.(x0[1:3]), Float64.(xF[1:3]), scenario, Ts, L, sampleN, cap, rx, ry, ryaw, xWS, uWS, N)
+    rc == 1 && return nothing                                   # no path (the reference prints "Error: Cannot find path")
+    rc == 0 || error("obca_plan_warmstart: ", rc)
+    n = Int(N[])
+    return (rx = rx[1:n+1], ry = ry[1:n+1], ryaw = ryaw[1:n+1], xWS = reshape(xWS[1:4*(n+1)], n + 1, 4), uWS = reshape(uWS[1:2*n], n, 2), N = n)
+end

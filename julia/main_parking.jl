@@ -8,6 +8,7 @@
 # summary and -- instead of the PyPlot animation of plotTraj.jl -- exports the trajectories as CSV.
 #
 #   julia julia/main_parking.jl DIR            (DIR as written by export_warmstart; results go to DIR/out_*.csv)
+# Without DIR/xWS.csv (export_warmstart ... --no-plan) the warm start is planned here by libobca_planner.so (include/obca_planner.h).
 #
 # NOT executed in this repository's image (no Julia): written against include/obca.h and the tested ctypes twin obca_b200/_lib.py.
 using DelimitedFiles
@@ -42,9 +43,17 @@ function main(dir)
     XYbounds = vec(readmat(dir, "XYbounds.csv"))
     vObMPC = Int.(readmat(dir, "vOb.csv"))                                             # half-space counts (main.jl:101)
     AOb = readmat(dir, "A.csv"); bOb = readmat(dir, "b.csv")                           # obstHrep (main.jl:252)
-    path = readdlm(joinpath(dir, "path.csv"), ',', Float64; skipstart = 1)
-    rx_sampled = path[:, 1]; ry_sampled = path[:, 2]; ryaw_sampled = path[:, 3]        # main.jl:237-239
-    xWS = readmat(dir, "xWS.csv"); uWS = readmat(dir, "uWS.csv")                       # main.jl:247-248
+    if isfile(joinpath(dir, "xWS.csv"))
+        path = readdlm(joinpath(dir, "path.csv"), ',', Float64; skipstart = 1)
+        rx_sampled = path[:, 1]; ry_sampled = path[:, 2]; ryaw_sampled = path[:, 3]    # main.jl:237-239
+        xWS = readmat(dir, "xWS.csv"); uWS = readmat(dir, "uWS.csv")                   # main.jl:247-248
+    else
+        # scenario files only (`export_warmstart DIR SCENARIO --no-plan`): plan here, with the native producer of libobca_planner.so
+        # (Hybrid A* + veloSmooth + down-sampling = main.jl:215-248); the horizon N is the planner's (main.jl:244)
+        w = plan_warm_start(vec(x0), vec(xF), Int(get(s, "scenario", 0.0)); Ts = Ts, L = L)
+        w === nothing && error("Hybrid A*: cannot find a path")
+        rx_sampled, ry_sampled, ryaw_sampled, xWS, uWS, N = w.rx, w.ry, w.ryaw, w.xWS, w.uWS, w.N
+    end
 
     println("Parking using Distance Approach (A* warm start)")                         # main.jl:256-265
     xp20, up20, scaleTime20, exitflag20, time20, lp20, np20 =

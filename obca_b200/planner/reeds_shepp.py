@@ -43,7 +43,7 @@ def pi_2_pi(a: float) -> float:        # reeds_shepp.jl:47-56
 
 
 def polar(x: float, y: float) -> Tuple[float, float]:
-    return math.hypot(x, y), math.atan2(y, x)
+    return math.sqrt(x * x + y * y), math.atan2(y, x)      # (not math.hypot: the native planner computes the same expression)
 
 
 def mod2pi(x: float) -> float:         # reeds_shepp.jl:146-156 (Julia mod: result has the sign of the divisor, i.e. in [0, 2 pi))

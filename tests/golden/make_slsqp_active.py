@@ -12,6 +12,8 @@ projection of the starting point into the bounds (kappa_1 = kappa_2 = 1e-2: lamb
 |A' lambda|^2 == 1 have a zero gradient and SLSQP's LSQ subproblem is singular).  Output:
 tests/golden/_slsqp/slsqp_active_<variant>.npz (z of SLSQP, objective, constraint violation).   Run:  PYTHONPATH=. python
 tests/golden/make_slsqp_active.py sd d d_local      (about an hour per variant on 4 cores)
+Config 3 (parallel parking, four obstacles incl. the triangle-free ragged rows 4/4/4/4 of main.jl:154-162): tags p4_sd, p4_d,
+p4_sd_local, p4_d_local -> slsqp_active_p4_*.npz.
 
 Findings (committed fixtures):
   sd       SLSQP stops (status 8: no further descent at its numerical limit, |c| 3e-14) at f = 6.134674280 -- the interior-point
@@ -34,9 +36,14 @@ from oracle.parking_nlp import build_parking_nlp, initial_point
 from oracle.parking_solve import solver_view
 
 N, PROBLEM = 20, 10
+PARALLEL_PROBLEM = 1      # config 3 (parallel parking, the reference's four obstacles): start pose 1 of parallel_parking_batch(16, N, 1, 4)
 
 
-def problem():
+def problem(scenario="reverse"):
+    if scenario == "parallel4":
+        sc = scenarios.parallel_parking_batch(16, N, 1, 4)
+        sc["Ts"] = sc["Ts"] * 80 / N
+        return sc, PARALLEL_PROBLEM
     sc = scenarios.reverse_parking_batch(16, N, 0)
     sc["Ts"] = sc["Ts"] * 80 / N
     return sc, PROBLEM
@@ -47,10 +54,12 @@ def dense(M):
 
 
 def main(variants):
-    sc, i = problem()
     for tag in variants:
-        variant, local = tag.split("_")[0], tag.endswith("_local")
-        nlp = solver_view(build_parking_nlp(sc["x0"][i], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], 3, sc["vOb"], sc["A"], sc["b"],
+        scenario = "parallel4" if tag.startswith("p4") else "reverse"
+        sc, i = problem(scenario)
+        parts = tag.split("_")
+        variant, local = parts[1] if scenario == "parallel4" else parts[0], tag.endswith("_local")
+        nlp = solver_view(build_parking_nlp(sc["x0"][i], sc["xF"], N, sc["Ts"], sc["L"], sc["ego"], sc["XYbounds"], sc["nOb"], sc["vOb"], sc["A"], sc["b"],
                                             sc["rx"][i], sc["ry"][i], sc["ryaw"][i], 0, variant))
         lay = nlp.lay
         gL, gU = nlp.gL, nlp.gU
@@ -58,7 +67,7 @@ def main(variants):
         cons = [dict(type="eq", fun=nlp.cE, jac=lambda z: dense(nlp.JE(z))),
                 dict(type="ineq", fun=lambda z: np.concatenate([(nlp.g(z) - gL)[mL], (gU - nlp.g(z))[mU]]),
                      jac=lambda z: np.vstack([dense(nlp.JI(z))[mL], -dense(nlp.JI(z))[mU]]))]
-        lWS, nWS, _ = dualmultws(N, 3, sc["vOb"], sc["A"], sc["b"], sc["rx"][i], sc["ry"][i], sc["ryaw"][i], sc["ego"])
+        lWS, nWS, _ = dualmultws(N, sc["nOb"], sc["vOb"], sc["A"], sc["b"], sc["rx"][i], sc["ry"][i], sc["ryaw"][i], sc["ego"])
         from oracle.ipm_ref import _push
         z0 = _push(initial_point(lay, sc["xWS"][i], sc["uWS"][i], lWS, nWS), nlp.zL, nlp.zU, 1e-2, 1e-2)
         if local:
