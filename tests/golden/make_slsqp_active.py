@@ -12,8 +12,10 @@ projection of the starting point into the bounds (kappa_1 = kappa_2 = 1e-2: lamb
 |A' lambda|^2 == 1 have a zero gradient and SLSQP's LSQ subproblem is singular).  Output:
 tests/golden/_slsqp/slsqp_active_<variant>.npz (z of SLSQP, objective, constraint violation).   Run:  PYTHONPATH=. python
 tests/golden/make_slsqp_active.py sd d d_local      (about an hour per variant on 4 cores)
-Config 3 (parallel parking, four obstacles incl. the triangle-free ragged rows 4/4/4/4 of main.jl:154-162): tags p4_sd, p4_d,
-p4_sd_local, p4_d_local -> slsqp_active_p4_*.npz.
+Config 3 (parallel parking, the reference's four obstacles, main.jl:154-162; start pose 1 of parallel_parking_batch(16, N, 1, 4)): tags
+p4_sd, p4_d, p4_sd_local, p4_d_local -> slsqp_active_p4_*.npz (one to two minutes each).
+  p4_sd_local / p4_d_local   return to the interior-point solutions: primal 3e-5 / 4e-5, lambda and mu on the two active blocks 6e-7
+  p4_sd / p4_d               from the far start: other local minima (f = 0.87854 against 0.88066; 21.886 against 21.916), 0.8 m / 2.4 m away
 
 Findings (committed fixtures):
   sd       SLSQP stops (status 8: no further descent at its numerical limit, |c| 3e-14) at f = 6.134674280 -- the interior-point

@@ -536,24 +536,26 @@ def test_returned_time_is_the_solve_alone(P, cfg2):
         assert np.array_equal(r[key], r2[key]), key       # the library's own DualMultWS == the public one
 
 
-@pytest.mark.parametrize("tag", ["sd", "d_local"])
+@pytest.mark.parametrize("tag", ["sd", "d_local", "p4_sd_local", "p4_d_local"])
 def test_gpu_solution_equals_independent_sqp_with_active_rows(P, tag):
     """The library against scipy's SLSQP (fixtures of tests/golden/make_slsqp_active.py) on a config-2 start pose whose optimum has
-    ACTIVE OBCA distance rows (N = 20; 5 blocks SignedDist, 8 blocks Dist): primal point to 5e-5, and the dual outputs lp, np --
-    unique on the active blocks -- to 5e-4 there."""
+    ACTIVE OBCA distance rows (N = 20; 5 blocks SignedDist, 8 blocks Dist) and on a config-3 one (parallel parking, four obstacles, tags
+    p4_*): primal point to 5e-5 (config 3: 1e-4), and the dual outputs lp, np -- unique on the active blocks -- to 5e-4 there."""
     import obca_b200
     from test_oracle_cross_solver import active_blocks, active_problem
     from oracle.parking_nlp import Layout
-    variant = tag.split("_")[0]
+    p4 = tag.startswith("p4_")
+    variant = tag.split("_")[1 if p4 else 0]
     fx = np.load(os.path.join(HERE, "golden", "_slsqp", f"slsqp_active_{tag}.npz"))
-    sc, N = active_problem()
+    sc, N = active_problem("parallel4" if p4 else "reverse")
     o = obca_b200.default_opts(); o.tol = 1e-8; o.mu_min = 1e-9
     r = solve(P, sc, sd=1 if variant == "sd" else 0, lWS=fx["lWS"][None], nWS=fx["nWS"][None], opts=o)
     assert r["exitflag"][0] == 1
-    xs, us, ts_s, ls, ns = Layout(N, 3, sc["vOb"], 0, variant).unpack(fx["z"])[:5]
-    assert np.abs(r["xp"][0] - xs).max() < 5e-5 and np.abs(r["up"][0] - us).max() < 5e-5 and np.abs(r["ts"][0] - ts_s).max() < 5e-5
+    xs, us, ts_s, ls, ns = Layout(N, sc["nOb"], sc["vOb"], 0, variant).unpack(fx["z"])[:5]
+    tolp = 1e-4 if p4 else 5e-5
+    assert np.abs(r["xp"][0] - xs).max() < tolp and np.abs(r["up"][0] - us).max() < tolp and np.abs(r["ts"][0] - ts_s).max() < tolp
     blocks = active_blocks(sc, N, variant, xs)
-    assert sum(len(a) for _, a, _ in blocks) >= 5
+    assert sum(len(a) for _, a, _ in blocks) >= (2 if p4 else 5)
     for j, act, rows in blocks:
         assert np.abs(r["lp"][0][rows][:, act] - ls[rows][:, act]).max() < 5e-4
         assert np.abs(r["np"][0][4 * j:4 * j + 4][:, act] - ns[4 * j:4 * j + 4][:, act]).max() < 5e-4
