@@ -40,6 +40,12 @@ int obca_scenario_obstacle_points(int scenario, int cap, double* ox, double* oy,
 int obca_plan_warmstart(const double* x0, const double* xF, int scenario, double Ts, double L, int sampleN, int cap, double* rx, double* ry,
                         double* ryaw, double* xWS, double* uWS, int* N_out);
 
+/* The same for B start poses (x0: 3 x B column-major) towards one goal -- the randomised sweeps of main.jl:165-168 --, on nthreads host
+ * threads (<= 0: hardware concurrency).  Problem i writes N[i], status[i] (OBCA_PLAN_OK / NO_PATH / CAPACITY) and, with the stride cap,
+ * rx / ry / ryaw [i*cap ..], xWS [i*4*cap ..] as (N[i]+1) x 4 column-major, uWS [i*2*cap ..] as N[i] x 2 column-major. */
+int obca_plan_warmstart_batch(int B, const double* x0, const double* xF, int scenario, double Ts, double L, int sampleN, int cap, int nthreads,
+                              double* rx, double* ry, double* ryaw, double* xWS, double* uWS, int* N, int* status);
+
 /* Reeds-Shepp shortest path length between two poses for maximum curvature maxc (reeds_shepp.jl:79-96); used by tests. */
 double obca_reeds_shepp_length(double sx, double sy, double syaw, double gx, double gy, double gyaw, double maxc);
 

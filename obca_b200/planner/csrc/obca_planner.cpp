@@ -10,7 +10,9 @@
 #include <functional>
 #include <limits>
 #include <queue>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <unordered_map>
 #include <unordered_set>
@@ -697,6 +699,28 @@ int obca_plan_warmstart(const double* x0, const double* xF, int scenario, double
     const int i = k * sampleN;
     uWS[k] = delta[i]; uWS[N + k] = a[i];
   }
+  return OBCA_PLAN_OK;
+}
+
+int obca_plan_warmstart_batch(int B, const double* x0, const double* xF, int scenario, double Ts, double L, int sampleN, int cap, int nthreads,
+                              double* rx, double* ry, double* ryaw, double* xWS, double* uWS, int* N, int* status) {
+  if (B < 0 || !x0 || !xF || !rx || !ry || !ryaw || !xWS || !uWS || !N || !status || cap < 2) return OBCA_PLAN_BAD_ARG;
+  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > B) nthreads = B > 0 ? B : 1;
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= B) break;
+      status[i] = obca_plan_warmstart(x0 + 3 * (size_t)i, xF, scenario, Ts, L, sampleN, cap, rx + (size_t)i * cap, ry + (size_t)i * cap,
+                                      ryaw + (size_t)i * cap, xWS + (size_t)i * 4 * cap, uWS + (size_t)i * 2 * cap, N + i);
+    }
+  };
+  vector<std::thread> pool;
+  for (int t = 1; t < nthreads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
   return OBCA_PLAN_OK;
 }
 

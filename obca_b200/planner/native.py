@@ -31,6 +31,8 @@ def lib():
         L.obca_scenario_obstacle_points.argtypes = [i, i, p, p, p]
         L.obca_plan_warmstart.restype = i
         L.obca_plan_warmstart.argtypes = [p, p, i, d, d, i, i, p, p, p, p, p, p]
+        L.obca_plan_warmstart_batch.restype = i
+        L.obca_plan_warmstart_batch.argtypes = [i, p, p, i, d, d, i, i, i] + [p] * 7
         L.obca_reeds_shepp_length.restype = d
         L.obca_reeds_shepp_length.argtypes = [d] * 7
         _lib = L
@@ -80,6 +82,28 @@ def plan_warm_start(x0, xF, scenario="backwards", Ts=None, L=2.7, sampleN=3, cap
     Ts = Ts or (0.6 if scenario == "backwards" else 0.9) / 3 * sampleN
     return dict(rx=rx[:n + 1].copy(), ry=ry[:n + 1].copy(), ryaw=ryaw[:n + 1].copy(), xWS=xWS[:4 * (n + 1)].reshape(4, n + 1).T.copy(),
                 uWS=uWS[:2 * n].reshape(2, n).T.copy(), N=n, Ts=Ts)
+
+
+def plan_batch(x0s, xF, scenario="backwards", workers=0, Ts=None, L=2.7, sampleN=3, cap=512):
+    """Hybrid A* warm starts for many start poses on a pool of host threads (the randomised sweeps of main.jl:165-168); same list of
+    dictionaries as obca_b200.planner.warmstart.plan_batch (None where no path was found)."""
+    x0s = np.ascontiguousarray(np.asarray(x0s, float)[:, :3]); B = x0s.shape[0]
+    xF = np.ascontiguousarray(np.asarray(xF, float)[:3])
+    rx = np.zeros((B, cap)); ry = np.zeros((B, cap)); ryaw = np.zeros((B, cap)); xWS = np.zeros((B, 4 * cap)); uWS = np.zeros((B, 2 * cap))
+    N = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+    rc = lib().obca_plan_warmstart_batch(B, _p(x0s), _p(xF), SCENARIOS[scenario], float(Ts or 0.0), float(L), int(sampleN), cap, int(workers),
+                                         _p(rx), _p(ry), _p(ryaw), _p(xWS), _p(uWS), _p(N), _p(st))
+    if rc or (st > 1).any():
+        raise PlannerError(f"obca_plan_warmstart_batch: {rc}, status {st[st > 1][:5]}")
+    Ts = Ts or (0.6 if scenario == "backwards" else 0.9) / 3 * sampleN
+    out = []
+    for i in range(B):
+        if st[i]:
+            out.append(None); continue
+        n = int(N[i])
+        out.append(dict(rx=rx[i, :n + 1].copy(), ry=ry[i, :n + 1].copy(), ryaw=ryaw[i, :n + 1].copy(), xWS=xWS[i, :4 * (n + 1)].reshape(4, n + 1).T.copy(),
+                        uWS=uWS[i, :2 * n].reshape(2, n).T.copy(), N=n, Ts=Ts))
+    return out
 
 
 def reeds_shepp_length(sx, sy, syaw, gx, gy, gyaw, maxc):

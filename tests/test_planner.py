@@ -285,3 +285,14 @@ def test_julia_runner_data_flow_through_the_ctypes_twin(tmp_path):
         assert ef == 1 and t > 0
         assert obca_b200.ParkingConstraints(e["x0"], e["xF"], e["N"], e["Ts"], e["L"], e["ego"], e["XYbounds"], e["nOb"], e["vOb"], e["A"], e["b"],
                                             xp, up, lp, np_, ts, e["fixTime"], sd) == 1
+
+
+@pytest.mark.gpu
+def test_randomised_sweep_planned_natively_and_solved_in_horizon_groups():
+    """main.jl:165-168 as a batch (examples/sweep_parking.py): 48 random start poses planned by libobca_planner.so on host threads,
+    grouped by the planner's horizon, solved group by group on the GPU; every converged trajectory passes the reference's checker."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import sweep_parking
+    o = sweep_parking.sweep(48, "backwards", 3)
+    assert o["planned"] == 48 and o["groups"] >= 5
+    assert o["converged"] >= 44 and o["feasible"] >= o["converged"]

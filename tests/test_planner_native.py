@@ -81,3 +81,20 @@ def test_exported_warm_start_files_identical(tmp_path):
     c = str(tmp_path / "noplan")
     assert export_warmstart.export(c, "parallel", (-6.0, 9.5, 0.0, 0.0), plan=False) == 0
     assert not os.path.exists(os.path.join(c, "xWS.csv")) and "scenario,1" in open(os.path.join(c, "scalars.csv")).read()
+
+
+def test_threaded_batch_equals_single_calls():
+    rng = np.random.default_rng(5)
+    x0s = np.column_stack([rng.uniform(-9, 9, 12), rng.uniform(6.8, 9.3, 12), np.zeros(12)])
+    xF = (0.0, 1.3, math.pi / 2)
+    t0 = time.time()
+    plans = native.plan_batch(x0s, xF, "backwards", workers=4)
+    t_batch = time.time() - t0
+    assert len(plans) == 12 and all(w is not None for w in plans)
+    for i in (0, 5, 11):
+        w = native.plan_warm_start(x0s[i], xF, "backwards")
+        assert w["N"] == plans[i]["N"]
+        for k in ("rx", "ry", "ryaw", "xWS", "uWS"):
+            assert np.array_equal(w[k], plans[i][k])
+    groups = warmstart.group_by_horizon(plans)                          # the batched C-ABI takes one horizon per call
+    assert sum(len(v) for v in groups.values()) == 12 and t_batch < 5.0
