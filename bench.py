@@ -150,7 +150,7 @@ def reference_arm(args):
                                        f"{threads} and fractions of it), DualMultWS + solve timed; "
                                        "model build untimed (as in the reference's `time`)"},
             "e2e": {"value": val, "unit": "traj/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -411,7 +411,7 @@ def gpu_arm(args):
                                       "sample": f"{nprob} problems of the same batch (seed 0), {wall_e:.1f} s wall, DualMultWS + solve"}
         except Exception as e:      # the emulation is optional test infrastructure
             line["cpu_structured"] = {"unavailable": repr(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -488,12 +488,30 @@ def gpu_arm_other(args):
                            "iters_mean": its_all / (B * world * args.steps)},
                 "clocks": sampler.result(),
                 "e2e": {"value": conv_all / e2e_s, "unit": "traj/s", "note": "wall clock of the host-pointer call (H2D + solve + D2H)"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_OUT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the run, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print on file descriptor 1 during the run (NCCL's version banner at
+    # NCCL_DEBUG=VERSION / WARN / INFO, for one) is sent to stderr; emit() writes the line to the original stdout.
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
