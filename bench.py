@@ -129,7 +129,7 @@ def reference_arm(args):
     if rank != 0:
         return
     threads = host_cores()
-    arm = CpuArm(4 * threads, threads)          # one step = 4 problems per host thread
+    arm = CpuArm(args.cpu_sample or 4 * threads, threads)          # one step = 4 problems per host thread (--cpu-sample: tests)
     arm.run()
     threads_used, _ = best_threads(arm, threads)      # (warm-up; all the host threads it can use)
     for _ in range(max(args.warmup - 1, 0)):
@@ -519,6 +519,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="obca")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems per step of the CPU arm (default: 4 per host thread)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the headline): --batch problems PER GPU; strong: --batch problems in total, sharded over the GPUs")
     ap.add_argument("--workload", default="reverse", choices=["reverse", "parallel", "parallel4", "quadcopter", "dist", "fixed"],

@@ -57,3 +57,20 @@ def test_compiled_solver_reproduces_golden(case):
     sub = dict(sc); sub.update(B=1, x0=sc["x0"][i:i + 1], rx=sc["rx"][i:i + 1], ry=sc["ry"][i:i + 1], ryaw=sc["ryaw"][i:i + 1])
     e = kkt_check.reference_kkt_error(sub, 0, out, variant, fix)
     assert e["E0"] < 1e-5
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver's contract for `bench.py --impl reference`: one JSON line on stdout (anything a library prints on fd 1 goes to stderr),
+    with the keys of the reference arm.  Tiny sample (--cpu-sample) so that the test takes seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "traj/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"].startswith("port") and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
